@@ -1,0 +1,98 @@
+/* libtvm_b200 — C ABI of the B200-native backend for Triton VM's Stark::prove() hot path.
+ *
+ * The reference (TritonVM/triton-vm @ 8cd9a0eb) has no FFI for this path; its seams are
+ * Rust-internal.  Each entry point below names the reference function(s) it
+ * replaces.  INTEGRATION.md shows the Rust `extern "C"` declarations and the patched
+ * `Prover::prove` that would call them.
+ *
+ * Conventions
+ *  - Host-buffer entry points take/return CANONICAL field elements (u64 < p, p = 2^64-2^32+1);
+ *    X-field elements are 3 consecutive u64 (c0,c1,c2); digests are 5 u64.
+ *  - `_dev` entry points take device pointers to HBM-resident data in MONTGOMERY form
+ *    (R = 2^64; twenty-first's in-memory representation) and never touch host memory.
+ *  - All functions return 0 on success or a negative TVM_ERR_* code; no exceptions or panics
+ *    cross the ABI.  tvm_last_error() gives a human-readable description.
+ *  - A tvm_ctx is single-caller (like the reference's prove(): one driving thread); several
+ *    contexts may run concurrently on different devices.
+ *  - Caller owns every host pointer, for the duration of the call only.
+ */
+#ifndef TVM_B200_H
+#define TVM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVM_OK 0
+#define TVM_ERR_INVALID_ARG (-1)
+#define TVM_ERR_CUDA (-2)
+#define TVM_ERR_OOM (-3)          /* ProvingError::OutOfMemory, triton-vm/src/error.rs:184-185 */
+#define TVM_ERR_ZK_VIOLATION (-4) /* ProvingError::ZeroKnowledgeViolation, stark.rs:648-663 */
+#define TVM_ERR_DOMAIN (-5)       /* ArithmeticDomainError, error.rs */
+#define TVM_ERR_LDT_PARAMS (-6)   /* LdtParameterError */
+#define TVM_ERR_STATE (-7)
+#define TVM_ERR_UNSUPPORTED (-8)
+
+typedef struct tvm_ctx tvm_ctx;
+
+/* ---- context ------------------------------------------------------------------------- */
+int tvm_ctx_create(tvm_ctx **out, int cuda_device);
+void tvm_ctx_destroy(tvm_ctx *ctx);
+int tvm_ctx_set_stream(tvm_ctx *ctx, void *cuda_stream /* cudaStream_t, NULL = own stream */);
+int tvm_ctx_synchronize(tvm_ctx *ctx);
+const char *tvm_strerror(int code);
+const char *tvm_last_error(const tvm_ctx *ctx);
+uint64_t tvm_launch_count(const tvm_ctx *ctx); /* CUDA kernels launched through this ctx */
+int tvm_device_count(void);
+
+/* ---- field representation ------------------------------------------------------------ */
+int tvm_to_mont_dev(tvm_ctx *ctx, uint64_t *d_data, size_t n);
+int tvm_from_mont_dev(tvm_ctx *ctx, uint64_t *d_data, size_t n);
+
+/* ---- NTT: twenty_first::math::ntt::{ntt,intt} (call sites stark.rs:872,877,997,1002,1176;
+ *      arithmetic_domain.rs:150,188).  ncols independent transforms of 2^log2n elements,
+ *      packed [ncols][n], natural order in and out. ------------------------------------- */
+int tvm_ntt_bfe_dev(tvm_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, uint64_t *d_tmp /* ncols*n */,
+                    unsigned log2n, size_t ncols, int inverse);
+int tvm_ntt_bfe(tvm_ctx *ctx, uint64_t *host_data, unsigned log2n, size_t ncols, int inverse);
+
+/* ---- column LDE: MasterTable::maybe_low_degree_extend_all_columns (master_table.rs:258-322)
+ *      = randomized_column_interpolant (392-403) + ArithmeticDomain::evaluate
+ *      (arithmetic_domain.rs:141-170) for every column.
+ *      d_trace [ncols][n]; d_rand [ncols][num_rand] trace-randomizer coefficients or NULL;
+ *      evaluation domain = offset * <w_{r n}>, r = 2^log2_cosets.
+ *      d_coef  [ncols][2n]  out: interpolant coefficients pre-scaled by offset^j (kept for
+ *                           later stages: OOD evaluation, row re-extrapolation)
+ *      d_out   [ncols][r*n] out: COSET-MAJOR codewords, d_out[q][c*n + k] = value at
+ *                           evaluation-domain index i = c + r*k
+ *      d_tmp   [ncols][r*n] scratch */
+int tvm_lde_bfe_dev(tvm_ctx *ctx, const uint64_t *d_trace, const uint64_t *d_rand, unsigned num_rand,
+                    unsigned log2_trace, unsigned log2_cosets, uint64_t offset_canon, size_t ncols,
+                    uint64_t *d_coef, uint64_t *d_out, uint64_t *d_tmp);
+/* host buffers, canonical; out is [ncols][r*n] in NATURAL evaluation-domain order */
+int tvm_lde_bfe(tvm_ctx *ctx, const uint64_t *trace_colmajor, const uint64_t *rand, unsigned num_rand,
+                unsigned log2_trace, unsigned log2_cosets, uint64_t offset_canon, size_t ncols, uint64_t *out);
+
+/* ---- Tip5 row hashing: MasterTable::hash_all_ldt_domain_rows (master_table.rs:455-465),
+ *      quotient-segment rows (stark.rs:425-446).  Table is column-major, column q at
+ *      d_table + q*col_stride; if log2_cosets > 0 each column is coset-major as produced by
+ *      tvm_lde_bfe_dev.  Digests are written in natural row order, [nrows][5]. ----------- */
+int tvm_tip5_hash_rows_dev(tvm_ctx *ctx, const uint64_t *d_table, size_t col_stride, size_t nrows,
+                           unsigned ncols, unsigned log2_cosets, uint64_t *d_digests);
+int tvm_tip5_hash_rows(tvm_ctx *ctx, const uint64_t *table_colmajor /* [ncols][nrows] */, size_t nrows,
+                       unsigned ncols, uint64_t *digests /* [nrows][5] */);
+/* Tip5::hash_varlen on the host (transcript-side helper; program/claim hashing) */
+int tvm_tip5_hash_varlen(const uint64_t *words, size_t n, uint64_t digest[5]);
+
+/* ---- Merkle tree: MerkleTree::par_new (master_table.rs:449, stark.rs:443, fri.rs:346).
+ *      d_nodes [2*nleaves][5]; leaves must already be at d_nodes[nleaves..2*nleaves);
+ *      node i = hash_pair(node 2i, node 2i+1); root = node 1. -------------------------- */
+int tvm_merkle_build_dev(tvm_ctx *ctx, uint64_t *d_nodes, size_t nleaves);
+int tvm_merkle_build(tvm_ctx *ctx, const uint64_t *leaves /* [nleaves][5] */, size_t nleaves,
+                     uint64_t *nodes_out /* [2*nleaves][5] or NULL */, uint64_t root[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVM_B200_H */

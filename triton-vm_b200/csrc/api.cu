@@ -1,0 +1,329 @@
+// extern "C" boundary of libtvm_b200 (kernel-level entry points).  See include/tvm_b200.h.
+#include "../../include/tvm_b200.h"
+#include "ctx.h"
+#include "launch.h"
+#include <cstring>
+#include <new>
+
+using namespace tvm;
+
+struct tvm_ctx {
+  Ctx c;
+};
+
+namespace tvm {
+
+int translate_exception(Ctx *c) {
+  try {
+    throw;
+  } catch (const CudaError &e) {
+    if (c) {
+      char buf[512];
+      snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d", (int)e.err, cudaGetErrorString(e.err), e.file, e.line);
+      c->last_error = buf;
+    }
+    cudaGetLastError();
+    return e.err == cudaErrorMemoryAllocation ? TVM_ERR_OOM : (e.err == cudaErrorInvalidValue ? TVM_ERR_INVALID_ARG : TVM_ERR_CUDA);
+  } catch (const std::bad_alloc &) {
+    if (c) c->last_error = "host allocation failed";
+    return TVM_ERR_OOM;
+  } catch (const ApiError &e) {
+    if (c) c->last_error = e.msg;
+    return e.code;
+  } catch (...) {
+    if (c) c->last_error = "unknown internal error";
+    return TVM_ERR_CUDA;
+  }
+}
+
+__global__ void to_mont_kernel(u64 *d, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = to_mont(d[i]);
+}
+__global__ void from_mont_kernel(u64 *d, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = from_mont(d[i]);
+}
+// coset-major [c][k] -> natural i = c + r*k, fused with from_mont (host-facing outputs)
+__global__ void coset_to_natural_canon_kernel(const u64 *in, u64 *out, size_t n, int log_r, size_t total) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over ncols * r * n, output order
+  if (idx >= total) return;
+  size_t rn = n << log_r;
+  size_t q = idx / rn, i = idx - q * rn;
+  size_t c = i & (((size_t)1 << log_r) - 1), k = i >> log_r;
+  out[idx] = from_mont(in[q * rn + c * n + k]);
+}
+
+void to_mont_run(Ctx &c, u64 *d, size_t n) {
+  if (!n) return;
+  to_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d, n);
+  c.launches++;
+  TVM_CUDA(cudaGetLastError());
+}
+void from_mont_run(Ctx &c, u64 *d, size_t n) {
+  if (!n) return;
+  from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d, n);
+  c.launches++;
+  TVM_CUDA(cudaGetLastError());
+}
+
+void lde_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned num_rand, unsigned log2_trace,
+             unsigned log2_cosets, u64 offset_mont, size_t ncols, u64 *d_coef, u64 *d_out, u64 *d_tmp) {
+  const size_t n = (size_t)1 << log2_trace;
+  if (num_rand > n) throw ApiError{TVM_ERR_INVALID_ARG, "more trace randomizers than trace rows"};
+  // 1) interpolate on the trace domain (offset 1), fold in zerofier*randomizer, pre-scale by offset^j
+  NttJob inv{};
+  inv.in = d_trace; inv.in_cstride = n;
+  inv.out = d_coef; inv.out_cstride = 2 * n;
+  inv.tmp = d_tmp;
+  inv.log_n = (int)log2_trace; inv.ncols = ncols; inv.inverse = true;
+  inv.has_post = true;
+  inv.post = c.get_pow_tab(offset_mont, (int)log2_trace + 1);
+  inv.rand = d_rand; inv.rand_count = d_rand ? num_rand : 0; inv.rand_pad = inv.rand_count;
+  // the single-pass path has no pass A; force the layout the LDE needs by always using tmp
+  ntt_run(c, inv);
+  // 2) evaluate on the r cosets
+  NttJob fwd{};
+  fwd.in = d_coef; fwd.in_cstride = 2 * n;
+  fwd.out = d_out; fwd.out_cstride = n;  // per (col*r + coset)
+  fwd.tmp = d_tmp;
+  fwd.log_n = (int)log2_trace; fwd.ncols = ncols; fwd.inverse = false;
+  fwd.num_cosets = 1 << log2_cosets;
+  fwd.coset_pre = true;
+  fwd.fold_count = inv.rand_count;
+  ntt_run(c, fwd);
+}
+
+}  // namespace tvm
+
+#define TVM_API_BEGIN(ctx) \
+  Ctx *c__ = (ctx) ? &(ctx)->c : nullptr; \
+  try { \
+    if (c__) TVM_CUDA(cudaSetDevice(c__->device));
+#define TVM_API_END \
+    return TVM_OK; \
+  } catch (...) { \
+    return translate_exception(c__); \
+  }
+
+extern "C" {
+
+int tvm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int tvm_ctx_create(tvm_ctx **out, int device) {
+  if (!out) return TVM_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = tvm_device_count();
+  if (device < 0 || device >= n) return TVM_ERR_CUDA;  // no CPU fallback: fail loudly without a GPU
+  tvm_ctx *ctx = new (std::nothrow) tvm_ctx();
+  if (!ctx) return TVM_ERR_OOM;
+  ctx->c.device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return TVM_ERR_CUDA;
+  }
+  ctx->c.own_stream = true;
+  *out = ctx;
+  return TVM_OK;
+}
+
+void tvm_ctx_destroy(tvm_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  delete ctx;
+}
+
+int tvm_ctx_set_stream(tvm_ctx *ctx, void *stream) {
+  if (!ctx) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  TVM_CUDA(cudaStreamSynchronize(c__->stream));
+  if (c__->own_stream) { cudaStreamDestroy(c__->stream); c__->own_stream = false; }
+  if (stream) c__->stream = (cudaStream_t)stream;
+  else { TVM_CUDA(cudaStreamCreateWithFlags(&c__->stream, cudaStreamNonBlocking)); c__->own_stream = true; }
+  TVM_API_END
+}
+
+int tvm_ctx_synchronize(tvm_ctx *ctx) {
+  if (!ctx) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  TVM_CUDA(cudaStreamSynchronize(c__->stream));
+  TVM_API_END
+}
+
+const char *tvm_strerror(int code) {
+  switch (code) {
+    case TVM_OK: return "ok";
+    case TVM_ERR_INVALID_ARG: return "invalid argument";
+    case TVM_ERR_CUDA: return "CUDA failure (or no CUDA device: this library has no CPU fallback)";
+    case TVM_ERR_OOM: return "out of memory (ProvingError::OutOfMemory)";
+    case TVM_ERR_ZK_VIOLATION: return "out-of-domain point collides with a revealed row (ProvingError::ZeroKnowledgeViolation)";
+    case TVM_ERR_DOMAIN: return "arithmetic domain error";
+    case TVM_ERR_LDT_PARAMS: return "low-degree-test parameter error";
+    case TVM_ERR_STATE: return "entry point called out of order";
+    case TVM_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+const char *tvm_last_error(const tvm_ctx *ctx) { return ctx ? ctx->c.last_error.c_str() : ""; }
+uint64_t tvm_launch_count(const tvm_ctx *ctx) { return ctx ? ctx->c.launches : 0; }
+
+int tvm_to_mont_dev(tvm_ctx *ctx, uint64_t *d, size_t n) {
+  if (!ctx) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  to_mont_run(*c__, (u64 *)d, n);
+  TVM_API_END
+}
+int tvm_from_mont_dev(tvm_ctx *ctx, uint64_t *d, size_t n) {
+  if (!ctx) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  from_mont_run(*c__, (u64 *)d, n);
+  TVM_API_END
+}
+
+int tvm_ntt_bfe_dev(tvm_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, uint64_t *d_tmp, unsigned log2n, size_t ncols, int inverse) {
+  if (!ctx || !d_in || !d_out || log2n > 32) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  if (!ncols) return TVM_OK;
+  NttJob j{};
+  size_t n = (size_t)1 << log2n;
+  j.in = (const u64 *)d_in; j.in_cstride = n; j.out = (u64 *)d_out; j.out_cstride = n; j.tmp = (u64 *)d_tmp;
+  j.log_n = (int)log2n; j.ncols = ncols; j.inverse = inverse != 0;
+  if (log2n > 12 && !d_tmp) throw ApiError{TVM_ERR_INVALID_ARG, "tvm_ntt_bfe_dev: d_tmp required for log2n > 12"};
+  if (log2n > 24) throw ApiError{TVM_ERR_UNSUPPORTED, "tvm_ntt_bfe_dev: log2n > 24 not supported"};
+  ntt_run(*c__, j);
+  TVM_API_END
+}
+
+int tvm_ntt_bfe(tvm_ctx *ctx, uint64_t *host, unsigned log2n, size_t ncols, int inverse) {
+  if (!ctx || !host) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  size_t n = (size_t)1 << log2n, total = n * ncols;
+  if (!total) return TVM_OK;
+  u64 *d = (u64 *)c__->scratch_get(0, total * 8);
+  u64 *t = (u64 *)c__->scratch_get(1, total * 8);
+  u64 *o = (u64 *)c__->scratch_get(2, total * 8);
+  TVM_CUDA(cudaMemcpyAsync(d, host, total * 8, cudaMemcpyHostToDevice, c__->stream));
+  to_mont_run(*c__, d, total);
+  int rc = tvm_ntt_bfe_dev(ctx, d, o, t, log2n, ncols, inverse);
+  if (rc) return rc;
+  from_mont_run(*c__, o, total);
+  TVM_CUDA(cudaMemcpyAsync(host, o, total * 8, cudaMemcpyDeviceToHost, c__->stream));
+  TVM_CUDA(cudaStreamSynchronize(c__->stream));
+  TVM_API_END
+}
+
+int tvm_lde_bfe_dev(tvm_ctx *ctx, const uint64_t *d_trace, const uint64_t *d_rand, unsigned num_rand, unsigned log2_trace,
+                    unsigned log2_cosets, uint64_t offset_canon, size_t ncols, uint64_t *d_coef, uint64_t *d_out, uint64_t *d_tmp) {
+  if (!ctx || !d_trace || !d_coef || !d_out || !d_tmp) return TVM_ERR_INVALID_ARG;
+  if (log2_trace > 24 || log2_cosets > 6 || offset_canon >= P || offset_canon == 0) return TVM_ERR_DOMAIN;
+  TVM_API_BEGIN(ctx)
+  if (!ncols) return TVM_OK;
+  lde_run(*c__, (const u64 *)d_trace, (const u64 *)d_rand, num_rand, log2_trace, log2_cosets, to_mont(offset_canon), ncols,
+          (u64 *)d_coef, (u64 *)d_out, (u64 *)d_tmp);
+  TVM_API_END
+}
+
+int tvm_lde_bfe(tvm_ctx *ctx, const uint64_t *trace, const uint64_t *rand, unsigned num_rand, unsigned log2_trace,
+                unsigned log2_cosets, uint64_t offset_canon, size_t ncols, uint64_t *out) {
+  if (!ctx || !trace || !out) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  size_t n = (size_t)1 << log2_trace, rn = n << log2_cosets;
+  if (!ncols) return TVM_OK;
+  // slot 0: trace + rand ; slot 1: coef ; slot 2: out (coset-major) ; slot 3: tmp, later natural-order output
+  size_t in_words = ncols * n + (rand ? ncols * (size_t)num_rand : 0);
+  u64 *d_in = (u64 *)c__->scratch_get(0, in_words * 8);
+  u64 *d_coef = (u64 *)c__->scratch_get(1, ncols * 2 * n * 8);
+  u64 *d_out = (u64 *)c__->scratch_get(2, ncols * rn * 8);
+  u64 *d_tmp = (u64 *)c__->scratch_get(3, ncols * rn * 8);
+  TVM_CUDA(cudaMemcpyAsync(d_in, trace, ncols * n * 8, cudaMemcpyHostToDevice, c__->stream));
+  u64 *d_rand = nullptr;
+  if (rand && num_rand) {
+    d_rand = d_in + ncols * n;
+    TVM_CUDA(cudaMemcpyAsync(d_rand, rand, ncols * (size_t)num_rand * 8, cudaMemcpyHostToDevice, c__->stream));
+  }
+  to_mont_run(*c__, d_in, in_words);
+  int rc = tvm_lde_bfe_dev(ctx, d_in, d_rand, num_rand, log2_trace, log2_cosets, offset_canon, ncols, d_coef, d_out, d_tmp);
+  if (rc) return rc;
+  size_t total = ncols * rn;
+  coset_to_natural_canon_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c__->stream>>>(d_out, d_tmp, n, (int)log2_cosets, total);
+  c__->launches++;
+  TVM_CUDA(cudaGetLastError());
+  TVM_CUDA(cudaMemcpyAsync(out, d_tmp, total * 8, cudaMemcpyDeviceToHost, c__->stream));
+  TVM_CUDA(cudaStreamSynchronize(c__->stream));
+  TVM_API_END
+}
+
+int tvm_tip5_hash_rows_dev(tvm_ctx *ctx, const uint64_t *d_table, size_t col_stride, size_t nrows, unsigned ncols,
+                           unsigned log2_cosets, uint64_t *d_digests) {
+  if (!ctx || !d_table || !d_digests) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  if (!nrows) return TVM_OK;
+  if (log2_cosets && (nrows & (((size_t)1 << log2_cosets) - 1))) throw ApiError{TVM_ERR_INVALID_ARG, "nrows not a multiple of the coset count"};
+  hash_rows_run(*c__, (const u64 *)d_table, col_stride, nrows, ncols, (int)log2_cosets, (u64 *)d_digests);
+  TVM_API_END
+}
+
+int tvm_tip5_hash_rows(tvm_ctx *ctx, const uint64_t *table, size_t nrows, unsigned ncols, uint64_t *digests) {
+  if (!ctx || !digests || (!table && nrows && ncols)) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  if (!nrows) return TVM_OK;
+  size_t words = nrows * (size_t)ncols;
+  u64 *d = (u64 *)c__->scratch_get(0, (words ? words : 1) * 8);
+  u64 *dg = (u64 *)c__->scratch_get(1, nrows * 5 * 8);
+  if (words) {
+    TVM_CUDA(cudaMemcpyAsync(d, table, words * 8, cudaMemcpyHostToDevice, c__->stream));
+    to_mont_run(*c__, d, words);
+  }
+  hash_rows_run(*c__, d, nrows, nrows, ncols, 0, dg);
+  from_mont_run(*c__, dg, nrows * 5);
+  TVM_CUDA(cudaMemcpyAsync(digests, dg, nrows * 5 * 8, cudaMemcpyDeviceToHost, c__->stream));
+  TVM_CUDA(cudaStreamSynchronize(c__->stream));
+  TVM_API_END
+}
+
+int tvm_tip5_hash_varlen(const uint64_t *words, size_t n, uint64_t digest[5]) {
+  if (!digest || (!words && n)) return TVM_ERR_INVALID_ARG;
+  try {
+    std::vector<u64> w(n);
+    for (size_t i = 0; i < n; i++) {
+      if (words[i] >= P) return TVM_ERR_INVALID_ARG;
+      w[i] = to_mont(words[i]);
+    }
+    u64 d[5];
+    tip5_hash_varlen_host(w.data(), n, d);
+    for (int i = 0; i < 5; i++) digest[i] = from_mont(d[i]);
+    return TVM_OK;
+  } catch (...) {
+    return TVM_ERR_OOM;
+  }
+}
+
+int tvm_merkle_build_dev(tvm_ctx *ctx, uint64_t *d_nodes, size_t nleaves) {
+  if (!ctx || !d_nodes || nleaves == 0 || (nleaves & (nleaves - 1))) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  merkle_run(*c__, (u64 *)d_nodes, nleaves);
+  TVM_API_END
+}
+
+int tvm_merkle_build(tvm_ctx *ctx, const uint64_t *leaves, size_t nleaves, uint64_t *nodes_out, uint64_t root[5]) {
+  if (!ctx || !leaves || !root || nleaves == 0 || (nleaves & (nleaves - 1))) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  u64 *d = (u64 *)c__->scratch_get(0, 2 * nleaves * 5 * 8);
+  TVM_CUDA(cudaMemsetAsync(d, 0, 40, c__->stream));
+  TVM_CUDA(cudaMemcpyAsync(d + 5 * nleaves, leaves, nleaves * 40, cudaMemcpyHostToDevice, c__->stream));
+  to_mont_run(*c__, d + 5 * nleaves, nleaves * 5);
+  merkle_run(*c__, d, nleaves);
+  from_mont_run(*c__, d, 2 * nleaves * 5);
+  if (nodes_out) TVM_CUDA(cudaMemcpyAsync(nodes_out, d, 2 * nleaves * 40, cudaMemcpyDeviceToHost, c__->stream));
+  TVM_CUDA(cudaMemcpyAsync(root, d + 5, 40, cudaMemcpyDeviceToHost, c__->stream));
+  TVM_CUDA(cudaStreamSynchronize(c__->stream));
+  TVM_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// Library context: device, stream, cached power/twiddle tables, scratch memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+#include "field.cuh"
+#include "../../include/tvm_b200.h"
+
+namespace tvm {
+
+
+struct CudaError {
+  cudaError_t err;
+  const char *file;
+  int line;
+};
+
+#define TVM_CUDA(x)                                              \
+  do {                                                           \
+    cudaError_t e__ = (x);                                       \
+    if (e__ != cudaSuccess) throw tvm::CudaError{e__, __FILE__, __LINE__}; \
+  } while (0)
+
+// two-level power table: base^e = lo[e & ((1<<shift)-1)] * hi[e >> shift]
+struct PowTab {
+  const u64 *lo;
+  const u64 *hi;
+  int shift;
+};
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string last_error;
+  unsigned long long launches = 0;  // kernels launched through this context
+
+  // caches
+  std::map<std::pair<int, int>, u64 *> tile_tw;                     // (LT, inverse) -> omega_{2^LT}^(+-e)
+  std::map<std::tuple<u64, int, int>, std::pair<u64 *, u64 *>> pow_tabs;  // (base, log_count, shift)
+  std::vector<void *> owned;
+
+  // scratch arena (grown on demand, reused)
+  DevBuf scratch[4];
+
+  ~Ctx();
+  void *alloc(size_t bytes);  // tracked device allocation (freed with the ctx)
+  void free_tracked(void *p);
+  void *scratch_get(int slot, size_t bytes);
+  const u64 *get_tile_tw(int LT, bool inverse);
+  PowTab get_pow_tab(u64 base_mont, int log_count);  // exponents < 2^log_count
+};
+
+u64 root_of_unity_mont(unsigned log2n);  // twenty-first's PRIMITIVE_ROOTS, Montgomery form
+
+}  // namespace tvm

@@ -1,0 +1,192 @@
+// Tip5 row hashing and Merkle tree construction for sm_100a.
+//
+// Reference behaviour: every low-degree-test-domain row of a master table is hashed with
+// Tip5::hash_varlen (master_table.rs:455-465; quotient segments stark.rs:425-446), the digests
+// are the leaves of MerkleTree::par_new (master_table.rs:443-453): node i = hash_pair(node 2i,
+// node 2i+1), root = node 1, leaf j = node n + j.  FRI codeword trees use the
+// unhashed leaf Digest::from(xfe) = (c0,c1,c2,0,0) (fri.rs:343-347, 927-929).
+//
+// B200 mapping: one thread per row with the 16-lane sponge state resident in registers for the
+// whole absorb loop (all 5 rounds fused; no state traffic), tables stored column-major so that
+// a warp's loads of one column are a single coalesced 256-byte segment.  The S-box lookup table
+// lives in shared memory; the round constants in constant memory (warp-uniform index).
+#include "ctx.h"
+#include "tip5.cuh"
+#include "tip5_constants.inc"
+
+namespace tvm {
+
+const u64 TIP5_ROUND_CONSTANTS_HOST[80] = {TVM_TIP5_RC_MONT};
+const unsigned char TIP5_LOOKUP_HOST[256] = {TVM_TIP5_LUT};
+__constant__ u64 c_tip5_rc[80] = {TVM_TIP5_RC_MONT};
+__constant__ unsigned char c_tip5_lut[256] = {TVM_TIP5_LUT};
+
+struct DevLut {
+  const unsigned char *s;
+  __device__ __forceinline__ unsigned char operator()(unsigned i) const { return s[i]; }
+};
+struct DevRc {
+  __device__ __forceinline__ u64 operator()(int i) const { return c_tip5_rc[i]; }
+};
+
+__device__ __forceinline__ void tip5_perm_dev(u64 (&s)[16], const unsigned char *lut_smem) {
+  tip5_permutation_generic(s, DevLut{lut_smem}, DevRc{});
+}
+
+static constexpr int HASH_THREADS = 128;
+
+// Row index mapping: the LDE tables are coset-major ([col][coset][k], row i = coset + r*k).
+// `log_r` = log2(#cosets); log_r = 0 means plain row-major-in-index ([col][i]).
+struct HashRowsParams {
+  const u64 *table;     // column q at table + q*col_stride
+  size_t col_stride;
+  size_t nrows;         // total rows (all cosets)
+  unsigned ncols;
+  int log_r;
+  u64 *digests;         // [nrows][5], natural row order
+};
+
+__global__ void __launch_bounds__(HASH_THREADS) tip5_hash_rows_kernel(HashRowsParams p) {
+  __shared__ unsigned char lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
+  __syncthreads();
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // memory-order index within a column
+  if (m >= p.nrows) return;
+  // memory index m = coset * (nrows >> log_r) + k  <->  row i = coset + (k << log_r)
+  size_t per = p.nrows >> p.log_r;
+  size_t coset = m / per, k = m - coset * per;
+  size_t row = coset + (k << p.log_r);
+  const u64 *base = p.table + m;
+  u64 s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = 0;
+  unsigned c = 0;
+  for (; c + 10 <= p.ncols; c += 10) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) s[i] = base[(size_t)(c + i) * p.col_stride];
+    tip5_perm_dev(s, lut);
+  }
+  unsigned rem = p.ncols - c;
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    u64 v = 0;
+    if ((unsigned)i < rem) v = base[(size_t)(c + i) * p.col_stride];
+    else if ((unsigned)i == rem) v = MONT_ONE;
+    s[i] = v;
+  }
+  tip5_perm_dev(s, lut);
+  u64 *d = p.digests + row * 5;
+#pragma unroll
+  for (int i = 0; i < 5; i++) d[i] = s[i];
+}
+
+// nodes: [2*nleaves][5]; computes nodes[lo .. lo+count) from their children.
+__global__ void __launch_bounds__(HASH_THREADS) merkle_level_kernel(u64 *nodes, size_t lo, size_t count) {
+  __shared__ unsigned char lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
+  __syncthreads();
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  size_t i = lo + t;
+  const u64 *ch = nodes + 10 * i;  // children 2i, 2i+1 are adjacent: 10 words
+  u64 s[16];
+#pragma unroll
+  for (int k = 0; k < 10; k++) s[k] = ch[k];
+#pragma unroll
+  for (int k = 10; k < 16; k++) s[k] = MONT_ONE;
+  tip5_perm_dev(s, lut);
+#pragma unroll
+  for (int k = 0; k < 5; k++) nodes[5 * i + k] = s[k];
+}
+
+// The last levels (<= 2*HASH_THREADS nodes wide) in one CTA.
+__global__ void __launch_bounds__(HASH_THREADS) merkle_top_kernel(u64 *nodes, size_t top_width) {
+  __shared__ unsigned char lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
+  __syncthreads();
+  for (size_t w = top_width; w >= 1; w >>= 1) {
+    for (size_t t = threadIdx.x; t < w; t += blockDim.x) {
+      size_t i = w + t;
+      const u64 *ch = nodes + 10 * i;
+      u64 s[16];
+#pragma unroll
+      for (int k = 0; k < 10; k++) s[k] = ch[k];
+#pragma unroll
+      for (int k = 10; k < 16; k++) s[k] = MONT_ONE;
+      tip5_perm_dev(s, lut);
+#pragma unroll
+      for (int k = 0; k < 5; k++) nodes[5 * i + k] = s[k];
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+// leaves of an X-field codeword tree: Digest::from(xfe) = (c0, c1, c2, 0, 0).
+// codeword is planar: coordinate d of element i at cw[d*stride + i].
+__global__ void xfe_leaves_kernel(const u64 *cw, size_t stride, size_t n, u64 *leaves) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 *d = leaves + 5 * i;
+  d[0] = cw[i]; d[1] = cw[stride + i]; d[2] = cw[2 * stride + i]; d[3] = 0; d[4] = 0;
+}
+
+void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, unsigned ncols, int log_r, u64 *digests) {
+  HashRowsParams p{table, col_stride, nrows, ncols, log_r, digests};
+  unsigned grid = (unsigned)((nrows + HASH_THREADS - 1) / HASH_THREADS);
+  tip5_hash_rows_kernel<<<grid, HASH_THREADS, 0, c.stream>>>(p);
+  c.launches++;
+  TVM_CUDA(cudaGetLastError());
+}
+
+// leaves already stored at nodes[nleaves .. 2*nleaves)
+void merkle_run(Ctx &c, u64 *nodes, size_t nleaves) {
+  size_t w = nleaves / 2;
+  const size_t TOP = 64;
+  for (; w > TOP; w >>= 1) {
+    unsigned grid = (unsigned)((w + HASH_THREADS - 1) / HASH_THREADS);
+    merkle_level_kernel<<<grid, HASH_THREADS, 0, c.stream>>>(nodes, w, w);
+    c.launches++;
+  }
+  if (w >= 1) {
+    merkle_top_kernel<<<1, HASH_THREADS, 0, c.stream>>>(nodes, w);
+    c.launches++;
+  }
+  TVM_CUDA(cudaGetLastError());
+}
+
+void xfe_leaves_run(Ctx &c, const u64 *cw, size_t stride, size_t n, u64 *leaves) {
+  xfe_leaves_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(cw, stride, n, leaves);
+  c.launches++;
+  TVM_CUDA(cudaGetLastError());
+}
+
+// ---- host Tip5 (transcript) -------------------------------------------------------------
+struct HostLutF { unsigned char operator()(unsigned i) const { return TIP5_LOOKUP_HOST[i]; } };
+struct HostRcF { u64 operator()(int i) const { return TIP5_ROUND_CONSTANTS_HOST[i]; } };
+
+void tip5_permutation_host(u64 s[16]) {
+  u64(&st)[16] = *reinterpret_cast<u64(*)[16]>(s);
+  tip5_permutation_generic(st, HostLutF{}, HostRcF{});
+}
+void tip5_hash_varlen_host(const u64 *w, size_t n, u64 digest[5]) {
+  u64 s[16] = {0};
+  size_t full = n / 10;
+  for (size_t i = 0; i < full; i++) {
+    for (int k = 0; k < 10; k++) s[k] = w[10 * i + k];
+    tip5_permutation_host(s);
+  }
+  size_t rem = n - 10 * full;
+  for (size_t k = 0; k < 10; k++) s[k] = k < rem ? w[10 * full + k] : (k == rem ? MONT_ONE : 0);
+  tip5_permutation_host(s);
+  for (int k = 0; k < 5; k++) digest[k] = s[k];
+}
+void tip5_hash_pair_host(const u64 l[5], const u64 r[5], u64 digest[5]) {
+  u64 s[16];
+  for (int k = 0; k < 5; k++) { s[k] = l[k]; s[5 + k] = r[k]; }
+  for (int k = 10; k < 16; k++) s[k] = MONT_ONE;
+  tip5_permutation_host(s);
+  for (int k = 0; k < 5; k++) digest[k] = s[k];
+}
+
+}  // namespace tvm

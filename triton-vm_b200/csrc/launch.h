@@ -1,0 +1,44 @@
+// Host-side launch interfaces shared between translation units.
+#pragma once
+#include "ctx.h"
+#include "tip5.cuh"
+
+namespace tvm {
+
+struct ApiError {
+  int code;
+  std::string msg;
+};
+
+struct NttJob {
+  const u64 *in;
+  size_t in_cstride;
+  u64 *out;
+  size_t out_cstride;   // per (col*num_cosets + coset)
+  u64 *tmp;             // ncols*num_cosets*n words, distinct from out
+  int log_n;
+  size_t ncols;
+  bool inverse;
+  // coset mode (forward only): evaluate on num_cosets cosets; pre table = w_{num_cosets * n}
+  int num_cosets = 1;
+  bool coset_pre = false;
+  unsigned fold_count = 0;
+  // output post-processing
+  u64 post_mul = MONT_ONE;
+  bool has_post = false;
+  PowTab post{};
+  const u64 *rand = nullptr;
+  unsigned rand_count = 0, rand_pad = 0;
+};
+
+void ntt_run(Ctx &c, const NttJob &job);
+void lde_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned num_rand, unsigned log2_trace,
+             unsigned log2_cosets, u64 offset_mont, size_t ncols, u64 *d_coef, u64 *d_out, u64 *d_tmp);
+void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, unsigned ncols, int log_r, u64 *digests);
+void merkle_run(Ctx &c, u64 *nodes, size_t nleaves);
+void xfe_leaves_run(Ctx &c, const u64 *cw, size_t stride, size_t n, u64 *leaves);
+void to_mont_run(Ctx &c, u64 *d, size_t n);
+void from_mont_run(Ctx &c, u64 *d, size_t n);
+int translate_exception(Ctx *c);
+
+}  // namespace tvm

@@ -1,0 +1,200 @@
+"""ctypes binding of libtvm_b200.so (include/tvm_b200.h) — the Python-side mirror used by the
+tests, bench.py and the multi-GPU driver.  PyTorch is used only for device memory, streams and
+torch.distributed plumbing; all arithmetic happens in the CUDA library.
+
+There is NO CPU fallback: if the library or a CUDA device is missing, creating a `Backend`
+raises `TvmError`.
+"""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # triton-vm_b200/
+LIB_PATH = os.path.join(_PKG, "lib", "libtvm_b200.so")
+P = (1 << 64) - (1 << 32) + 1
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_vp = ctypes.c_void_p
+
+
+class TvmError(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        super().__init__(f"libtvm_b200 error {code}: {msg}")
+
+
+def build(force=False, verbose=False):
+    """Compile libtvm_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    args = ["make", "-C", _PKG, "-j8", "lib/libtvm_b200.so"]
+    if force:
+        args.insert(1, "-B")
+    r = subprocess.run(args, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libtvm_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stdout[-2000:])
+    return LIB_PATH
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol declared in include/tvm_b200.h
+_SIGNATURES = {
+    "tvm_ctx_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int]),
+    "tvm_ctx_destroy": (None, [_vp]),
+    "tvm_ctx_set_stream": (ctypes.c_int, [_vp, _vp]),
+    "tvm_ctx_synchronize": (ctypes.c_int, [_vp]),
+    "tvm_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "tvm_last_error": (ctypes.c_char_p, [_vp]),
+    "tvm_launch_count": (ctypes.c_uint64, [_vp]),
+    "tvm_device_count": (ctypes.c_int, []),
+    "tvm_to_mont_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "tvm_from_mont_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "tvm_ntt_bfe_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_uint, ctypes.c_size_t, ctypes.c_int]),
+    "tvm_ntt_bfe": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint, ctypes.c_size_t, ctypes.c_int]),
+    "tvm_lde_bfe_dev": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint64,
+                                       ctypes.c_size_t, _vp, _vp, _vp]),
+    "tvm_lde_bfe": (ctypes.c_int, [_vp, _u64p, _u64p, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint64,
+                                   ctypes.c_size_t, _u64p]),
+    "tvm_tip5_hash_rows_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, ctypes.c_uint, _vp]),
+    "tvm_tip5_hash_rows": (ctypes.c_int, [_vp, _u64p, ctypes.c_size_t, ctypes.c_uint, _u64p]),
+    "tvm_tip5_hash_varlen": (ctypes.c_int, [_u64p, ctypes.c_size_t, _u64p]),
+    "tvm_merkle_build_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "tvm_merkle_build": (ctypes.c_int, [_vp, _u64p, ctypes.c_size_t, _u64p, _u64p]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TvmError(-2, f"{LIB_PATH} not built (run __graft_entry__.build()); no CPU fallback exists")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            f = getattr(l, name)  # AttributeError if the library does not export a declared symbol
+            f.restype = res
+            f.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _np_u64(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a, a.ctypes.data_as(_u64p)
+
+
+def hash_varlen(words):
+    """Tip5::hash_varlen on the host (no GPU needed)."""
+    w, wp = _np_u64(np.array(words, dtype=np.uint64))
+    d = np.zeros(5, dtype=np.uint64)
+    rc = lib().tvm_tip5_hash_varlen(wp, w.size, d.ctypes.data_as(_u64p))
+    if rc:
+        raise TvmError(rc, lib().tvm_strerror(rc).decode())
+    return [int(v) for v in d]
+
+
+class Backend:
+    """One context = one GPU = one driving thread (mirrors Prover::prove being single-caller)."""
+
+    def __init__(self, device=0):
+        self._l = lib()
+        h = _vp()
+        rc = self._l.tvm_ctx_create(ctypes.byref(h), device)
+        if rc:
+            raise TvmError(rc, self._l.tvm_strerror(rc).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.tvm_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            raise TvmError(rc, self._l.tvm_strerror(rc).decode() + " | " + self._l.tvm_last_error(self._h).decode())
+
+    @property
+    def launches(self):
+        return int(self._l.tvm_launch_count(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(self._l.tvm_ctx_set_stream(self._h, _vp(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._chk(self._l.tvm_ctx_synchronize(self._h))
+
+    # ---- host-buffer (canonical) entry points ------------------------------------------
+    def ntt(self, x, inverse=False):
+        """x: [ncols, n] or [n] canonical uint64 -> same shape"""
+        a = np.array(x, dtype=np.uint64, copy=True)
+        shape = a.shape
+        a2 = np.ascontiguousarray(a.reshape(-1, shape[-1]))
+        n = a2.shape[1]
+        self._chk(self._l.tvm_ntt_bfe(self._h, a2.ctypes.data_as(_u64p), n.bit_length() - 1, a2.shape[0], int(inverse)))
+        return a2.reshape(shape)
+
+    def lde(self, trace, rand, log2_cosets, offset):
+        """trace [ncols, n]; rand [ncols, h] or None -> [ncols, n << log2_cosets] natural order"""
+        t, tp = _np_u64(trace)
+        ncols, n = t.shape
+        if rand is not None:
+            r, rp = _np_u64(rand)
+            h = r.shape[1]
+        else:
+            rp, h = None, 0
+        out = np.empty((ncols, n << log2_cosets), dtype=np.uint64)
+        self._chk(self._l.tvm_lde_bfe(self._h, tp, rp, h, n.bit_length() - 1, log2_cosets, offset, ncols,
+                                      out.ctypes.data_as(_u64p)))
+        return out
+
+    def hash_rows(self, table_colmajor):
+        """table [ncols, nrows] -> digests [nrows, 5]"""
+        t, tp = _np_u64(table_colmajor)
+        ncols, nrows = t.shape
+        d = np.empty((nrows, 5), dtype=np.uint64)
+        self._chk(self._l.tvm_tip5_hash_rows(self._h, tp, nrows, ncols, d.ctypes.data_as(_u64p)))
+        return d
+
+    def merkle(self, leaves, want_nodes=False):
+        l, lp = _np_u64(leaves)
+        n = l.shape[0]
+        root = np.empty(5, dtype=np.uint64)
+        nodes = np.empty((2 * n, 5), dtype=np.uint64) if want_nodes else None
+        self._chk(self._l.tvm_merkle_build(self._h, lp, n, nodes.ctypes.data_as(_u64p) if want_nodes else None,
+                                           root.ctypes.data_as(_u64p)))
+        return (root, nodes) if want_nodes else root
+
+    # ---- device-pointer entry points (torch tensors, int64 view of u64, Montgomery) -------
+    @staticmethod
+    def _dp(t):
+        return _vp(t.data_ptr()) if t is not None else None
+
+    def to_mont_(self, t):
+        self._chk(self._l.tvm_to_mont_dev(self._h, self._dp(t), t.numel()))
+        return t
+
+    def from_mont_(self, t):
+        self._chk(self._l.tvm_from_mont_dev(self._h, self._dp(t), t.numel()))
+        return t
+
+    def ntt_dev(self, d_in, d_out, d_tmp, log2n, ncols, inverse=False):
+        self._chk(self._l.tvm_ntt_bfe_dev(self._h, self._dp(d_in), self._dp(d_out), self._dp(d_tmp), log2n, ncols, int(inverse)))
+
+    def lde_dev(self, d_trace, d_rand, num_rand, log2_trace, log2_cosets, offset, ncols, d_coef, d_out, d_tmp):
+        self._chk(self._l.tvm_lde_bfe_dev(self._h, self._dp(d_trace), self._dp(d_rand), num_rand, log2_trace, log2_cosets,
+                                          offset, ncols, self._dp(d_coef), self._dp(d_out), self._dp(d_tmp)))
+
+    def hash_rows_dev(self, d_table, col_stride, nrows, ncols, log2_cosets, d_digests):
+        self._chk(self._l.tvm_tip5_hash_rows_dev(self._h, self._dp(d_table), col_stride, nrows, ncols, log2_cosets,
+                                                 self._dp(d_digests)))
+
+    def merkle_dev(self, d_nodes, nleaves):
+        self._chk(self._l.tvm_merkle_build_dev(self._h, self._dp(d_nodes), nleaves))
