@@ -92,6 +92,23 @@ int tvm_merkle_build_dev(tvm_ctx *ctx, uint64_t *d_nodes, size_t nleaves);
 int tvm_merkle_build(tvm_ctx *ctx, const uint64_t *leaves /* [nleaves][5] */, size_t nleaves,
                      uint64_t *nodes_out /* [2*nleaves][5] or NULL */, uint64_t root[5]);
 
+/* ---- AIR quotient codeword: all_quotients_combined (master_table.rs:1264-1363) with the
+ *      build-time generated constraint evaluators (constraint-builder/src/codegen.rs:59-269)
+ *      and the four zerofier inverses (master_table.rs:1194-1252).
+ *      d_main [>=379 columns][r*n], d_aux [>=270 B-field columns = 90 X-field columns x 3][r*n],
+ *      both coset-major LDE tables on the quotient domain offset*<w_{rn}>;
+ *      challenges: 63 X-field elements, weights: 604 X-field elements (host, canonical);
+ *      d_out: 3 planes (coordinate d at d_out + d*out_stride) of r*n words, coset-major order:
+ *      d_out[c*n + k] = quotient value at domain index i = c + r*k. ----------------------- */
+#define TVM_NUM_MAIN_COLUMNS 379
+#define TVM_NUM_AUX_COLUMNS 91
+#define TVM_NUM_CHALLENGES 63
+#define TVM_NUM_CONSTRAINTS 604
+int tvm_air_quotient_dev(tvm_ctx *ctx, const uint64_t *d_main, size_t main_stride, const uint64_t *d_aux,
+                         size_t aux_stride, const uint64_t *challenges, const uint64_t *weights,
+                         unsigned log2_trace, unsigned log2_cosets, uint64_t offset_canon,
+                         uint64_t *d_out, size_t out_stride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,3 +118,57 @@ def test_device_pipeline_lde_hash_merkle(backend):
     assert np.array_equal(nodes[rn:], digests)
     assert np.array_equal(nodes[1], want[1])
     assert backend.launches > 0
+
+
+def test_air_quotient_matches_python_evaluator(backend):
+    """Generated quotient kernels vs node-by-node evaluation of the same circuits in Python
+    (which is pinned to the reference's golden fingerprint in tests/test_air.py)."""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "triton-vm_b200"))
+    from airgen.build import CATEGORIES, build_air
+    from airgen.evaluate import evaluate_constraints
+    air = build_air()
+    rng = np.random.default_rng(77)
+    log_n, log_r = 4, 3
+    n, rn = 1 << log_n, 1 << (log_n + log_r)
+    r = 1 << log_r
+    main = rand_bfes(rng, (379, rn))          # memory order: [col][coset*n + k]
+    aux = rand_bfes(rng, (270, rn))
+    ch = rand_bfes(rng, (63, 3))
+    w = rand_bfes(rng, (604, 3))
+    dev = torch.device("cuda:0")
+    d_main = torch.from_numpy(main.view(np.int64)).to(dev)
+    d_aux = torch.from_numpy(aux.view(np.int64)).to(dev)
+    backend.to_mont_(d_main); backend.to_mont_(d_aux)
+    d_out = torch.zeros((3, rn), dtype=torch.int64, device=dev)
+    backend.air_quotient_dev(d_main, rn, d_aux, rn, ch, w, log_n, log_r, 7, d_out, rn)
+    backend.from_mont_(d_out)
+    backend.synchronize()
+    got = d_out.cpu().numpy().view(np.uint64)
+
+    P = F.P
+    wn = F.primitive_root_of_unity(n)
+    wrn = F.primitive_root_of_unity(rn)
+    wn_inv = F.inv(wn)
+    chal = [tuple(int(v) for v in row) for row in ch]
+    weights = [tuple(int(v) for v in row) for row in w]
+    for m in list(range(0, rn, 7)) + [n - 1, rn - 1]:
+        c, k = m // n, m % n
+        m_next = c * n + (k + 1) % n
+        x = 7 * pow(wrn, c + r * k, P) % P
+        cm = [int(v) for v in main[:, m]]; nm = [int(v) for v in main[:, m_next]]
+        ca = [tuple(int(v) for v in aux[3 * q:3 * q + 3, m]) for q in range(90)]
+        na = [tuple(int(v) for v in aux[3 * q:3 * q + 3, m_next]) for q in range(90)]
+        zinv = {"init": F.inv((x - 1) % P), "cons": F.inv((pow(x, n, P) - 1) % P),
+                "tran": (x - wn_inv) * F.inv((pow(x, n, P) - 1) % P) % P, "term": F.inv((x - wn_inv) % P)}
+        acc, off = (0, 0, 0), 0
+        for cat in CATEGORIES:
+            vals = evaluate_constraints(air.constraints[cat], cm, ca, nm, na, chal)
+            s = (0, 0, 0)
+            for j, v in enumerate(vals):
+                s = F.xadd(s, F.xmul(weights[off + j], v))
+            off += len(vals)
+            acc = F.xadd(acc, F.xscale(s, zinv[cat]))
+        assert tuple(int(got[d, m]) for d in range(3)) == acc, m

@@ -45,6 +45,14 @@ def main():
         ms = timeit(lambda: b.hash_rows_dev(tab, nrows, nrows, ncols, 3, dg), it=3)
         perms = nrows * (ncols // 10 + 1)
         res[f"hash_rows_{ncols}x2^{log2r}"] = dict(ms=ms, mperm_s=perms / ms / 1e3, gbs_alg=(8 * ncols + 40) * nrows / ms / 1e6)
+    # AIR quotient
+    for log_n in (17,):
+        log_r = 3; rn = 1 << (log_n + log_r)
+        main = rnd(379, rn) % (2**61); aux = rnd(270, rn) % (2**61)
+        out = torch.zeros((3, rn), dtype=torch.int64, device=dev)
+        ch = np.arange(1, 190, dtype=np.uint64); w = np.arange(1, 1813, dtype=np.uint64)
+        ms = timeit(lambda: b.air_quotient_dev(main, rn, aux, rn, ch, w, log_n, log_r, 7, out, rn), warm=1, it=3)
+        res[f"air_quotient_2^{log_n+log_r}rows"] = dict(ms=ms, mrows_s=rn / ms / 1e3, gbs_alg=(5216 + 24) * rn / ms / 1e6)
     # merkle
     nl = 1 << 22
     nodes = rnd(2 * nl, 5)

@@ -326,4 +326,22 @@ int tvm_merkle_build(tvm_ctx *ctx, const uint64_t *leaves, size_t nleaves, uint6
   TVM_API_END
 }
 
+int tvm_air_quotient_dev(tvm_ctx *ctx, const uint64_t *d_main, size_t main_stride, const uint64_t *d_aux, size_t aux_stride,
+                         const uint64_t *challenges, const uint64_t *weights, unsigned log2_trace, unsigned log2_cosets,
+                         uint64_t offset_canon, uint64_t *d_out, size_t out_stride) {
+  if (!ctx || !d_main || !d_aux || !challenges || !weights || !d_out) return TVM_ERR_INVALID_ARG;
+  if (offset_canon == 0 || offset_canon >= P || log2_trace + log2_cosets > 32) return TVM_ERR_DOMAIN;
+  TVM_API_BEGIN(ctx)
+  const size_t nc = 3 * TVM_NUM_CHALLENGES, nw = 3 * TVM_NUM_CONSTRAINTS;
+  std::vector<u64> h(nc + nw);
+  for (size_t i = 0; i < nc; i++) h[i] = to_mont(challenges[i] % P);
+  for (size_t i = 0; i < nw; i++) h[nc + i] = to_mont(weights[i] % P);
+  u64 *d = (u64 *)c__->scratch_get(3, (nc + nw) * 8);
+  TVM_CUDA(cudaMemcpyAsync(d, h.data(), (nc + nw) * 8, cudaMemcpyHostToDevice, c__->stream));
+  TVM_CUDA(cudaStreamSynchronize(c__->stream));  // h is a stack-owned staging buffer
+  air_quotient_run(*c__, (const u64 *)d_main, main_stride, (const u64 *)d_aux, aux_stride, d, d + nc, log2_trace, log2_cosets,
+                   to_mont(offset_canon), (u64 *)d_out, out_stride);
+  TVM_API_END
+}
+
 }  // extern "C"

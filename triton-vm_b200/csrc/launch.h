@@ -39,6 +39,9 @@ void merkle_run(Ctx &c, u64 *nodes, size_t nleaves);
 void xfe_leaves_run(Ctx &c, const u64 *cw, size_t stride, size_t n, u64 *leaves);
 void to_mont_run(Ctx &c, u64 *d, size_t n);
 void from_mont_run(Ctx &c, u64 *d, size_t n);
+void air_quotient_run(Ctx &c, const u64 *d_main, size_t main_stride, const u64 *d_aux, size_t aux_stride,
+                      const u64 *d_challenges, const u64 *d_weights, unsigned log_n, unsigned log_r,
+                      u64 offset_mont, u64 *d_out, size_t out_stride);
 int translate_exception(Ctx *c);
 
 }  // namespace tvm

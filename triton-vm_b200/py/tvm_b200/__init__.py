@@ -62,6 +62,8 @@ _SIGNATURES = {
     "tvm_tip5_hash_varlen": (ctypes.c_int, [_u64p, ctypes.c_size_t, _u64p]),
     "tvm_merkle_build_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "tvm_merkle_build": (ctypes.c_int, [_vp, _u64p, ctypes.c_size_t, _u64p, _u64p]),
+    "tvm_air_quotient_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _u64p, _u64p, ctypes.c_uint,
+                                            ctypes.c_uint, ctypes.c_uint64, _vp, ctypes.c_size_t]),
 }
 
 
@@ -195,6 +197,14 @@ class Backend:
     def hash_rows_dev(self, d_table, col_stride, nrows, ncols, log2_cosets, d_digests):
         self._chk(self._l.tvm_tip5_hash_rows_dev(self._h, self._dp(d_table), col_stride, nrows, ncols, log2_cosets,
                                                  self._dp(d_digests)))
+
+    def air_quotient_dev(self, d_main, main_stride, d_aux, aux_stride, challenges, weights, log2_trace, log2_cosets,
+                         offset, d_out, out_stride):
+        ch, chp = _np_u64(np.asarray(challenges, dtype=np.uint64).reshape(-1))
+        w, wp = _np_u64(np.asarray(weights, dtype=np.uint64).reshape(-1))
+        assert ch.size == 189 and w.size == 1812
+        self._chk(self._l.tvm_air_quotient_dev(self._h, self._dp(d_main), main_stride, self._dp(d_aux), aux_stride, chp, wp,
+                                               log2_trace, log2_cosets, offset, self._dp(d_out), out_stride))
 
     def merkle_dev(self, d_nodes, nleaves):
         self._chk(self._l.tvm_merkle_build_dev(self._h, self._dp(d_nodes), nleaves))
