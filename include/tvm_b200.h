@@ -109,6 +109,47 @@ int tvm_air_quotient_dev(tvm_ctx *ctx, const uint64_t *d_main, size_t main_strid
                          unsigned log2_trace, unsigned log2_cosets, uint64_t offset_canon,
                          uint64_t *d_out, size_t out_stride);
 
+/* ---- STARK parameters: Stark::{ldt,fri,max_degree,randomized_trace_len,num_trace_randomizers}
+ *      (stark.rs:1885-2089), ProverDomains::derive (263-286), FriParameters (fri.rs:799-924),
+ *      ReedSolomonCode (low_degree_test/mod.rs:215-300).  Pure function, no GPU needed. ------- */
+typedef struct tvm_params {
+  uint32_t security_level;            /* Stark::default(): 160 */
+  uint32_t log2_ldt_expansion_factor; /* Stark::default(): 2   */
+  uint32_t ldt_choice;                /* 1 = FRI (LdtChoice::Fri); 0 (auto) and 2 (STIR) -> TVM_ERR_UNSUPPORTED for now */
+} tvm_params;
+typedef struct tvm_domains {
+  uint64_t padded_height, num_trace_randomizers, randomized_trace_len, trace_len, quotient_len, ldt_len;
+  uint64_t ldt_offset;                /* canonical; trace and randomized-trace domains have offset 1 */
+  uint64_t num_collinearity_checks, fri_num_rounds, fri_last_round_max_degree;
+  uint64_t num_quotient_randomizer_coefficients; /* (h + 1) * 5 X-field coefficients, stark.rs:1320-1322 */
+} tvm_domains;
+int tvm_derive_domains(const tvm_params *params, uint64_t padded_height, tvm_domains *out);
+
+/* ---- Stark::prove (stark.rs:1845-1851 -> Prover::prove 331-719) for already generated traces.
+ *      claim: program digest (5 words), version, public input / output (proof.rs:68-88).
+ *      main_trace   [379][trace_len]  column-major, canonical (MasterMainTable after pad(),
+ *                                      master_table.rs:881-983, trace_table is column-major: 888)
+ *      main_rand    [379][h]          trace-randomizer coefficients per column (master_table.rs:423-434)
+ *      aux_cb       called once with the 63 challenges (canonical X-field, challenges.rs:88-135); must
+ *                   fill aux_trace [91][trace_len][3] (MasterMainTable::extend, 1006-1075, incl. the
+ *                   batch-randomizer column 90) and aux_rand [91][h][3]
+ *      quot_rand    [(h+1)*5][3]      quotient-segment randomizer (stark.rs:1316-1322)
+ *      proof_out    receives Proof.0 (Vec<BFieldElement>, canonical); *proof_len in: capacity, out: needed
+ *                   length (TVM_ERR_INVALID_ARG with *proof_len set if the capacity is too small).
+ *      All randomness is the caller's: the backend is a deterministic function of its inputs. --- */
+typedef int (*tvm_aux_callback)(void *user, const uint64_t *challenges /*[63][3]*/, uint64_t *aux_trace, uint64_t *aux_rand);
+typedef struct tvm_claim {
+  uint64_t program_digest[5];
+  uint32_t version;
+  const uint64_t *input; size_t num_input;
+  const uint64_t *output; size_t num_output;
+} tvm_claim;
+int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height,
+              const uint64_t *main_trace, const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user,
+              const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len);
+/* device time per stage of the last tvm_prove on this ctx, reference profiler labels; returns #stages */
+int tvm_last_prove_timings(const tvm_ctx *ctx, const char **names /*[16]*/, float *ms /*[16]*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -305,3 +305,105 @@ void orc_lde_table(const u64 *trace_colmajor, unsigned log2_trace, size_t ncols,
     orc_lde_column(trace_colmajor + c * n, log2_trace, randomizers ? randomizers + c * num_rand : NULL,
                    randomizers ? num_rand : 0, eval_offset, log2_eval, out_colmajor + c * m, NULL);
 }
+
+/* ---- AIR quotient (master_table.rs:1194-1363) ------------------------------------------- */
+void orc_air_eval_init(const u64 *mc, const u64 *ac, const u64 *mn, const u64 *an, const u64 *ch, u64 *out);
+void orc_air_eval_cons(const u64 *mc, const u64 *ac, const u64 *mn, const u64 *an, const u64 *ch, u64 *out);
+void orc_air_eval_tran(const u64 *mc, const u64 *ac, const u64 *mn, const u64 *an, const u64 *ch, u64 *out);
+void orc_air_eval_term(const u64 *mc, const u64 *ac, const u64 *mn, const u64 *an, const u64 *ch, u64 *out);
+extern const int ORC_AIR_NUM_CONSTRAINTS[4];
+
+static void batch_inverse(u64 *x, size_t n) {
+  if (!n) return;
+  u64 *pre = (u64 *)malloc(n * sizeof(u64));
+  u64 acc = MONT_ONE;
+  for (size_t i = 0; i < n; i++) { pre[i] = acc; acc = fmul(acc, x[i]); }
+  acc = orc_inv(acc);
+  for (size_t i = n; i-- > 0;) { u64 t = fmul(acc, pre[i]); acc = fmul(acc, x[i]); x[i] = t; }
+  free(pre);
+}
+void orc_batch_inverse(u64 *x, size_t n) { batch_inverse(x, n); }
+
+/* main: column-major [nmain][N] in natural domain order; aux: [3*naux][N] (X-field columns planar).
+ * Row i's successor is row (i + unit_distance) mod N.  weights: 604 X-field; out: [N][3]. */
+void orc_air_quotient(const u64 *main, size_t nmain, const u64 *aux, size_t naux3, size_t N, unsigned log2_trace,
+                      u64 domain_offset, const u64 *ch, const u64 *w, u64 *out) {
+  unsigned log2N = 0; while (((size_t)1 << log2N) < N) log2N++;
+  size_t n = (size_t)1 << log2_trace, unit = N / n;
+  u64 g = orc_root_of_unity(log2N), wn_inv = orc_inv(orc_root_of_unity(log2_trace));
+  u64 *zi = (u64 *)malloc(4 * N * sizeof(u64));
+  u64 *z_init = zi, *z_cons = zi + N, *z_tran = zi + 2 * N, *z_term = zi + 3 * N;
+  u64 x = domain_offset;
+  for (size_t i = 0; i < N; i++) {
+    z_init[i] = fsub(x, MONT_ONE);
+    z_cons[i] = fsub(orc_pow(x, n), MONT_ONE);
+    z_term[i] = fsub(x, wn_inv);
+    x = fmul(x, g);
+  }
+  batch_inverse(z_init, N); batch_inverse(z_cons, N); batch_inverse(z_term, N);
+  x = domain_offset;
+  for (size_t i = 0; i < N; i++) { z_tran[i] = fmul(fsub(x, wn_inv), z_cons[i]); x = fmul(x, g); }
+  const int nc[4] = {ORC_AIR_NUM_CONSTRAINTS[0], ORC_AIR_NUM_CONSTRAINTS[1], ORC_AIR_NUM_CONSTRAINTS[2], ORC_AIR_NUM_CONSTRAINTS[3]};
+#pragma omp parallel
+  {
+    u64 *mc = (u64 *)malloc((2 * nmain + 2 * naux3) * sizeof(u64));
+    u64 *mn = mc + nmain, *ac = mn + nmain, *an = ac + naux3;
+    u64 *vals = (u64 *)malloc(3 * 512 * sizeof(u64));
+#pragma omp for schedule(static)
+    for (size_t i = 0; i < N; i++) {
+      size_t j = (i + unit) % N;
+      for (size_t c = 0; c < nmain; c++) { mc[c] = main[c * N + i]; mn[c] = main[c * N + j]; }
+      for (size_t c = 0; c < naux3; c++) { ac[c] = aux[c * N + i]; an[c] = aux[c * N + j]; }
+      u64 acc[3] = {0, 0, 0};
+      size_t off = 0;
+      for (int cat = 0; cat < 4; cat++) {
+        if (cat == 0) orc_air_eval_init(mc, ac, mn, an, ch, vals);
+        else if (cat == 1) orc_air_eval_cons(mc, ac, mn, an, ch, vals);
+        else if (cat == 2) orc_air_eval_tran(mc, ac, mn, an, ch, vals);
+        else orc_air_eval_term(mc, ac, mn, an, ch, vals);
+        u64 s[3] = {0, 0, 0}, t[3];
+        for (int k = 0; k < nc[cat]; k++) {
+          orc_xmul(w + 3 * (off + k), vals + 3 * k, t);
+          s[0] = fadd(s[0], t[0]); s[1] = fadd(s[1], t[1]); s[2] = fadd(s[2], t[2]);
+        }
+        off += nc[cat];
+        u64 z = zi[cat * N + i];
+        acc[0] = fadd(acc[0], fmul(s[0], z)); acc[1] = fadd(acc[1], fmul(s[1], z)); acc[2] = fadd(acc[2], fmul(s[2], z));
+      }
+      out[3 * i] = acc[0]; out[3 * i + 1] = acc[1]; out[3 * i + 2] = acc[2];
+    }
+    free(mc); free(vals);
+  }
+  free(zi);
+}
+
+/* row evaluation of one category (for tests): out has 3 words per constraint */
+void orc_air_eval_category(int cat, const u64 *mc, const u64 *ac, const u64 *mn, const u64 *an, const u64 *ch, u64 *out) {
+  if (cat == 0) orc_air_eval_init(mc, ac, mn, an, ch, out);
+  else if (cat == 1) orc_air_eval_cons(mc, ac, mn, an, ch, out);
+  else if (cat == 2) orc_air_eval_tran(mc, ac, mn, an, ch, out);
+  else orc_air_eval_term(mc, ac, mn, an, ch, out);
+}
+
+/* ---- X-field vector helpers (elements interleaved [n][3]) -------------------------------- */
+/* FRI fold: fri.rs:349-366 */
+void orc_fri_fold(const u64 *cw, size_t n, u64 domain_offset, const u64 chal[3], u64 *out) {
+  unsigned log2n = 0; while (((size_t)1 << log2n) < n) log2n++;
+  u64 g = orc_root_of_unity(log2n);
+  u64 *inv = (u64 *)malloc((n / 2) * sizeof(u64));
+  u64 x = domain_offset;
+  for (size_t i = 0; i < n / 2; i++) { inv[i] = x; x = fmul(x, g); }
+  batch_inverse(inv, n / 2);
+  u64 two_inv = orc_inv(fadd(MONT_ONE, MONT_ONE));
+#pragma omp parallel for schedule(static) if (n >= 4096)
+  for (size_t i = 0; i < n / 2; i++) {
+    u64 s[3] = {fmul(chal[0], inv[i]), fmul(chal[1], inv[i]), fmul(chal[2], inv[i])};
+    u64 one_plus[3] = {fadd(MONT_ONE, s[0]), s[1], s[2]};
+    u64 one_minus[3] = {fsub(MONT_ONE, s[0]), fneg(s[1]), fneg(s[2])};
+    u64 l[3], r[3];
+    orc_xmul(one_plus, cw + 3 * i, l);
+    orc_xmul(one_minus, cw + 3 * (n / 2 + i), r);
+    for (int d = 0; d < 3; d++) out[3 * i + d] = fmul(fadd(l[d], r[d]), two_inv);
+  }
+  free(inv);
+}

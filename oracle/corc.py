@@ -122,3 +122,41 @@ def merkle_build(leaves, mont_io=False):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def _xarr(xs):
+    """list of X-field tuples / [k,3] array -> Montgomery uint64 [k,3]"""
+    return to_mont(np.array(xs, dtype=np.uint64).reshape(-1, 3)).reshape(-1, 3)
+
+
+def air_quotient(main_lde, aux_lde, log2_trace, offset, challenges, weights):
+    """all_quotients_combined on natural-order column-major LDE tables -> [N,3] canonical"""
+    m = np.ascontiguousarray(to_mont(main_lde)).reshape(main_lde.shape)
+    a = np.ascontiguousarray(to_mont(aux_lde)).reshape(aux_lde.shape)
+    N = m.shape[1]
+    ch, w = _xarr(challenges), _xarr(weights)
+    assert ch.shape[0] == 63 and w.shape[0] == 604 and a.shape[1] == N
+    out = np.empty((N, 3), dtype=np.uint64)
+    lib().orc_air_quotient(_p(m), ctypes.c_size_t(m.shape[0]), _p(a), ctypes.c_size_t(a.shape[0]), ctypes.c_size_t(N),
+                           ctypes.c_uint(log2_trace), ctypes.c_uint64(mont1(offset)), _p(ch), _p(w), _p(out))
+    return from_mont(out).reshape(N, 3)
+
+
+def air_eval_category(cat, mc, ac, mn, an, challenges):
+    """cat in 0..3; rows as canonical arrays (main 379 B-field, aux 90 X-field) -> [num_constraints, 3]"""
+    l = lib()
+    counts = (ctypes.c_int * 4).in_dll(l, "ORC_AIR_NUM_CONSTRAINTS")
+    out = np.empty((counts[cat], 3), dtype=np.uint64)
+    args = [to_mont(np.array(v, dtype=np.uint64).reshape(-1)) for v in (mc, ac, mn, an)]
+    ch = _xarr(challenges)
+    l.orc_air_eval_category(ctypes.c_int(cat), _p(args[0]), _p(args[1]), _p(args[2]), _p(args[3]), _p(ch), _p(out))
+    return from_mont(out).reshape(-1, 3)
+
+
+def fri_fold(cw, domain_offset, challenge):
+    c = np.ascontiguousarray(to_mont(np.array(cw, dtype=np.uint64).reshape(-1, 3))).reshape(-1, 3)
+    n = c.shape[0]
+    ch = _xarr([challenge])
+    out = np.empty((n // 2, 3), dtype=np.uint64)
+    lib().orc_fri_fold(_p(c), ctypes.c_size_t(n), ctypes.c_uint64(mont1(domain_offset)), _p(ch), _p(out))
+    return from_mont(out).reshape(-1, 3)

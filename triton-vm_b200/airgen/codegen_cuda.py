@@ -214,6 +214,14 @@ def main():
         f.write(f"// {len(names)} chunks, {total_ops} binary operations emitted ({unique_ops} unique in the circuit)\n")
         for kname, cat, ncons, nops in names:
             f.write(f"TVM_AIR_CHUNK({kname}) // {cat}: {ncons} constraints, {nops} ops\n")
+    with open(os.path.join(OUT_DIR, "air_meta.inc"), "w") as f:
+        f.write("// GENERATED by airgen/codegen_cuda.py — constraint degrees in evaluator order\n")
+        f.write("// (the generated *_quotient_degree_bounds of the reference, codegen.rs:222-229).\n")
+        for cat in CATEGORIES:
+            b = air.builders[cat]
+            degs = [b.degree(c) for c in air.constraints[cat]]
+            f.write(f"static const int AIR_NUM_{cat.upper()} = {len(degs)};\n")
+            f.write(f"static const unsigned char AIR_DEGREES_{cat.upper()}[] = {{{', '.join(map(str, degs))}}};\n")
     print(f"wrote {len(names)} chunks to {OUT_DIR}: {total_ops} ops emitted, {unique_ops} unique")
     for n in names:
         print("  ", n)

@@ -2,6 +2,7 @@
 #include "../../include/tvm_b200.h"
 #include "ctx.h"
 #include "launch.h"
+#include "stark.h"
 #include <cstring>
 #include <new>
 
@@ -9,6 +10,7 @@ using namespace tvm;
 
 struct tvm_ctx {
   Ctx c;
+  ProveTimings timings;
 };
 
 namespace tvm {
@@ -342,6 +344,49 @@ int tvm_air_quotient_dev(tvm_ctx *ctx, const uint64_t *d_main, size_t main_strid
   air_quotient_run(*c__, (const u64 *)d_main, main_stride, (const u64 *)d_aux, aux_stride, d, d + nc, log2_trace, log2_cosets,
                    to_mont(offset_canon), (u64 *)d_out, out_stride);
   TVM_API_END
+}
+
+int tvm_derive_domains(const tvm_params *p, uint64_t padded_height, tvm_domains *out) {
+  if (!p || !out) return TVM_ERR_INVALID_ARG;
+  if (p->ldt_choice != 1) return TVM_ERR_UNSUPPORTED;
+  StarkDerived d{};
+  int rc = stark_derive(StarkParams{p->security_level, p->log2_ldt_expansion_factor}, padded_height, d);
+  if (rc) return rc;
+  out->padded_height = d.padded_height; out->num_trace_randomizers = d.num_trace_randomizers;
+  out->randomized_trace_len = d.randomized_trace_len; out->trace_len = d.trace_len; out->quotient_len = d.quotient_len;
+  out->ldt_len = d.ldt_len; out->ldt_offset = d.ldt_offset; out->num_collinearity_checks = d.num_collinearity_checks;
+  out->fri_num_rounds = d.fri_num_rounds; out->fri_last_round_max_degree = d.fri_last_round_max_degree;
+  out->num_quotient_randomizer_coefficients = d.num_quotient_randomizer_coefficients;
+  return TVM_OK;
+}
+
+int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height, const uint64_t *main_trace,
+              const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user, const uint64_t *quot_rand, uint64_t *proof_out,
+              size_t *proof_len) {
+  if (!ctx || !params || !claim || !main_trace || !main_rand || !aux_cb || !quot_rand || !proof_len) return TVM_ERR_INVALID_ARG;
+  if (params->ldt_choice != 1) return TVM_ERR_UNSUPPORTED;
+  TVM_API_BEGIN(ctx)
+  ClaimView cv{claim->program_digest, claim->version, claim->input, claim->num_input, claim->output, claim->num_output};
+  std::vector<u64> proof;
+  stark_prove(*c__, StarkParams{params->security_level, params->log2_ldt_expansion_factor}, cv, padded_height, (const u64 *)main_trace,
+              (const u64 *)main_rand, (AuxCallback)aux_cb, aux_user, (const u64 *)quot_rand, proof, &ctx->timings);
+  size_t cap = *proof_len;
+  *proof_len = proof.size();
+  if (!proof_out || cap < proof.size()) throw ApiError{TVM_ERR_INVALID_ARG, "proof buffer too small"};
+  memcpy(proof_out, proof.data(), proof.size() * 8);
+  TVM_API_END
+}
+
+int tvm_last_prove_timings(const tvm_ctx *ctx, const char **names, float *ms) {
+  if (!ctx) return 0;
+  int n = 0;
+  for (auto &st : ctx->timings.stages) {
+    if (n >= 16) break;
+    if (names) names[n] = st.first.c_str();
+    if (ms) ms[n] = st.second;
+    n++;
+  }
+  return n;
 }
 
 }  // extern "C"

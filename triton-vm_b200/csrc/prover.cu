@@ -1,0 +1,540 @@
+// Stark::prove on one B200: orchestration of the device kernels + host Fiat-Shamir transcript.
+//
+// Restates Prover::prove (triton-vm/src/stark.rs:331-719) step by step for the cached-LDE branch
+// with the FRI low-degree test (stark.with_ldt_choice(LdtChoice::Fri); STIR is not built yet) and
+// the parameter derivation of stark.rs:1885-2089, fri.rs:799-924, low_degree_test/mod.rs:250-300.
+// Trace generation stays with the caller: the main trace and all randomizer
+// coefficients are inputs; the auxiliary trace is requested through a callback once the
+// challenges exist (stark.rs:374-380).
+//
+// Device layout: every table is column-major; LDE tables are additionally coset-major
+// ([col][coset][k], evaluation-domain row i = coset + r*k).  X-field columns are stored as three
+// planar B-field columns.  Interpolant coefficients are kept pre-scaled by offset^j.
+#include <cmath>
+#include <cstring>
+#include <set>
+#include "air.cuh"
+#include "launch.h"
+#include "stark.h"
+#include "transcript.h"
+
+namespace tvm {
+#include "air_gen/air_meta.inc"
+
+static size_t next_pow2(size_t x) {
+  size_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+static int ilog2(size_t x) {
+  int l = 0;
+  while (((size_t)1 << (l + 1)) <= x) l++;
+  return l;
+}
+
+int stark_derive(const StarkParams &sp, size_t padded_height, StarkDerived &d) {
+  if (sp.log2_expansion == 0 || sp.log2_expansion > 8 || sp.security_level == 0) return TVM_ERR_LDT_PARAMS;
+  padded_height = next_pow2(padded_height ? padded_height : 1);
+  if (padded_height > ((size_t)1 << 31)) return TVM_ERR_DOMAIN;
+  const int log2_ph = ilog2(padded_height);
+  // low_degree_test/mod.rs:250-300 (ProximityRegime::Proven) and fri.rs:832-836
+  const double rate = 1.0 / (double)(1u << sp.log2_expansion);
+  const double margin = std::sqrt(rate);
+  const double proximity_parameter = 1.0 - margin - margin / 20.0;
+  const size_t checks = (size_t)std::ceil(-(double)sp.security_level / std::log2(1.0 - proximity_parameter));
+  const size_t h = checks + NUM_QUOTIENT_SEGMENTS * 3 * 2 + 1;           // stark.rs:2083-2089
+  const size_t nqr = (h + 1) * NUM_RANDOMIZED_QUOTIENT_SEGMENTS;         // stark.rs:1894-1896
+  const size_t expansion = (size_t)1 << sp.log2_expansion;
+  size_t rtl = next_pow2(std::max(std::max(padded_height + h, 2 * h + 1), nqr));   // stark.rs:1885-1890
+  int hdb = log2_ph;
+  size_t ldt_len;
+  for (;;) {                                                             // stark.rs:1975-1984
+    hdb++;
+    if (hdb + (int)sp.log2_expansion > 32) return TVM_ERR_LDT_PARAMS;
+    ldt_len = (size_t)1 << (hdb + sp.log2_expansion);
+    if (ldt_len >= rtl * expansion) break;
+  }
+  const long long interpolant_degree = (long long)rtl - 1;
+  long long max_cd = 0;
+  auto upd = [&](const unsigned char *degs, int n, long long zerofier_degree) {
+    for (int i = 0; i < n; i++) max_cd = std::max(max_cd, interpolant_degree * degs[i] - zerofier_degree);
+  };
+  upd(AIR_DEGREES_INIT, AIR_NUM_INIT, 1);
+  upd(AIR_DEGREES_CONS, AIR_NUM_CONS, (long long)padded_height);
+  upd(AIR_DEGREES_TRAN, AIR_NUM_TRAN, (long long)padded_height - 1);
+  upd(AIR_DEGREES_TERM, AIR_NUM_TERM, 1);
+  const size_t max_degree = next_pow2((size_t)max_cd) - 1;              // stark.rs:1905-1916
+  const size_t fri_max_degree = ldt_len / expansion - 1;                 // fri.rs:885-887
+  const int max_num_rounds = ilog2(next_pow2(fri_max_degree + 1));
+  const int skip = (checks ? ilog2(checks) : 0) + 1;                     // fri.rs:907-920
+  d.padded_height = padded_height;
+  d.num_trace_randomizers = h;
+  d.randomized_trace_len = rtl;
+  d.trace_len = rtl / 2;
+  d.quotient_len = next_pow2(max_degree);
+  d.ldt_len = ldt_len;
+  d.ldt_offset = 7;                                                      // BFieldElement::generator(), fri.rs:829
+  d.num_collinearity_checks = checks;
+  d.fri_num_rounds = max_num_rounds > skip ? (size_t)(max_num_rounds - skip) : 0;
+  d.fri_last_round_max_degree = fri_max_degree >> d.fri_num_rounds;
+  d.num_quotient_randomizer_coefficients = nqr;
+  return TVM_OK;
+}
+
+namespace {
+
+struct DevMem {   // RAII device buffers of one prove() call
+  std::vector<void *> ptrs;
+  ~DevMem() { for (void *p : ptrs) cudaFree(p); }
+  u64 *words(size_t n) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(u64));
+    if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
+    ptrs.push_back(p);
+    return (u64 *)p;
+  }
+  void release(void *p) {
+    for (size_t i = 0; i < ptrs.size(); i++)
+      if (ptrs[i] == p) { cudaFree(p); ptrs.erase(ptrs.begin() + i); return; }
+  }
+};
+
+xfe xmul_by_X(xfe a) { return xmake(fneg(a.c2), fadd(a.c0, a.c2), a.c1); }   // X^3 = X - 1
+// value of an X-field column stored as 3 planar B-field columns from the 3 per-plane dot products
+xfe combine_planes(xfe r0, xfe r1, xfe r2) { return xadd(r0, xadd(xmul_by_X(r1), xmul_by_X(xmul_by_X(r2)))); }
+
+xfe eval_arg_terminal(const u64 *symbols_canon, size_t n, xfe challenge) {  // cross_table_argument.rs:60-73
+  xfe acc = xone();
+  for (size_t i = 0; i < n; i++) acc = xaddb(xmul(challenge, acc), to_mont(symbols_canon[i] % P));
+  return acc;
+}
+
+std::vector<unsigned> auth_structure_node_indices(size_t num_leafs, const std::vector<uint32_t> &leaf_indices) {
+  // twenty-first MerkleTree::authentication_structure: needed-but-not-computable
+  // sibling nodes, descending node index
+  std::set<size_t> needed, computable;
+  for (uint32_t li : leaf_indices) {
+    size_t node = (size_t)li + num_leafs;
+    while (node > 1) {
+      computable.insert(node);
+      needed.insert(node ^ 1);
+      node >>= 1;
+    }
+  }
+  std::vector<unsigned> out;
+  for (auto it = needed.rbegin(); it != needed.rend(); ++it)
+    if (!computable.count(*it)) out.push_back((unsigned)*it);
+  return out;
+}
+
+void lde_batched(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned h, unsigned log_n, unsigned log_r, u64 offset_mont, size_t ncols,
+                 u64 *d_coef, u64 *d_lde, u64 *d_tmp, size_t tmp_cols) {
+  const size_t n = (size_t)1 << log_n, N = n << log_r;
+  for (size_t c0 = 0; c0 < ncols; c0 += tmp_cols) {
+    size_t b = std::min(tmp_cols, ncols - c0);
+    lde_run(c, d_trace + c0 * n, d_rand ? d_rand + c0 * h : nullptr, h, log_n, log_r, offset_mont, b, d_coef + c0 * 2 * n,
+            d_lde + c0 * N, d_tmp);
+  }
+}
+
+// forward coset-LDE of already pre-scaled coefficient columns (stride 2n, upper half folded)
+void coef_to_lde(Ctx &c, const u64 *d_coef, size_t ncols, unsigned log_n, unsigned log_r, unsigned fold_count, u64 *d_lde, u64 *d_tmp,
+                 size_t tmp_cols) {
+  const size_t n = (size_t)1 << log_n, N = n << log_r;
+  for (size_t c0 = 0; c0 < ncols; c0 += tmp_cols) {
+    size_t b = std::min(tmp_cols, ncols - c0);
+    NttJob fwd{};
+    fwd.in = d_coef + c0 * 2 * n; fwd.in_cstride = 2 * n;
+    fwd.out = d_lde + c0 * N; fwd.out_cstride = n;
+    fwd.tmp = d_tmp;
+    fwd.log_n = (int)log_n; fwd.ncols = b; fwd.inverse = false;
+    fwd.num_cosets = 1 << log_r; fwd.coset_pre = true; fwd.fold_count = fold_count;
+    ntt_run(c, fwd);
+  }
+}
+
+std::vector<u64> d2h(Ctx &c, const u64 *d, size_t n) {
+  std::vector<u64> h(n);
+  TVM_CUDA(cudaMemcpyAsync(h.data(), d, n * sizeof(u64), cudaMemcpyDeviceToHost, c.stream));
+  TVM_CUDA(cudaStreamSynchronize(c.stream));
+  return h;
+}
+
+}  // namespace
+
+void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t padded_height, const u64 *h_main_trace,
+                 const u64 *h_main_rand, AuxCallback aux_cb, void *aux_user, const u64 *h_quot_rand, std::vector<u64> &proof,
+                 ProveTimings *timings) {
+  StarkDerived d{};
+  int rc = stark_derive(sp, padded_height, d);
+  if (rc) throw ApiError{rc, "parameter derivation failed"};
+  if (d.quotient_len != d.ldt_len) throw ApiError{TVM_ERR_UNSUPPORTED, "quotient domain != LDT domain is not supported yet"};
+  const size_t n = d.trace_len, N = d.ldt_len, h = d.num_trace_randomizers;
+  const unsigned log_n = (unsigned)ilog2(n), log_N = (unsigned)ilog2(N), log_r = log_N - log_n;
+  if (N != 8 * n) throw ApiError{TVM_ERR_UNSUPPORTED, "only LDT domain = 8 x trace domain (expansion factor 4) is supported yet"};
+  const u64 off = to_mont(d.ldt_offset);
+  const size_t NM = TVM_NUM_MAIN_COLUMNS, NA = TVM_NUM_AUX_COLUMNS, NA3 = 3 * NA;
+  const size_t tmp_cols = 16;
+  cudaEvent_t ev[16];
+  int nev = 0;
+  auto mark = [&]() {
+    if (!timings) return;
+    cudaEventCreate(&ev[nev]);
+    cudaEventRecord(ev[nev], c.stream);
+    nev++;
+  };
+
+  DevMem mem;
+  ProofStream ps;
+  ps.alter_fiat_shamir_state_with(encode_claim(claim.program_digest, claim.version, claim.input, claim.num_input, claim.output,
+                                               claim.num_output));
+  ps.enqueue(ItemKind::Log2PaddedHeight, {(u64)ilog2(d.padded_height)});
+  mark();  // 0
+
+  // ---- main table: upload, LDE, row hashes, Merkle tree (stark.rs:359-374) -------------------------
+  u64 *d_tmp = mem.words(tmp_cols * N);
+  u64 *d_main_trace = mem.words(NM * n + NM * h);
+  u64 *d_main_rand = d_main_trace + NM * n;
+  TVM_CUDA(cudaMemcpyAsync(d_main_trace, h_main_trace, NM * n * 8, cudaMemcpyHostToDevice, c.stream));
+  TVM_CUDA(cudaMemcpyAsync(d_main_rand, h_main_rand, NM * h * 8, cudaMemcpyHostToDevice, c.stream));
+  to_mont_run(c, d_main_trace, NM * n + NM * h);
+  u64 *d_main_coef = mem.words(NM * 2 * n);
+  u64 *d_main_lde = mem.words(NM * N);
+  TVM_CUDA(cudaMemsetAsync(d_main_coef, 0, NM * 2 * n * 8, c.stream));
+  lde_batched(c, d_main_trace, d_main_rand, (unsigned)h, log_n, log_r, off, NM, d_main_coef, d_main_lde, d_tmp, tmp_cols);
+  mark();  // 1: main LDE
+  u64 *d_main_nodes = mem.words(2 * N * 5);
+  TVM_CUDA(cudaMemsetAsync(d_main_nodes, 0, 40, c.stream));
+  hash_rows_run(c, d_main_lde, N, N, (unsigned)NM, (int)log_r, d_main_nodes + 5 * N);
+  merkle_run(c, d_main_nodes, N);
+  {
+    std::vector<u64> root = d2h(c, d_main_nodes + 5, 5);
+    for (auto &v : root) v = from_mont(v);
+    ps.enqueue(ItemKind::MerkleRoot, root);
+  }
+  mark();  // 2: main Merkle
+  mem.release(d_main_trace);
+
+  // ---- challenges (stark.rs:374-376, challenges.rs:88-135) -------------------------------------------
+  std::vector<xfe> ch = ps.sponge.sample_scalars(59);
+  {
+    u64 lut[256];
+    for (int i = 0; i < 256; i++) lut[i] = TIP5_LOOKUP_HOST[i];
+    xfe compressed_digest = eval_arg_terminal(claim.program_digest, 5, ch[0]);
+    xfe input_terminal = eval_arg_terminal(claim.input, claim.num_input, ch[1]);
+    xfe output_terminal = eval_arg_terminal(claim.output, claim.num_output, ch[2]);
+    xfe lookup_terminal = eval_arg_terminal(lut, 256, ch[54]);
+    ch.push_back(input_terminal); ch.push_back(output_terminal); ch.push_back(lookup_terminal); ch.push_back(compressed_digest);
+  }
+  std::vector<u64> ch_canon, ch_mont;
+  for (xfe x : ch) {
+    push_xfe_canon(ch_canon, x);
+    ch_mont.push_back(x.c0); ch_mont.push_back(x.c1); ch_mont.push_back(x.c2);
+  }
+
+  // ---- auxiliary table (stark.rs:380-392) ---------------------------------------------------------------
+  u64 *h_aux = nullptr;
+  TVM_CUDA(cudaMallocHost(&h_aux, (NA * n * 3 + NA * h * 3) * 8));
+  struct HostFree { u64 *p; ~HostFree() { cudaFreeHost(p); } } host_free{h_aux};
+  if (!aux_cb) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback missing"};
+  if (int crc = aux_cb(aux_user, ch_canon.data(), h_aux, h_aux + NA * n * 3)) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback failed: " + std::to_string(crc)};
+  mark();  // 3: extend (caller)
+  u64 *d_aux_in = mem.words(NA * n * 3 + NA * h * 3);
+  TVM_CUDA(cudaMemcpyAsync(d_aux_in, h_aux, (NA * n * 3 + NA * h * 3) * 8, cudaMemcpyHostToDevice, c.stream));
+  to_mont_run(c, d_aux_in, NA * n * 3 + NA * h * 3);
+  u64 *d_aux_trace = mem.words(NA3 * n + NA3 * h);
+  u64 *d_aux_rand = d_aux_trace + NA3 * n;
+  deinterleave3_run(c, d_aux_in, d_aux_trace, n, NA);
+  deinterleave3_run(c, d_aux_in + NA * n * 3, d_aux_rand, h, NA);
+  mem.release(d_aux_in);
+  u64 *d_aux_coef = mem.words(NA3 * 2 * n);
+  u64 *d_aux_lde = mem.words(NA3 * N);
+  TVM_CUDA(cudaMemsetAsync(d_aux_coef, 0, NA3 * 2 * n * 8, c.stream));
+  lde_batched(c, d_aux_trace, d_aux_rand, (unsigned)h, log_n, log_r, off, NA3, d_aux_coef, d_aux_lde, d_tmp, tmp_cols);
+  mark();  // 4: aux LDE
+  u64 *d_aux_nodes = mem.words(2 * N * 5);
+  TVM_CUDA(cudaMemsetAsync(d_aux_nodes, 0, 40, c.stream));
+  hash_rows_run(c, d_aux_lde, N, N, (unsigned)NA3, (int)log_r, d_aux_nodes + 5 * N);
+  merkle_run(c, d_aux_nodes, N);
+  {
+    std::vector<u64> root = d2h(c, d_aux_nodes + 5, 5);
+    for (auto &v : root) v = from_mont(v);
+    ps.enqueue(ItemKind::MerkleRoot, root);
+  }
+  mark();  // 5: aux Merkle
+  mem.release(d_aux_trace);
+
+  // ---- quotient codeword (stark.rs:396-411, master_table.rs:1264-1363) ---------------------------------------
+  xfe w0 = ps.sponge.sample_scalars(1)[0];
+  std::vector<u64> consts(ch_mont);
+  {
+    xfe acc = xone();
+    for (int i = 0; i < TVM_NUM_CONSTRAINTS; i++) {
+      consts.push_back(acc.c0); consts.push_back(acc.c1); consts.push_back(acc.c2);
+      acc = xmul(acc, w0);
+    }
+  }
+  u64 *d_consts = mem.words(consts.size());
+  TVM_CUDA(cudaMemcpyAsync(d_consts, consts.data(), consts.size() * 8, cudaMemcpyHostToDevice, c.stream));
+  TVM_CUDA(cudaStreamSynchronize(c.stream));
+  u64 *d_quot = mem.words(3 * N);
+  air_quotient_run(c, d_main_lde, N, d_aux_lde, N, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, off, d_quot, N);
+  mark();  // 6: AIR quotient
+
+  // interpolate (stark.rs:1224-1231): natural order, iNTT, (coset offset undone inside the segment kernel)
+  u64 *d_qnat = mem.words(3 * N);
+  coset_to_natural_run(c, d_quot, d_qnat, N, N, (int)log_n, (int)log_r, 3);
+  {
+    NttJob inv{};
+    inv.in = d_qnat; inv.in_cstride = N; inv.out = d_quot; inv.out_cstride = N; inv.tmp = d_tmp;
+    inv.log_n = (int)log_N; inv.ncols = 3; inv.inverse = true;
+    ntt_run(c, inv);   // d_quot[d][j] = a_j * offset^j
+  }
+  // split into 4 segments + randomizer segment, randomize (stark.rs:1252-1263, 1302-1356)
+  const size_t seg_len = N / NUM_QUOTIENT_SEGMENTS;     // == 2n
+  const size_t nqr = d.num_quotient_randomizer_coefficients;
+  u64 *d_qr_in = mem.words(3 * nqr);
+  u64 *d_qr = mem.words(3 * nqr);
+  TVM_CUDA(cudaMemcpyAsync(d_qr_in, h_quot_rand, 3 * nqr * 8, cudaMemcpyHostToDevice, c.stream));
+  to_mont_run(c, d_qr_in, 3 * nqr);
+  deinterleave3_run(c, d_qr_in, d_qr, nqr, 1);
+  u64 *d_seg_coef = mem.words(15 * seg_len);
+  {
+    // undo the coset offset: a_j = (a_j offset^j) * offset^-j
+    scale_by_powers_run(c, d_quot, N, 3, N, c.get_pow_tab(finv(off), (int)log_N));
+    SegmentArgs sa{};
+    sa.quot = d_quot; sa.quot_stride = N;
+    sa.rnd = d_qr; sa.rnd_stride = nqr; sa.rnd_len = (unsigned)nqr;
+    sa.out = d_seg_coef; sa.out_stride = seg_len; sa.seg_len = seg_len;
+    u64 zeta = to_mont(3);
+    sa.zeta4 = c.get_pow_tab(fpow(zeta, NUM_QUOTIENT_SEGMENTS), ilog2(seg_len));
+    sa.off = c.get_pow_tab(off, ilog2(seg_len));
+    for (int i = 0; i < 4; i++) sa.zeta_pow[i] = fpow(zeta, (u64)i);
+    segment_chain_run(c, sa);
+  }
+  u64 *d_seg_lde = mem.words(15 * N);
+  coef_to_lde(c, d_seg_coef, 15, log_n, log_r, (unsigned)n, d_seg_lde, d_tmp, tmp_cols);
+  mark();  // 7: quotient LDE
+  u64 *d_quot_nodes = mem.words(2 * N * 5);
+  TVM_CUDA(cudaMemsetAsync(d_quot_nodes, 0, 40, c.stream));
+  hash_rows_run(c, d_seg_lde, N, N, 15, (int)log_r, d_quot_nodes + 5 * N);
+  merkle_run(c, d_quot_nodes, N);
+  {
+    std::vector<u64> root = d2h(c, d_quot_nodes + 5, 5);
+    for (auto &v : root) v = from_mont(v);
+    ps.enqueue(ItemKind::MerkleRoot, root);
+  }
+  mark();  // 8: quotient Merkle
+  mem.release(d_qnat);
+
+  // ---- out-of-domain rows (stark.rs:450-495) --------------------------------------------------------------------
+  const xfe alpha = ps.sponge.sample_scalars(1)[0];
+  const u64 omega = root_of_unity_mont(log_n);
+  const xfe alpha_next = xmulb(alpha, omega);
+  const u64 off_inv = finv(off);
+  const size_t clen = 2 * n;
+  u64 *d_pw = mem.words(4 * 3 * clen);   // 4 power vectors (alpha, omega*alpha, alpha^4, (zeta alpha)^4), each / offset
+  const xfe alpha_pow = xpow(alpha, NUM_QUOTIENT_SEGMENTS);
+  const xfe alpha_zeta_pow = xpow(xmulb(alpha, to_mont(3)), NUM_QUOTIENT_SEGMENTS);
+  const xfe pts[4] = {alpha, alpha_next, alpha_pow, alpha_zeta_pow};
+  for (int t = 0; t < 4; t++) xpow_vector_run(c, xmulb(pts[t], off_inv), d_pw + (size_t)t * 3 * clen, clen, clen);
+  u64 *d_dots = mem.words((NM + NA3 + 15 + 9) * 2 * 3);
+  col_dot_run(c, d_main_coef, clen, NM, clen, d_pw, clen, 3 * clen, 2, d_dots);
+  col_dot_run(c, d_aux_coef, clen, NA3, clen, d_pw, clen, 3 * clen, 2, d_dots + NM * 6);
+  col_dot_run(c, d_seg_coef, seg_len, 15, seg_len, d_pw + 2 * 3 * clen, clen, 3 * clen, 2, d_dots + (NM + NA3) * 6);
+  std::vector<u64> dots = d2h(c, d_dots, (NM + NA3 + 15) * 6);
+  auto dot_at = [&](size_t col, int v) { const u64 *p = &dots[(col * 2 + v) * 3]; return xmake(p[0], p[1], p[2]); };
+  for (int v = 0; v < 2; v++) {
+    std::vector<u64> row;
+    for (size_t q = 0; q < NM; q++) push_xfe_canon(row, dot_at(q, v));
+    ps.enqueue(ItemKind::OutOfDomainMainRow, row);
+    row.clear();
+    for (size_t q = 0; q < NA; q++)
+      push_xfe_canon(row, combine_planes(dot_at(NM + 3 * q, v), dot_at(NM + 3 * q + 1, v), dot_at(NM + 3 * q + 2, v)));
+    ps.enqueue(ItemKind::OutOfDomainAuxRow, row);
+  }
+  xfe seg_at[5][2];
+  for (int s = 0; s < 5; s++)
+    for (int v = 0; v < 2; v++)
+      seg_at[s][v] = combine_planes(dot_at(NM + NA3 + 3 * s, v), dot_at(NM + NA3 + 3 * s + 1, v), dot_at(NM + NA3 + 3 * s + 2, v));
+  {
+    std::vector<u64> row;
+    for (int s = 0; s < 4; s++) push_xfe_canon(row, seg_at[s][0]);       // p: s_0..s_3 at alpha^4
+    ps.enqueue(ItemKind::OutOfDomainQuotientSegments, row);
+    row.clear();
+    for (int s = 1; s < 5; s++) push_xfe_canon(row, seg_at[s][1]);       // r: s_1..s_4 at (zeta alpha)^4
+    ps.enqueue(ItemKind::OutOfDomainQuotientSegments, row);
+  }
+  mark();  // 9: OOD rows
+
+  // ---- combination codeword (stark.rs:498-639) ----------------------------------------------------------------------
+  std::vector<xfe> cw3 = ps.sponge.sample_scalars(3);
+  std::vector<u64> wts;   // [470 main&aux][5 p][5 r] X-field weights
+  {
+    xfe acc = xone();
+    for (size_t i = 0; i < NM + NA; i++) { wts.push_back(acc.c0); wts.push_back(acc.c1); wts.push_back(acc.c2); acc = xmul(acc, cw3[0]); }
+    xfe wq[5];
+    acc = xone();
+    for (int i = 0; i < 5; i++) { wq[i] = acc; acc = xmul(acc, cw3[1]); }
+    for (int i = 0; i < 5; i++) { xfe w = i < 4 ? wq[i] : xzero(); wts.push_back(w.c0); wts.push_back(w.c1); wts.push_back(w.c2); }
+    for (int i = 0; i < 5; i++) { xfe w = i > 0 ? wq[i] : xzero(); wts.push_back(w.c0); wts.push_back(w.c1); wts.push_back(w.c2); }
+  }
+  xfe w_deep[4];
+  {
+    xfe acc = xone();
+    for (int i = 0; i < 4; i++) { w_deep[i] = acc; acc = xmul(acc, cw3[2]); }
+  }
+  u64 *d_wts = mem.words(wts.size());
+  TVM_CUDA(cudaMemcpyAsync(d_wts, wts.data(), wts.size() * 8, cudaMemcpyHostToDevice, c.stream));
+  TVM_CUDA(cudaStreamSynchronize(c.stream));
+  u64 *d_cpr = mem.words(9 * clen);    // combination, p, r polynomials (pre-scaled), 3 planes each
+  weighted_colsum_run(c, d_main_coef, clen, (unsigned)NM, false, d_wts, clen, d_cpr, clen, false);
+  weighted_colsum_run(c, d_aux_coef, clen, (unsigned)NA, true, d_wts + 3 * NM, clen, d_cpr, clen, true);
+  weighted_colsum_run(c, d_seg_coef, seg_len, 5, true, d_wts + 3 * (NM + NA), seg_len, d_cpr + 3 * clen, clen, false);
+  weighted_colsum_run(c, d_seg_coef, seg_len, 5, true, d_wts + 3 * (NM + NA + 5), seg_len, d_cpr + 6 * clen, clen, false);
+  // values at the out-of-domain points
+  col_dot_run(c, d_cpr, clen, 3, clen, d_pw, clen, 3 * clen, 2, d_dots);                               // comb at alpha, omega*alpha
+  col_dot_run(c, d_cpr + 3 * clen, clen, 6, clen, d_pw + 2 * 3 * clen, clen, 3 * clen, 2, d_dots + 18);  // p, r at alpha^4, (zeta alpha)^4
+  std::vector<u64> dv = d2h(c, d_dots, 9 * 6);
+  auto dvat = [&](size_t col, int v) { const u64 *p = &dv[(col * 2 + v) * 3]; return xmake(p[0], p[1], p[2]); };
+  DeepArgs da{};
+  da.value[0] = combine_planes(dvat(0, 0), dvat(1, 0), dvat(2, 0));
+  da.value[1] = combine_planes(dvat(0, 1), dvat(1, 1), dvat(2, 1));
+  da.value[2] = combine_planes(dvat(3, 0), dvat(4, 0), dvat(5, 0));
+  da.value[3] = combine_planes(dvat(6, 1), dvat(7, 1), dvat(8, 1));
+  u64 *d_cpr_lde = mem.words(9 * N);
+  coef_to_lde(c, d_cpr, 9, log_n, log_r, (unsigned)n, d_cpr_lde, d_tmp, tmp_cols);
+  u64 *d_fri = mem.words(3 * N);
+  da.cw = d_cpr_lde; da.cw_stride = N; da.out = d_fri; da.out_stride = N;
+  da.log_n = (int)log_n; da.log_r = (int)log_r;
+  da.dom = c.get_pow_tab(root_of_unity_mont(log_N), (int)log_N);
+  da.offset = off;
+  for (int t = 0; t < 4; t++) { da.point[t] = pts[t]; da.weight[t] = w_deep[t]; }
+  deep_run(c, da);
+  mark();  // 10: linear combination + DEEP
+
+  // ---- FRI (fri.rs:212-366, 754-772) ------------------------------------------------------------------------------------
+  struct Round { u64 *cw; size_t len; u64 *nodes; u64 offset; };
+  std::vector<Round> rounds;
+  {
+    u64 *cur = d_fri;
+    size_t len = N;
+    u64 offset = off;
+    for (size_t r = 0; r <= d.fri_num_rounds; r++) {
+      if (r > 0) {
+        xfe chal = ps.sponge.sample_scalars(1)[0];
+        u64 *nxt = mem.words(3 * (len / 2));
+        fri_fold_run(c, cur, len, len, offset, chal, nxt, len / 2);
+        cur = nxt; len /= 2; offset = fmul(offset, offset);
+      }
+      u64 *nodes = mem.words(2 * len * 5);
+      TVM_CUDA(cudaMemsetAsync(nodes, 0, 40, c.stream));
+      fri_leaves_run(c, cur, len, len, nodes + 5 * len);
+      merkle_run(c, nodes, len);
+      std::vector<u64> root = d2h(c, nodes + 5, 5);
+      for (auto &v : root) v = from_mont(v);
+      ps.enqueue(ItemKind::MerkleRoot, root);
+      rounds.push_back({cur, len, nodes, offset});
+    }
+  }
+  {
+    const Round &last = rounds.back();
+    std::vector<u64> planes = d2h(c, last.cw, 3 * last.len);
+    std::vector<u64> payload;
+    payload.push_back(last.len);
+    for (size_t i = 0; i < last.len; i++)
+      for (int dd = 0; dd < 3; dd++) payload.push_back(from_mont(planes[dd * last.len + i]));
+    ps.enqueue(ItemKind::FriCodeword, payload);
+    // last polynomial: interpolant over the unit-offset domain of that length (fri.rs:255-268)
+    u64 *d_lp = mem.words(3 * last.len);
+    u64 *d_lp_tmp = mem.words(3 * last.len);
+    NttJob inv{};
+    inv.in = last.cw; inv.in_cstride = last.len; inv.out = d_lp; inv.out_cstride = last.len; inv.tmp = d_lp_tmp;
+    inv.log_n = ilog2(last.len); inv.ncols = 3; inv.inverse = true;
+    ntt_run(c, inv);
+    std::vector<u64> co = d2h(c, d_lp, 3 * last.len);
+    size_t deg_plus_1 = last.len;
+    while (deg_plus_1 > 0 && co[deg_plus_1 - 1] == 0 && co[last.len + deg_plus_1 - 1] == 0 && co[2 * last.len + deg_plus_1 - 1] == 0) deg_plus_1--;
+    payload.clear();
+    payload.push_back(deg_plus_1);
+    for (size_t i = 0; i < deg_plus_1; i++)
+      for (int dd = 0; dd < 3; dd++) payload.push_back(from_mont(co[dd * last.len + i]));
+    ps.enqueue(ItemKind::Polynomial, payload);
+  }
+  std::vector<uint32_t> a_indices = ps.sponge.sample_indices((uint32_t)N, d.num_collinearity_checks);
+  const unsigned nq = (unsigned)a_indices.size();
+  unsigned *d_idx = (unsigned *)mem.words(nq * 64 + 64);
+  u64 *d_gather = mem.words((size_t)nq * 400 + (size_t)nq * 5 * 40 + 64);
+  auto reveal = [&](const Round &rd, const std::vector<uint32_t> &idx) {
+    TVM_CUDA(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, c.stream));
+    gather_rows_run(c, rd.cw, rd.len, 3, d_idx, (unsigned)idx.size(), 0, -1, d_gather);
+    std::vector<u64> leaves = d2h(c, d_gather, idx.size() * 3);
+    std::vector<unsigned> nodes = auth_structure_node_indices(rd.len, idx);
+    std::vector<u64> auth;
+    if (!nodes.empty()) {
+      TVM_CUDA(cudaMemcpyAsync(d_idx, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice, c.stream));
+      gather_digests_run(c, rd.nodes, d_idx, (unsigned)nodes.size(), d_gather);
+      auth = d2h(c, d_gather, nodes.size() * 5);
+    }
+    ps.enqueue(ItemKind::FriResponse, encode_fri_response(leaves, auth));
+  };
+  reveal(rounds[0], a_indices);
+  for (size_t r = 0; r + 1 < rounds.size(); r++) {
+    std::vector<uint32_t> b(a_indices.size());
+    for (size_t i = 0; i < b.size(); i++) b[i] = (uint32_t)(((size_t)a_indices[i] + rounds[r].len / 2) % rounds[r].len);
+    reveal(rounds[r], b);
+  }
+  ps.sponge.sample_scalars(1);   // fri.rs:764-769
+  mark();  // 11: FRI
+
+  // ---- zero-knowledge guard (stark.rs:648-663) -----------------------------------------------------------------------------
+  if (alpha_pow.c1 == 0 && alpha_pow.c2 == 0) {
+    u64 g = root_of_unity_mont(log_N);
+    u64 second = fmul(alpha_pow.c0, fpow(to_mont(3), NUM_QUOTIENT_SEGMENTS));
+    for (uint32_t i : a_indices) {
+      u64 x = fmul(off, fpow(g, i));
+      if (x == alpha_pow.c0 || x == second) throw ApiError{TVM_ERR_ZK_VIOLATION, "out-of-domain point collides with a revealed row"};
+    }
+  }
+
+  // ---- open rows (stark.rs:665-716) ---------------------------------------------------------------------------------------------
+  auto open_table = [&](const u64 *table, unsigned ncols, ItemKind kind, const u64 *nodes) {
+    TVM_CUDA(cudaMemcpyAsync(d_idx, a_indices.data(), nq * 4, cudaMemcpyHostToDevice, c.stream));
+    gather_rows_run(c, table, N, ncols, d_idx, nq, (int)log_n, (int)log_r, d_gather);
+    std::vector<u64> rows = d2h(c, d_gather, (size_t)nq * ncols);
+    std::vector<u64> payload;
+    payload.push_back(nq);
+    payload.insert(payload.end(), rows.begin(), rows.end());
+    ps.enqueue(kind, payload);
+    std::vector<unsigned> an = auth_structure_node_indices(N, a_indices);
+    std::vector<u64> auth;
+    auth.push_back(an.size());
+    if (!an.empty()) {
+      TVM_CUDA(cudaMemcpyAsync(d_idx, an.data(), an.size() * 4, cudaMemcpyHostToDevice, c.stream));
+      gather_digests_run(c, nodes, d_idx, (unsigned)an.size(), d_gather);
+      std::vector<u64> dg = d2h(c, d_gather, an.size() * 5);
+      auth.insert(auth.end(), dg.begin(), dg.end());
+    }
+    ps.enqueue(ItemKind::AuthenticationStructure, auth);
+  };
+  open_table(d_main_lde, (unsigned)NM, ItemKind::MasterMainTableRows, d_main_nodes);
+  open_table(d_aux_lde, (unsigned)NA3, ItemKind::MasterAuxTableRows, d_aux_nodes);
+  open_table(d_seg_lde, 15, ItemKind::QuotientSegmentsElements, d_quot_nodes);
+  mark();  // 12: open
+
+  proof = ps.encode();
+  if (timings) {
+    TVM_CUDA(cudaStreamSynchronize(c.stream));
+    static const char *names[] = {"LDE(main)", "Merkle(main)", "extend(caller)", "LDE(aux)", "Merkle(aux)", "quotient(AIR)",
+                                  "quotient LDE", "Merkle(quot)", "OOD rows", "linear combination+DEEP", "LDT(FRI)", "open"};
+    timings->stages.clear();
+    for (int i = 1; i < nev; i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      timings->stages.push_back({names[i - 1], ms});
+    }
+    for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
+  }
+}
+
+}  // namespace tvm

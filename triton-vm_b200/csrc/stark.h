@@ -1,0 +1,73 @@
+// Prover-level declarations shared by prover.cu, stark_kernels.cu and the C ABI.
+#pragma once
+#include <string>
+#include <vector>
+#include "ctx.h"
+
+namespace tvm {
+
+static constexpr int NUM_QUOTIENT_SEGMENTS = 4;              // stark.rs:66 (= air::TARGET_DEGREE)
+static constexpr int NUM_RANDOMIZED_QUOTIENT_SEGMENTS = 5;   // stark.rs:75
+
+struct StarkParams {          // stark.rs:113-145 (proven regime, FRI)
+  unsigned security_level;
+  unsigned log2_expansion;
+};
+struct StarkDerived {
+  size_t padded_height, num_trace_randomizers, randomized_trace_len, trace_len, quotient_len, ldt_len;
+  u64 ldt_offset;  // canonical
+  size_t num_collinearity_checks, fri_num_rounds, fri_last_round_max_degree, num_quotient_randomizer_coefficients;
+};
+int stark_derive(const StarkParams &sp, size_t padded_height, StarkDerived &d);
+
+struct ClaimView {            // proof.rs:68-88, canonical words
+  const u64 *program_digest;  // 5
+  unsigned version;
+  const u64 *input; size_t num_input;
+  const u64 *output; size_t num_output;
+};
+// fills aux_trace [91][n][3] and aux_rand [91][h][3] (canonical) given the 63 challenges (canonical)
+typedef int (*AuxCallback)(void *user, const u64 *challenges, u64 *aux_trace, u64 *aux_rand);
+
+struct ProveTimings {
+  std::vector<std::pair<std::string, float>> stages;   // device ms per stage, reference profiler labels
+};
+
+void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t padded_height, const u64 *h_main_trace,
+                 const u64 *h_main_rand, AuxCallback aux_cb, void *aux_user, const u64 *h_quot_rand, std::vector<u64> &proof,
+                 ProveTimings *timings);
+
+// ---- stark_kernels.cu ----
+struct SegmentArgs {
+  const u64 *quot; size_t quot_stride;
+  const u64 *rnd; size_t rnd_stride; unsigned rnd_len;
+  u64 *out; size_t out_stride;
+  size_t seg_len;
+  PowTab zeta4, off;
+  u64 zeta_pow[4];
+};
+struct DeepArgs {
+  const u64 *cw; size_t cw_stride;
+  u64 *out; size_t out_stride;
+  int log_n, log_r;
+  PowTab dom;
+  u64 offset;
+  xfe point[4], value[4], weight[4];
+};
+void coset_to_natural_run(Ctx &c, const u64 *in, u64 *out, size_t in_stride, size_t out_stride, int log_n, int log_r, int planes);
+void deinterleave3_run(Ctx &c, const u64 *in, u64 *out, size_t len, size_t ncols);
+void segment_chain_run(Ctx &c, const SegmentArgs &a);
+void xpow_vector_run(Ctx &c, xfe base, u64 *out, size_t stride, size_t len);
+void col_dot_run(Ctx &c, const u64 *cols, size_t col_stride, size_t ncols, size_t len, const u64 *xvec, size_t xvec_stride,
+                 size_t xvec_set_stride, int nvec, u64 *out);
+void weighted_colsum_run(Ctx &c, const u64 *cols, size_t col_stride, unsigned ncols, bool xfield, const u64 *d_w, size_t len, u64 *out,
+                         size_t out_stride, bool accumulate);
+void deep_run(Ctx &c, const DeepArgs &a);
+void fri_leaves_run(Ctx &c, const u64 *cw, size_t stride, size_t n, u64 *leaves);
+void fri_fold_run(Ctx &c, const u64 *in, size_t in_stride, size_t n, u64 offset_mont, xfe chal, u64 *out, size_t out_stride);
+void gather_rows_run(Ctx &c, const u64 *table, size_t col_stride, unsigned ncols, const unsigned *d_idx, unsigned nidx, int log_n, int log_r,
+                     u64 *d_out);
+void gather_digests_run(Ctx &c, const u64 *nodes, const unsigned *d_idx, unsigned nidx, u64 *d_out);
+void scale_by_powers_run(Ctx &c, u64 *v, size_t stride, int planes, size_t len, PowTab tab);
+
+}  // namespace tvm

@@ -37,6 +37,28 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+class Params(ctypes.Structure):
+    _fields_ = [("security_level", ctypes.c_uint32), ("log2_ldt_expansion_factor", ctypes.c_uint32), ("ldt_choice", ctypes.c_uint32)]
+
+
+class Domains(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in (
+        "padded_height", "num_trace_randomizers", "randomized_trace_len", "trace_len", "quotient_len", "ldt_len",
+        "ldt_offset", "num_collinearity_checks", "fri_num_rounds", "fri_last_round_max_degree",
+        "num_quotient_randomizer_coefficients")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class ClaimStruct(ctypes.Structure):
+    _fields_ = [("program_digest", ctypes.c_uint64 * 5), ("version", ctypes.c_uint32), ("input", _u64p),
+                ("num_input", ctypes.c_size_t), ("output", _u64p), ("num_output", ctypes.c_size_t)]
+
+
+AUX_CALLBACK = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _u64p, _u64p, _u64p)
+LDT_FRI = 1
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol declared in include/tvm_b200.h
@@ -62,6 +84,10 @@ _SIGNATURES = {
     "tvm_tip5_hash_varlen": (ctypes.c_int, [_u64p, ctypes.c_size_t, _u64p]),
     "tvm_merkle_build_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "tvm_merkle_build": (ctypes.c_int, [_vp, _u64p, ctypes.c_size_t, _u64p, _u64p]),
+    "tvm_derive_domains": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_uint64, ctypes.POINTER(Domains)]),
+    "tvm_prove": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, _u64p, _u64p,
+                                 AUX_CALLBACK, _vp, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
+    "tvm_last_prove_timings": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]),
     "tvm_air_quotient_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _u64p, _u64p, ctypes.c_uint,
                                             ctypes.c_uint, ctypes.c_uint64, _vp, ctypes.c_size_t]),
 }
@@ -94,6 +120,16 @@ def hash_varlen(words):
     if rc:
         raise TvmError(rc, lib().tvm_strerror(rc).decode())
     return [int(v) for v in d]
+
+
+def derive_domains(security_level=160, log2_expansion=2, padded_height=1 << 10, ldt_choice=LDT_FRI):
+    """Stark::{fri, max_degree, ...} + ProverDomains::derive; pure host function."""
+    p = Params(security_level, log2_expansion, ldt_choice)
+    d = Domains()
+    rc = lib().tvm_derive_domains(ctypes.byref(p), padded_height, ctypes.byref(d))
+    if rc:
+        raise TvmError(rc, lib().tvm_strerror(rc).decode())
+    return d.as_dict()
 
 
 class Backend:
@@ -173,6 +209,57 @@ class Backend:
         self._chk(self._l.tvm_merkle_build(self._h, lp, n, nodes.ctypes.data_as(_u64p) if want_nodes else None,
                                            root.ctypes.data_as(_u64p)))
         return (root, nodes) if want_nodes else root
+
+    def prove(self, claim, main_trace, main_rand, aux_provider, quot_rand, security_level=160, log2_expansion=2,
+              padded_height=None):
+        """Stark::prove (LdtChoice::Fri).  claim = (program_digest[5], input, output[, version]);
+        main_trace [379, n], main_rand [379, h] canonical uint64; aux_provider(challenges [63,3]) ->
+        (aux_trace [91, n, 3], aux_rand [91, h, 3]); quot_rand [(h+1)*5, 3].  Returns the proof words."""
+        mt, mtp = _np_u64(main_trace)
+        mr, mrp = _np_u64(main_rand)
+        qr, qrp = _np_u64(quot_rand)
+        n = mt.shape[1]
+        ph = padded_height or n
+        dom = derive_domains(security_level, log2_expansion, ph)
+        h = dom["num_trace_randomizers"]
+        assert mt.shape == (379, dom["trace_len"]) and mr.shape == (379, h), (mt.shape, mr.shape, dom)
+        assert qr.size == 3 * dom["num_quotient_randomizer_coefficients"]
+        digest, inp, out = claim[0], claim[1], claim[2]
+        version = claim[3] if len(claim) > 3 else 6
+        ia, iap = _np_u64(np.array(list(inp), dtype=np.uint64))
+        oa, oap = _np_u64(np.array(list(out), dtype=np.uint64))
+        cs = ClaimStruct((ctypes.c_uint64 * 5)(*[int(v) for v in digest]), version, iap, ia.size, oap, oa.size)
+        err = []
+
+        def cb(_user, ch_p, trace_p, rand_p):
+            try:
+                ch = np.ctypeslib.as_array(ch_p, shape=(63, 3)).copy()
+                t, r = aux_provider(ch)
+                np.ctypeslib.as_array(trace_p, shape=(91, n, 3))[...] = np.asarray(t, dtype=np.uint64).reshape(91, n, 3)
+                np.ctypeslib.as_array(rand_p, shape=(91, h, 3))[...] = np.asarray(r, dtype=np.uint64).reshape(91, h, 3)
+                return 0
+            except Exception as e:  # noqa: BLE001 - must not propagate through the C frame
+                err.append(e)
+                return 1
+
+        p = Params(security_level, log2_expansion, LDT_FRI)
+        cap = ctypes.c_size_t(0)
+        est = 64 + dom["num_collinearity_checks"] * (379 + 273 + 15 + 3 * 40 * (dom["fri_num_rounds"] + 4)) + \
+            3 * (dom["ldt_len"] >> dom["fri_num_rounds"]) * 2 + 3 * 470 * 2 + 4096
+        buf = np.empty(est, dtype=np.uint64)
+        cap.value = est
+        rc = self._l.tvm_prove(self._h, ctypes.byref(p), ctypes.byref(cs), ph, mtp, mrp, AUX_CALLBACK(cb), None, qrp,
+                               buf.ctypes.data_as(_u64p), ctypes.byref(cap))
+        if err:
+            raise err[0]
+        self._chk(rc)
+        return buf[:cap.value].copy()
+
+    def last_prove_timings(self):
+        names = (ctypes.c_char_p * 16)()
+        ms = (ctypes.c_float * 16)()
+        k = self._l.tvm_last_prove_timings(self._h, names, ms)
+        return [(names[i].decode(), float(ms[i])) for i in range(k)]
 
     # ---- device-pointer entry points (torch tensors, int64 view of u64, Montgomery) -------
     @staticmethod
