@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py — Stark::prove() wall-clock at padded height 2^20 on B200 (BASELINE.json metric).
+
+One "step" = one complete prove() of a synthetic instance (uniform random main / aux traces and
+randomizers of the real shape: 379 main columns, 91 aux columns, trace length 2^20, LDT domain 2^23,
+security 160, expansion 4, FRI) through the public C ABI call `tvm_prove` with HOST buffers
+(pinned), i.e. host->device copies of the traces are inside the timed region (`e2e`).
+`value` is the same prove() with the host->device copies subtracted (device-side stage timers),
+i.e. the inputs-resident-in-HBM figure.  Trace generation (VM, table fill/extend) is outside the
+hot path and outside the timed region: the aux-trace callback only hands back a
+pointer to pre-generated pinned memory.
+
+`--impl reference` times the CPU restatement of the same path (oracle/, C + OpenMP on all host
+cores) on a bounded sample and extrapolates to the full prove — the Rust reference cannot be built
+in this image (no cargo), see DESIGN.md.
+
+N > 1 (torchrun): independent replicas, one proof per rank (weak scaling, no collective on the data
+path); value = time per proof = T / N.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "triton-vm_b200", "py"))
+
+import numpy as np  # noqa: E402
+
+P = (1 << 64) - (1 << 32) + 1
+NM, NA = 379, 91
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def algorithmic_lde_bytes(n, ncols):
+    # column LDE reads 8 B per trace element and writes 64 B (8x blow-up): 72 B per trace element
+    return 72 * n * ncols
+
+
+# ---- CPU baseline (oracle port) --------------------------------------------------------------------
+def cpu_baseline(log2_height, budget_note=True):
+    """Times the C/OpenMP oracle on a bounded sample of the 2^log2_height workload and extrapolates.
+    Returns (estimated prove ms, cores, sample description, per-stage dict)."""
+    from oracle import corc
+    rng = np.random.default_rng(7)
+    n = 1 << log2_height
+    N = 8 * n
+    cores = corc.num_threads()
+    stages = {}
+    # LDE: K full-size columns (iNTT n + NTT 8n each), OpenMP over columns like rayon
+    K = max(cores, 8)
+    tr = rng.integers(0, P, size=(K, n), dtype=np.uint64)
+    rd = rng.integers(0, P, size=(K, 198), dtype=np.uint64)
+    t0 = time.perf_counter()
+    corc.lde_table(tr, rd, 7, log2_height + 3, mont_io=True)
+    per_col = (time.perf_counter() - t0) / K
+    stages["LDE (652 table + 24 quotient/combination columns)"] = per_col * 676 * 1e3
+    # Tip5 row hashing: sample rows, all columns
+    rows = 1 << 13
+    for name, ncols in (("main", 379), ("aux", 273), ("quot", 15)):
+        tab = rng.integers(0, P, size=(ncols, rows), dtype=np.uint64)
+        t0 = time.perf_counter()
+        corc.hash_rows_colmajor(tab, mont_io=True)
+        stages[f"hash rows ({name})"] = (time.perf_counter() - t0) / rows * N * 1e3
+    leaves = rng.integers(0, P, size=(1 << 16, 5), dtype=np.uint64)
+    t0 = time.perf_counter()
+    corc.merkle_build(leaves, mont_io=True)
+    per_node = (time.perf_counter() - t0) / (1 << 16)
+    stages["Merkle trees (3 tables + FRI)"] = per_node * (3 * N + 2 * N) * 1e3
+    # AIR quotient
+    arows = 1 << 11
+    main = rng.integers(0, P, size=(379, arows), dtype=np.uint64)
+    aux = rng.integers(0, P, size=(270, arows), dtype=np.uint64)
+    ch = [(1 + i, 2 + i, 3 + i) for i in range(63)]
+    w = [(5 + i, 6 + i, 7 + i) for i in range(604)]
+    t0 = time.perf_counter()
+    corc.air_quotient(main, aux, 8, 7, ch, w)
+    stages["AIR quotient"] = (time.perf_counter() - t0) / arows * N * 1e3
+    total = sum(stages.values())
+    sample = (f"{K} full-size LDE columns of 2^{log2_height}->2^{log2_height + 3}; Tip5 rows on 2^13 rows x (379,273,15) cols; "
+              f"Merkle on 2^16 leaves; AIR on 2^11 rows; each scaled linearly to the full prove "
+              f"(OOD rows, DEEP, FRI folds not included: < 5% of the GPU path)")
+    return total, cores, sample, stages
+
+
+# ---- clocks ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- GPU arm -------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import tvm_b200
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dom = tvm_b200.derive_domains(160, 2, 1 << args.log2_height)
+    n, h = dom["trace_len"], dom["num_trace_randomizers"]
+    nqr = dom["num_quotient_randomizer_coefficients"]
+
+    def pinned(shape):
+        t = torch.empty(shape, dtype=torch.int64, pin_memory=True)
+        return t, t.numpy().view(np.uint64)
+
+    rng = np.random.default_rng(0x5452_4954 + rank)
+    keep = []
+
+    def fill(shape):
+        t, a = pinned(shape)
+        flat = a.reshape(-1)
+        step = 1 << 24
+        for s in range(0, flat.size, step):
+            flat[s:s + step] = rng.integers(0, P, size=min(step, flat.size - s), dtype=np.uint64)
+        keep.append(t)
+        return a
+
+    main_trace, main_rand = fill((NM, n)), fill((NM, h))
+    aux_trace, aux_rand = fill((NA, n, 3)), fill((NA, h, 3))
+    quot_rand = fill((nqr, 3))
+    claim = ([1, 2, 3, 4, 5], [7, 8, 9], [10])
+    b = tvm_b200.Backend(local_rank)
+
+    def aux_provider(_challenges):
+        return aux_trace, aux_rand          # pre-generated: tracegen is outside the hot path
+
+    def step():
+        return b.prove(claim, main_trace, main_rand, aux_provider, quot_rand, 160, 2, 1 << args.log2_height)
+
+    for _ in range(args.warmup):
+        proof = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = b.launches
+    stage_acc = {}
+    start = torch.cuda.Event(enable_timing=True); end = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    start.record()
+    for _ in range(args.steps):
+        proof = step()
+        for name, ms in b.last_prove_timings():
+            stage_acc[name] = stage_acc.get(name, 0.0) + ms
+    end.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([wall_ms], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall_ms = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = b.launches - launches0
+    if rank != 0:
+        return
+    stages = {k: v / args.steps for k, v in stage_acc.items()}
+    e2e_ms = wall_ms / args.steps
+    h2d_ms = stages.get("H2D(main)", 0.0) + stages.get("H2D(aux)", 0.0)
+    device_ms = e2e_ms - h2d_ms
+    lde_ms = stages.get("LDE(main)", 0.0) + stages.get("LDE(aux)", 0.0)
+    peaks = measured_peaks()
+    peak = peaks["hbm_gbs"] if peaks else 6650.0
+    alg = algorithmic_lde_bytes(n, NM + 3 * NA)
+    achieved = alg / (lde_ms * 1e-3) / 1e9 if lde_ms else 0.0
+    out = {
+        "metric": "prove() ms @ padded height 2^%d; NTT GF(p) elems/s vs HBM roofline" % args.log2_height,
+        "value": device_ms / world, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": e2e_ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": f"Stark::prove (LdtChoice::Fri, security 160, expansion 4) at padded height 2^{args.log2_height}: "
+                               f"379 main + 91 aux columns, trace domain 2^{args.log2_height}, LDT domain 2^{args.log2_height + 3}",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one proof per GPU)",
+                   "l2": "inputs (GBs) larger than L2", "h2d_excluded_from_value_ms": h2d_ms},
+        "e2e": {"value": e2e_ms / world, "unit": "ms",
+                "h2d_bytes_per_step": int(main_trace.nbytes + main_rand.nbytes + aux_trace.nbytes + aux_rand.nbytes + quot_rand.nbytes),
+                "d2h_bytes_per_step": int(proof.nbytes)},
+        "gpu_launches": int(launches),
+        "stages_ms": {k: round(v, 3) for k, v in stages.items()},
+        "roofline": {"bound": "hbm", "kernel": "coset LDE (ntt_pass_a/ntt_pass_b) of the 652 table columns",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                     "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                     "algorithmic_bytes": alg,
+                     "ntt_gelems_per_s": (NM + 3 * NA) * 8 * n / (lde_ms * 1e-3) / 1e9 if lde_ms else None},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        total, cores, sample, cstages = cpu_baseline(args.log2_height)
+        out["cpu_baseline"] = {"value": total, "unit": "ms", "cores": cores, "kind": "port", "sample": sample,
+                               "stages_ms": {k: round(v, 1) for k, v in cstages.items()}}
+    print(json.dumps(out))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, args.warmup // 3)):
+        cpu_baseline(min(args.log2_height, 16))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        total, cores, sample, stages = cpu_baseline(args.log2_height)
+        vals.append(total)
+    per_step = (time.perf_counter() - t0) * 1e3 / args.steps
+    v = float(np.median(vals))
+    print(json.dumps({
+        "impl": "reference", "metric": "prove() ms @ padded height 2^%d; NTT GF(p) elems/s vs HBM roofline" % args.log2_height,
+        "value": v, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step,
+        "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"Stark::prove (FRI) at padded height 2^{args.log2_height}, CPU restatement (oracle/, C + OpenMP), "
+                               "extrapolated from a bounded sample per step"},
+        "cpu_baseline": {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-height", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,13 +131,14 @@ int tvm_derive_domains(const tvm_params *params, uint64_t padded_height, tvm_dom
  *                                      master_table.rs:881-983, trace_table is column-major: 888)
  *      main_rand    [379][h]          trace-randomizer coefficients per column (master_table.rs:423-434)
  *      aux_cb       called once with the 63 challenges (canonical X-field, challenges.rs:88-135); must
- *                   fill aux_trace [91][trace_len][3] (MasterMainTable::extend, 1006-1075, incl. the
- *                   batch-randomizer column 90) and aux_rand [91][h][3]
+ *                   provide aux_trace [91][trace_len][3] (MasterMainTable::extend, 1006-1075, incl. the
+ *                   batch-randomizer column 90) and aux_rand [91][h][3] by setting *aux_trace / *aux_rand
+ *                   to caller-owned (ideally pinned) buffers that stay valid until tvm_prove returns
  *      quot_rand    [(h+1)*5][3]      quotient-segment randomizer (stark.rs:1316-1322)
  *      proof_out    receives Proof.0 (Vec<BFieldElement>, canonical); *proof_len in: capacity, out: needed
  *                   length (TVM_ERR_INVALID_ARG with *proof_len set if the capacity is too small).
  *      All randomness is the caller's: the backend is a deterministic function of its inputs. --- */
-typedef int (*tvm_aux_callback)(void *user, const uint64_t *challenges /*[63][3]*/, uint64_t *aux_trace, uint64_t *aux_rand);
+typedef int (*tvm_aux_callback)(void *user, const uint64_t *challenges /*[63][3]*/, uint64_t **aux_trace, uint64_t **aux_rand);
 typedef struct tvm_claim {
   uint64_t program_digest[5];
   uint32_t version;
@@ -148,7 +149,7 @@ int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, ui
               const uint64_t *main_trace, const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user,
               const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len);
 /* device time per stage of the last tvm_prove on this ctx, reference profiler labels; returns #stages */
-int tvm_last_prove_timings(const tvm_ctx *ctx, const char **names /*[16]*/, float *ms /*[16]*/);
+int tvm_last_prove_timings(const tvm_ctx *ctx, const char **names /*[20]*/, float *ms /*[20]*/);
 
 #ifdef __cplusplus
 }

@@ -381,7 +381,7 @@ int tvm_last_prove_timings(const tvm_ctx *ctx, const char **names, float *ms) {
   if (!ctx) return 0;
   int n = 0;
   for (auto &st : ctx->timings.stages) {
-    if (n >= 16) break;
+    if (n >= 20) break;
     if (names) names[n] = st.first.c_str();
     if (ms) ms[n] = st.second;
     n++;

@@ -175,7 +175,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   const u64 off = to_mont(d.ldt_offset);
   const size_t NM = TVM_NUM_MAIN_COLUMNS, NA = TVM_NUM_AUX_COLUMNS, NA3 = 3 * NA;
   const size_t tmp_cols = 16;
-  cudaEvent_t ev[16];
+  cudaEvent_t ev[20];
   int nev = 0;
   auto mark = [&]() {
     if (!timings) return;
@@ -197,6 +197,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   u64 *d_main_rand = d_main_trace + NM * n;
   TVM_CUDA(cudaMemcpyAsync(d_main_trace, h_main_trace, NM * n * 8, cudaMemcpyHostToDevice, c.stream));
   TVM_CUDA(cudaMemcpyAsync(d_main_rand, h_main_rand, NM * h * 8, cudaMemcpyHostToDevice, c.stream));
+  mark();  // H2D(main)
   to_mont_run(c, d_main_trace, NM * n + NM * h);
   u64 *d_main_coef = mem.words(NM * 2 * n);
   u64 *d_main_lde = mem.words(NM * N);
@@ -233,14 +234,16 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   }
 
   // ---- auxiliary table (stark.rs:380-392) ---------------------------------------------------------------
-  u64 *h_aux = nullptr;
-  TVM_CUDA(cudaMallocHost(&h_aux, (NA * n * 3 + NA * h * 3) * 8));
-  struct HostFree { u64 *p; ~HostFree() { cudaFreeHost(p); } } host_free{h_aux};
   if (!aux_cb) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback missing"};
-  if (int crc = aux_cb(aux_user, ch_canon.data(), h_aux, h_aux + NA * n * 3)) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback failed: " + std::to_string(crc)};
-  mark();  // 3: extend (caller)
+  u64 *h_aux_trace = nullptr, *h_aux_rand = nullptr;   // the callee hands back pointers to its own buffers
+  TVM_CUDA(cudaStreamSynchronize(c.stream));
+  if (int crc = aux_cb(aux_user, ch_canon.data(), &h_aux_trace, &h_aux_rand)) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback failed: " + std::to_string(crc)};
+  if (!h_aux_trace || !h_aux_rand) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback returned a null buffer"};
+  mark();  // extend (caller)
   u64 *d_aux_in = mem.words(NA * n * 3 + NA * h * 3);
-  TVM_CUDA(cudaMemcpyAsync(d_aux_in, h_aux, (NA * n * 3 + NA * h * 3) * 8, cudaMemcpyHostToDevice, c.stream));
+  TVM_CUDA(cudaMemcpyAsync(d_aux_in, h_aux_trace, NA * n * 3 * 8, cudaMemcpyHostToDevice, c.stream));
+  TVM_CUDA(cudaMemcpyAsync(d_aux_in + NA * n * 3, h_aux_rand, NA * h * 3 * 8, cudaMemcpyHostToDevice, c.stream));
+  mark();  // H2D(aux)
   to_mont_run(c, d_aux_in, NA * n * 3 + NA * h * 3);
   u64 *d_aux_trace = mem.words(NA3 * n + NA3 * h);
   u64 *d_aux_rand = d_aux_trace + NA3 * n;
@@ -525,8 +528,9 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   proof = ps.encode();
   if (timings) {
     TVM_CUDA(cudaStreamSynchronize(c.stream));
-    static const char *names[] = {"LDE(main)", "Merkle(main)", "extend(caller)", "LDE(aux)", "Merkle(aux)", "quotient(AIR)",
-                                  "quotient LDE", "Merkle(quot)", "OOD rows", "linear combination+DEEP", "LDT(FRI)", "open"};
+    static const char *names[] = {"H2D(main)", "LDE(main)", "Merkle(main)", "extend(caller)", "H2D(aux)", "LDE(aux)", "Merkle(aux)",
+                                  "quotient(AIR)", "quotient LDE", "Merkle(quot)", "OOD rows", "linear combination+DEEP", "LDT(FRI)",
+                                  "open"};
     timings->stages.clear();
     for (int i = 1; i < nev; i++) {
       float ms = 0;

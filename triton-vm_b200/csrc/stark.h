@@ -26,8 +26,10 @@ struct ClaimView {            // proof.rs:68-88, canonical words
   const u64 *input; size_t num_input;
   const u64 *output; size_t num_output;
 };
-// fills aux_trace [91][n][3] and aux_rand [91][h][3] (canonical) given the 63 challenges (canonical)
-typedef int (*AuxCallback)(void *user, const u64 *challenges, u64 *aux_trace, u64 *aux_rand);
+// Given the 63 challenges (canonical), provides aux_trace [91][n][3] and aux_rand [91][h][3] (canonical).
+// The callee sets *aux_trace / *aux_rand to its own (ideally pinned) buffers, which must stay valid
+// until prove returns (zero copy: the library reads them straight into the H2D transfer).
+typedef int (*AuxCallback)(void *user, const u64 *challenges, u64 **aux_trace, u64 **aux_rand);
 
 struct ProveTimings {
   std::vector<std::pair<std::string, float>> stages;   // device ms per stage, reference profiler labels

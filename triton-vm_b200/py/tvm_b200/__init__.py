@@ -56,7 +56,7 @@ class ClaimStruct(ctypes.Structure):
                 ("num_input", ctypes.c_size_t), ("output", _u64p), ("num_output", ctypes.c_size_t)]
 
 
-AUX_CALLBACK = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _u64p, _u64p, _u64p)
+AUX_CALLBACK = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _u64p, ctypes.POINTER(_u64p), ctypes.POINTER(_u64p))
 LDT_FRI = 1
 
 _lib = None
@@ -231,12 +231,17 @@ class Backend:
         cs = ClaimStruct((ctypes.c_uint64 * 5)(*[int(v) for v in digest]), version, iap, ia.size, oap, oa.size)
         err = []
 
-        def cb(_user, ch_p, trace_p, rand_p):
+        keep = []
+
+        def cb(_user, ch_p, trace_pp, rand_pp):
             try:
                 ch = np.ctypeslib.as_array(ch_p, shape=(63, 3)).copy()
                 t, r = aux_provider(ch)
-                np.ctypeslib.as_array(trace_p, shape=(91, n, 3))[...] = np.asarray(t, dtype=np.uint64).reshape(91, n, 3)
-                np.ctypeslib.as_array(rand_p, shape=(91, h, 3))[...] = np.asarray(r, dtype=np.uint64).reshape(91, h, 3)
+                t = np.ascontiguousarray(t, dtype=np.uint64).reshape(91, n, 3)
+                r = np.ascontiguousarray(r, dtype=np.uint64).reshape(91, h, 3)
+                keep.extend([t, r])           # redirect to the caller's buffers (zero copy)
+                trace_pp[0] = t.ctypes.data_as(_u64p)
+                rand_pp[0] = r.ctypes.data_as(_u64p)
                 return 0
             except Exception as e:  # noqa: BLE001 - must not propagate through the C frame
                 err.append(e)
@@ -256,8 +261,8 @@ class Backend:
         return buf[:cap.value].copy()
 
     def last_prove_timings(self):
-        names = (ctypes.c_char_p * 16)()
-        ms = (ctypes.c_float * 16)()
+        names = (ctypes.c_char_p * 20)()
+        ms = (ctypes.c_float * 20)()
         k = self._l.tvm_last_prove_timings(self._h, names, ms)
         return [(names[i].decode(), float(ms[i])) for i in range(k)]
 
