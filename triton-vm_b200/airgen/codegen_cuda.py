@@ -24,6 +24,7 @@ from .circuit import P, reachable_postorder
 R = (1 << 64) % P
 OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "air_gen")
 CHUNK_COST_BUDGET = 1300.0
+SYNC_EVERY = int(os.environ.get("TVM_AIR_SYNC_EVERY", "40"))
 
 
 def mont(v):
@@ -147,8 +148,9 @@ __constant__ u64 c_ch[189];  // 63 challenges (X-field, Montgomery)
 }
 
 __global__ void __launch_bounds__(AIR_THREADS) %(kname)s(AirArgs a) {
-  const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= a.nrows) return;
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = m < a.nrows;
+  if (!active) m = 0;              // keep every thread alive for the block-wide barriers below
   const size_t n = (size_t)1 << a.log_n;
   const size_t coset = m >> a.log_n, k = m & (n - 1);
   const size_t m_next = (coset << a.log_n) | ((k + 1) & (n - 1));
@@ -177,7 +179,12 @@ def emit_chunk(air, idx, cat, items):
         em.emit_node(n)
     kname = f"air_chunk_{idx:02d}_{cat}"
     src = [HEADER % {"nw": 3 * len(items), "kname": kname}]
-    src.append("  " + "\n  ".join(em.lines))
+    body = []
+    for k, line in enumerate(em.lines):
+        body.append(line)
+        if SYNC_EVERY and (k + 1) % SYNC_EVERY == 0:
+            body.append("__syncthreads();   // instruction-fetch locality: the CTA's warps share one I-cache window")
+    src.append("  " + "\n  ".join(body))
     src.append("  xfe acc = xzero();")
     for slot, (_, c) in enumerate(items):
         w = f"xmake(c_w[{3 * slot}], c_w[{3 * slot + 1}], c_w[{3 * slot + 2}])"
@@ -186,7 +193,7 @@ def emit_chunk(air, idx, cat, items):
             src.append(f"  acc = xadd(acc, xmul({w}, {nm}));")
         else:
             src.append(f"  acc = xadd(acc, xmulb({w}, {nm}));")
-    src.append(f"  air_accumulate_{cat}(a, m, coset, k, acc);")
+    src.append(f"  if (active) air_accumulate_{cat}(a, m, coset, k, acc);")
     src.append("}")
     idxs = [j for j, _ in items]
     assert idxs == list(range(idxs[0], idxs[0] + len(idxs)))

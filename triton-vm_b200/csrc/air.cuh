@@ -9,7 +9,10 @@
 
 namespace tvm {
 
-static constexpr int AIR_THREADS = 128;
+#ifndef TVM_AIR_THREADS
+#define TVM_AIR_THREADS 256
+#endif
+static constexpr int AIR_THREADS = TVM_AIR_THREADS;
 static constexpr int AIR_MAX_COSETS = 64;
 
 struct AirArgs {

@@ -50,6 +50,12 @@ struct Ctx {
 
   // scratch arena (grown on demand, reused)
   DevBuf scratch[4];
+  // block pool for prove(): cudaMalloc/cudaFree are synchronising and slow (ms each for GB-sized
+  // blocks); blocks are recycled across prove() calls instead.
+  std::multimap<size_t, void *> pool_free;
+  std::map<void *, size_t> pool_live;
+  void *pool_alloc(size_t bytes);
+  void pool_release(void *p);
 
   ~Ctx();
   void *alloc(size_t bytes);  // tracked device allocation (freed with the ctx)

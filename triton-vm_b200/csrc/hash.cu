@@ -10,6 +10,7 @@
 // whole absorb loop (all 5 rounds fused; no state traffic), tables stored column-major so that
 // a warp's loads of one column are a single coalesced 256-byte segment.  The S-box lookup table
 // lives in shared memory; the round constants in constant memory (warp-uniform index).
+#include <cstdlib>
 #include "ctx.h"
 #include "tip5.cuh"
 #include "tip5_constants.inc"
@@ -131,10 +132,114 @@ __global__ void xfe_leaves_kernel(const u64 *cw, size_t stride, size_t n, u64 *l
   d[0] = cw[i]; d[1] = cw[stride + i]; d[2] = cw[2 * stride + i]; d[3] = 0; d[4] = 0;
 }
 
+
+// ---- warp-resident variant: 4 lanes per row ---------------------------------------------------
+// Lane l of a 4-lane group holds state elements {l, l+4, l+8, l+12}: every lane has one
+// split-and-lookup element (slot 0) and three x^7 elements, so the S-box layer is divergence-free.
+// The circulant MDS product gathers the 16 inputs by warp shuffle in a lane-rotated order
+// (X[k] = x_{(k+l) mod 16}), which makes the matrix constants identical for all lanes
+// (y_{l+4i} = sum_k M[(4i-k) mod 16] X[k]).  Compared with one thread per row this keeps the round
+// body ~4x smaller (instruction-cache resident) and the register count low (more resident warps).
+__device__ __forceinline__ u64 shfl64(u64 v, int src) {
+  unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
+  unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+  return ((u64)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void tip5_perm_quad(u64 (&s)[4], int l, int group_base, const unsigned char *lut, const u64 *rc_smem) {
+  constexpr unsigned short MDS[16] = TVM_MDS_COL;
+#pragma unroll 1
+  for (int rnd = 0; rnd < TIP5_ROUNDS; rnd++) {
+    {  // slot 0: split-and-lookup
+      u64 v = s[0], o = 0;
+#pragma unroll
+      for (int b = 0; b < 8; b++) o |= (u64)lut[(unsigned)((v >> (8 * b)) & 0xFF)] << (8 * b);
+      s[0] = o;
+    }
+#pragma unroll
+    for (int i = 1; i < 4; i++) {
+      u64 x = s[i], x2 = fmul(x, x), x3 = fmul(x2, x), x4 = fmul(x2, x2);
+      s[i] = fmul(x3, x4);
+    }
+    u64 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      // this lane provides, to the lane l' that wants element (k + l') mod 16 with (k + l') mod 4 == l,
+      // its slot ((k + ((l - k) & 3)) & 15) >> 2
+      const int wrap = (((l - k) & 3) + (k & 3)) >> 2;          // 0 or 1
+      const u64 provide = wrap ? s[((k >> 2) + 1) & 3] : s[k >> 2];
+      const u64 X = shfl64(provide, group_base + ((k + l) & 3));
+      const u64 xl = X & 0xFFFFFFFFULL, xh = X >> 32;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const u64 m = MDS[(4 * i - k) & 15];
+        lo[i] += m * xl;
+        hi[i] += m * xh;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      u64 lsum = lo[i] + (hi[i] << 32);
+      u64 carry = lsum < lo[i];
+      u64 h = (hi[i] >> 32) + carry;
+      s[i] = fadd(reduce96(lsum, h), rc_smem[16 * rnd + l + 4 * i]);
+    }
+  }
+}
+
+static constexpr int HASHQ_THREADS = 128;
+__global__ void __launch_bounds__(HASHQ_THREADS) tip5_hash_rows_quad_kernel(HashRowsParams p) {
+  __shared__ unsigned char lut[256];
+  __shared__ u64 rc[80];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
+  for (int i = threadIdx.x; i < 80; i += blockDim.x) rc[i] = c_tip5_rc[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l = lane & 3, group_base = lane & ~3;
+  size_t m = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;   // one row per 4 lanes
+  const bool active = m < p.nrows;
+  if (!active) m = p.nrows - 1;                                     // keep the quad alive for the shuffles
+  size_t per = p.nrows >> p.log_r;
+  size_t coset = m / per, k = m - coset * per;
+  size_t row = coset + (k << p.log_r);
+  const u64 *base = p.table + m;
+  u64 s[4] = {0, 0, 0, 0};
+  unsigned c = 0;
+  for (; c + 10 <= p.ncols; c += 10) {
+    s[0] = base[(size_t)(c + l) * p.col_stride];
+    s[1] = base[(size_t)(c + l + 4) * p.col_stride];
+    if (l < 2) s[2] = base[(size_t)(c + l + 8) * p.col_stride];
+    tip5_perm_quad(s, l, group_base, lut, rc);
+  }
+  unsigned rem = p.ncols - c;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    unsigned e = (unsigned)(l + 4 * i);
+    if (e < 10) {
+      u64 v = 0;
+      if (e < rem) v = base[(size_t)(c + e) * p.col_stride];
+      else if (e == rem) v = MONT_ONE;
+      s[i] = v;
+    }
+  }
+  tip5_perm_quad(s, l, group_base, lut, rc);
+  if (active) {
+    u64 *d = p.digests + row * 5;
+    d[l] = s[0];
+    if (l == 0) d[4] = s[1];
+  }
+}
+
 void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, unsigned ncols, int log_r, u64 *digests) {
   HashRowsParams p{table, col_stride, nrows, ncols, log_r, digests};
-  unsigned grid = (unsigned)((nrows + HASH_THREADS - 1) / HASH_THREADS);
-  tip5_hash_rows_kernel<<<grid, HASH_THREADS, 0, c.stream>>>(p);
+  static const bool use_thread_per_row = getenv("TVM_TIP5_THREAD_PER_ROW") != nullptr;
+  if (use_thread_per_row) {
+    unsigned grid = (unsigned)((nrows + HASH_THREADS - 1) / HASH_THREADS);
+    tip5_hash_rows_kernel<<<grid, HASH_THREADS, 0, c.stream>>>(p);
+  } else {
+    size_t threads = nrows * 4;
+    unsigned grid = (unsigned)((threads + HASHQ_THREADS - 1) / HASHQ_THREADS);
+    tip5_hash_rows_quad_kernel<<<grid, HASHQ_THREADS, 0, c.stream>>>(p);
+  }
   c.launches++;
   TVM_CUDA(cudaGetLastError());
 }

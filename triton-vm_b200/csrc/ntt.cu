@@ -240,7 +240,38 @@ u64 root_of_unity_mont(unsigned log2n) {
   return r;
 }
 
+void *Ctx::pool_alloc(size_t bytes) {
+  if (!bytes) bytes = 8;
+  auto it = pool_free.lower_bound(bytes);
+  if (it != pool_free.end() && it->first <= bytes + bytes / 4 + 4096) {
+    void *p = it->second;
+    pool_live[p] = it->first;
+    pool_free.erase(it);
+    return p;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    // give cached blocks back to the driver and retry once
+    cudaGetLastError();
+    for (auto &kv : pool_free) cudaFree(kv.second);
+    pool_free.clear();
+    e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
+  }
+  pool_live[p] = bytes;
+  return p;
+}
+void Ctx::pool_release(void *p) {
+  auto it = pool_live.find(p);
+  if (it == pool_live.end()) return;
+  pool_free.emplace(it->second, p);
+  pool_live.erase(it);
+}
+
 Ctx::~Ctx() {
+  for (auto &kv : pool_free) cudaFree(kv.second);
+  for (auto &kv : pool_live) cudaFree(kv.first);
   for (void *p : owned) cudaFree(p);
   for (auto &s : scratch)
     if (s.p) cudaFree(s.p);

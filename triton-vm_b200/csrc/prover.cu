@@ -83,19 +83,22 @@ int stark_derive(const StarkParams &sp, size_t padded_height, StarkDerived &d) {
 
 namespace {
 
-struct DevMem {   // RAII device buffers of one prove() call
+struct DevMem {   // RAII device buffers of one prove() call, recycled through the context's block pool
+  Ctx &c;
   std::vector<void *> ptrs;
-  ~DevMem() { for (void *p : ptrs) cudaFree(p); }
+  explicit DevMem(Ctx &ctx) : c(ctx) {}
+  ~DevMem() {
+    cudaStreamSynchronize(c.stream);
+    for (void *p : ptrs) c.pool_release(p);
+  }
   u64 *words(size_t n) {
-    void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(u64));
-    if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
+    void *p = c.pool_alloc((n ? n : 1) * sizeof(u64));
     ptrs.push_back(p);
     return (u64 *)p;
   }
-  void release(void *p) {
+  void release(void *p) {   // stream-ordered reuse: later kernels on the same stream see earlier ones complete
     for (size_t i = 0; i < ptrs.size(); i++)
-      if (ptrs[i] == p) { cudaFree(p); ptrs.erase(ptrs.begin() + i); return; }
+      if (ptrs[i] == p) { c.pool_release(p); ptrs.erase(ptrs.begin() + i); return; }
   }
 };
 
@@ -184,7 +187,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     nev++;
   };
 
-  DevMem mem;
+  DevMem mem(c);
   ProofStream ps;
   ps.alter_fiat_shamir_state_with(encode_claim(claim.program_digest, claim.version, claim.input, claim.num_input, claim.output,
                                                claim.num_output));
@@ -342,8 +345,9 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   const xfe pts[4] = {alpha, alpha_next, alpha_pow, alpha_zeta_pow};
   for (int t = 0; t < 4; t++) xpow_vector_run(c, xmulb(pts[t], off_inv), d_pw + (size_t)t * 3 * clen, clen, clen);
   u64 *d_dots = mem.words((NM + NA3 + 15 + 9) * 2 * 3);
-  col_dot_run(c, d_main_coef, clen, NM, clen, d_pw, clen, 3 * clen, 2, d_dots);
-  col_dot_run(c, d_aux_coef, clen, NA3, clen, d_pw, clen, 3 * clen, 2, d_dots + NM * 6);
+  const size_t used = n + h;   // table interpolants have n + h non-zero (pre-scaled) coefficients
+  col_dot_run(c, d_main_coef, clen, NM, used, d_pw, clen, 3 * clen, 2, d_dots);
+  col_dot_run(c, d_aux_coef, clen, NA3, used, d_pw, clen, 3 * clen, 2, d_dots + NM * 6);
   col_dot_run(c, d_seg_coef, seg_len, 15, seg_len, d_pw + 2 * 3 * clen, clen, 3 * clen, 2, d_dots + (NM + NA3) * 6);
   std::vector<u64> dots = d2h(c, d_dots, (NM + NA3 + 15) * 6);
   auto dot_at = [&](size_t col, int v) { const u64 *p = &dots[(col * 2 + v) * 3]; return xmake(p[0], p[1], p[2]); };
@@ -391,8 +395,9 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   TVM_CUDA(cudaMemcpyAsync(d_wts, wts.data(), wts.size() * 8, cudaMemcpyHostToDevice, c.stream));
   TVM_CUDA(cudaStreamSynchronize(c.stream));
   u64 *d_cpr = mem.words(9 * clen);    // combination, p, r polynomials (pre-scaled), 3 planes each
-  weighted_colsum_run(c, d_main_coef, clen, (unsigned)NM, false, d_wts, clen, d_cpr, clen, false);
-  weighted_colsum_run(c, d_aux_coef, clen, (unsigned)NA, true, d_wts + 3 * NM, clen, d_cpr, clen, true);
+  TVM_CUDA(cudaMemsetAsync(d_cpr, 0, 3 * clen * 8, c.stream));
+  weighted_colsum_run(c, d_main_coef, clen, (unsigned)NM, false, d_wts, used, d_cpr, clen, false);
+  weighted_colsum_run(c, d_aux_coef, clen, (unsigned)NA, true, d_wts + 3 * NM, used, d_cpr, clen, true);
   weighted_colsum_run(c, d_seg_coef, seg_len, 5, true, d_wts + 3 * (NM + NA), seg_len, d_cpr + 3 * clen, clen, false);
   weighted_colsum_run(c, d_seg_coef, seg_len, 5, true, d_wts + 3 * (NM + NA + 5), seg_len, d_cpr + 6 * clen, clen, false);
   // values at the out-of-domain points

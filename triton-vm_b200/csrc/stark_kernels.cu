@@ -189,12 +189,23 @@ __global__ void deep_kernel(DeepArgs a) {
 #pragma unroll
   for (int v = 0; v < 3; v++) f[v] = xmake(p[(3 * v) * a.cw_stride], p[(3 * v + 1) * a.cw_stride], p[(3 * v + 2) * a.cw_stride]);
   const int src[4] = {0, 0, 1, 2};
-  xfe acc = xzero();
+  // one X-field inversion for the four denominators (Montgomery's trick)
+  xfe den[4], pre[4];
+  xfe run = xone();
 #pragma unroll
   for (int t = 0; t < 4; t++) {
-    xfe den = xneg(a.point[t]);
-    den.c0 = fadd(den.c0, x);                       // x - point
-    xfe term = xmul(xsub(f[src[t]], a.value[t]), xinv(den));
+    den[t] = xneg(a.point[t]);
+    den[t].c0 = fadd(den[t].c0, x);                 // x - point
+    pre[t] = run;
+    run = xmul(run, den[t]);
+  }
+  xfe inv = xinv(run);
+  xfe acc = xzero();
+#pragma unroll
+  for (int t = 3; t >= 0; t--) {
+    xfe dinv = xmul(inv, pre[t]);
+    inv = xmul(inv, den[t]);
+    xfe term = xmul(xsub(f[src[t]], a.value[t]), dinv);
     acc = xadd(acc, xmul(term, a.weight[t]));
   }
   a.out[i] = acc.c0; a.out[a.out_stride + i] = acc.c1; a.out[2 * a.out_stride + i] = acc.c2;
