@@ -1,0 +1,94 @@
+#!/usr/bin/env python3
+"""Turn ncu output brought back in gpurun_out/ into the small text summaries committed under profiles/.
+
+  summarize_ncu.py launches <launches.csv> <out.md>     per-kernel launch count / total time / share of the step
+  summarize_ncu.py report   <file.ncu-rep> <out.md>     key metrics of one `ncu --set full` capture
+
+Only reads files; the ncu CLI in this image does the .ncu-rep decoding (`ncu -i ... --page raw --csv`).
+"""
+import csv
+import io
+import re
+import subprocess
+import sys
+from collections import OrderedDict
+
+KEY_METRICS = [
+    "gpu__time_duration.sum",
+    "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_static", "launch__occupancy_limit_registers",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed.sum", "smsp__inst_executed.sum",
+    "sm__inst_executed.avg.per_cycle_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio",
+    "local_load_requests", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+]
+
+
+def short(name):
+    name = re.sub(r"\(.*", "", name)
+    return name.replace("tvm::", "")
+
+
+def launches(src, dst):
+    rows = []
+    with open(src, newline="") as f:
+        lines = [l for l in f if l.startswith('"')]
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            v = float(r["Metric Value"].replace(",", ""))
+            if r["Metric Unit"] == "us":
+                v *= 1e3
+            elif r["Metric Unit"] == "ms":
+                v *= 1e6
+            rows.append((short(r["Kernel Name"]), v))
+    agg = OrderedDict()
+    for k, v in rows:
+        c, t = agg.get(k, (0, 0.0))
+        agg[k] = (c + 1, t + v)
+    total = sum(t for _, t in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list summary\n\nsource: `{src}` ({len(rows)} launches captured, {total/1e6:.1f} ms summed kernel time; "
+                "times are ncu's serialised cold-cache per-launch durations — use the SHARE, not the absolute)\n\n")
+        f.write("| kernel | launches | total ms | avg us | share |\n|---|---:|---:|---:|---:|\n")
+        for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {c} | {t/1e6:.2f} | {t/c/1e3:.1f} | {100*t/total:.1f}% |\n")
+
+
+def report(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    lines = [l for l in out.splitlines(True) if l.startswith('"')]
+    rd = list(csv.reader(io.StringIO("".join(lines))))
+    header, units = rd[0], rd[1]
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full summary\n\nsource: `{src}` (kept in gpurun_out/, not tracked)\n\n")
+        for row in rd[2:]:
+            d = dict(zip(header, row))
+            u = dict(zip(header, units))
+            f.write(f"## `{short(d.get('Kernel Name', '?'))}`  grid {d.get('Grid Size')} block {d.get('Block Size')}\n\n")
+            f.write("| metric | value | unit |\n|---|---:|---|\n")
+            for m in KEY_METRICS:
+                if m in d and d[m] != "":
+                    f.write(f"| {m} | {d[m]} | {u.get(m, '')} |\n")
+            f.write("\n")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2], sys.argv[3])

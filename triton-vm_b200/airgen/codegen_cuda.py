@@ -8,10 +8,18 @@ with constraint order init | cons | tran | term and, inside a category, base-fie
 constraints before extension-field-valued ones (codegen.rs:210-212).
 
 B200 mapping: one thread per row, straight-line code with common sub-expressions shared inside a
-chunk.  The 404 transition constraints are split into several kernels ("chunks") so that each is a
-basic block ptxas compiles in seconds; a node needed by two chunks is recomputed.  Every chunk
-adds its zerofier-weighted partial sum into the row-planar X-field output.  Weights and
-challenges live in constant memory (warp-uniform operands).
+chunk.  The 604 constraints are split into many small kernels ("chunks"): ncu showed the first
+design (14 chunks of ~30k SASS instructions each, profiles/r01a_ncu_air_chunk06.md) issuing at
+15 % with `stalled_no_instruction` dominating - straight-line code that large streams through the
+32 KB L1.5 instruction cache once per warp.  A chunk is therefore sized to stay instruction-cache
+resident (budget below, ~25 SASS instructions per cost unit); a node needed by two chunks is
+recomputed and a chunk re-reads the table columns it touches, which HBM has ample headroom for.
+Every chunk adds its zerofier-weighted partial sum into the row-planar X-field output.  The
+weighted sum  sum_j w_j * c_j  is accumulated UNREDUCED (three 128-bit accumulators + overflow
+words, one Montgomery reduction per chunk instead of one per product); the per-weight linear map
+a -> a*w is a 3x3 matrix over F_p whose entries are precomputed (7 distinct words per weight).
+Weights and challenges live in constant memory (warp-uniform operands).  Chunks are packed into a
+few translation units so `make -j` compiles them in parallel.
 
 Run:  python -m airgen.codegen_cuda   (writes csrc/air_gen/*)
 """
@@ -23,8 +31,11 @@ from .circuit import P, reachable_postorder
 
 R = (1 << 64) % P
 OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "air_gen")
-CHUNK_COST_BUDGET = 1300.0
-SYNC_EVERY = int(os.environ.get("TVM_AIR_SYNC_EVERY", "40"))
+CHUNK_COST_BUDGET = float(os.environ.get("TVM_AIR_BUDGET", "100"))
+SYNC_EVERY = int(os.environ.get("TVM_AIR_SYNC_EVERY", "0"))
+NUM_TUS = int(os.environ.get("TVM_AIR_TUS", "8"))
+MIN_BLOCKS = int(os.environ.get("TVM_AIR_MIN_BLOCKS", "1"))
+WTAB_WORDS = 7   # per weight: b0, b1, b2, -b1, -b2, b0+b2, b1-b2
 
 
 def mont(v):
@@ -135,7 +146,7 @@ class Emitter:
             self.name[key] = v; self.isx[key] = resx
 
 
-HEADER = """// GENERATED by triton-vm_b200/airgen/codegen_cuda.py from the re-derived AIR — do not edit.
+TU_HEADER = """// GENERATED by triton-vm_b200/airgen/codegen_cuda.py from the re-derived AIR - do not edit.
 // Replaces the build-time generated Evaluable::evaluate_{cat}_constraints of the reference
 // (triton-constraint-builder/src/codegen.rs:59-269) fused with the weighted sum and zerofier
 // division of all_quotients_combined (triton-vm/src/table/master_table.rs:1264-1363).
@@ -143,29 +154,29 @@ HEADER = """// GENERATED by triton-vm_b200/airgen/codegen_cuda.py from the re-de
 
 namespace tvm {
 namespace {
-__constant__ u64 c_w[%(nw)d];   // this chunk's quotient weights (X-field, Montgomery), 3 words each
-__constant__ u64 c_ch[189];  // 63 challenges (X-field, Montgomery)
-}
+__constant__ u64 c_w[%(nw)d];   // weight table of ALL constraints: AIR_WTAB_WORDS words each (see air.cuh)
+__constant__ u64 c_ch[189];     // 63 challenges (X-field, Montgomery)
+"""
 
-__global__ void __launch_bounds__(AIR_THREADS) %(kname)s(AirArgs a) {
+KERNEL_HEADER = """
+__global__ void __launch_bounds__(AIR_THREADS, %(minb)d) %(kname)s(AirArgs a) {
   size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = m < a.nrows;
-  if (!active) m = 0;              // keep every thread alive for the block-wide barriers below
+%(guard)s
   const size_t n = (size_t)1 << a.log_n;
   const size_t coset = m >> a.log_n, k = m & (n - 1);
   const size_t m_next = (coset << a.log_n) | ((k + 1) & (n - 1));
   const u64 *mc = a.main + m, *mn = a.main + m_next;
   const u64 *ac = a.aux + m, *an = a.aux + m_next;
-  (void)mn; (void)an; (void)ac; (void)mc;
+  (void)mn; (void)an; (void)ac; (void)mc; (void)coset;
 """
 
-FOOTER = """
-void %(kname)s_launch(const AirArgs &a, const u64 *d_weights_all, const u64 *d_challenges, cudaStream_t s) {
-  // this chunk covers the contiguous constraint range [%(wstart)d, %(wstart)d + %(wcount)d) of the weight vector
-  cudaMemcpyToSymbolAsync(c_w, d_weights_all + 3 * %(wstart)d, sizeof(u64) * 3 * %(wcount)d, 0, cudaMemcpyDeviceToDevice, s);
+TU_FOOTER = """
+void %(tuname)s_launch(const AirArgs &a, const u64 *d_wtab, const u64 *d_challenges, cudaStream_t s, unsigned long long *launches) {
+  cudaMemcpyToSymbolAsync(c_w, d_wtab, sizeof(u64) * %(nw)d, 0, cudaMemcpyDeviceToDevice, s);
   cudaMemcpyToSymbolAsync(c_ch, d_challenges, sizeof(u64) * 189, 0, cudaMemcpyDeviceToDevice, s);
   unsigned grid = (unsigned)((a.nrows + AIR_THREADS - 1) / AIR_THREADS);
-  %(kname)s<<<grid, AIR_THREADS, 0, s>>>(a);
+%(launches)s
+  *launches += %(nk)d;
 }
 }  // namespace tvm
 """
@@ -177,27 +188,27 @@ def emit_chunk(air, idx, cat, items):
     roots = [c for _, c in items]
     for n in reachable_postorder(roots):
         em.emit_node(n)
-    kname = f"air_chunk_{idx:02d}_{cat}"
-    src = [HEADER % {"nw": 3 * len(items), "kname": kname}]
+    kname = f"air_chunk_{idx:03d}_{cat}"
+    if SYNC_EVERY:
+        guard = "  const bool active = m < a.nrows;\n  if (!active) m = 0;   // keep every thread alive for the block-wide barriers below"
+    else:
+        guard = "  if (m >= a.nrows) return;\n  const bool active = true;"
+    src = [KERNEL_HEADER % {"kname": kname, "guard": guard, "minb": MIN_BLOCKS}]
     body = []
     for k, line in enumerate(em.lines):
         body.append(line)
         if SYNC_EVERY and (k + 1) % SYNC_EVERY == 0:
             body.append("__syncthreads();   // instruction-fetch locality: the CTA's warps share one I-cache window")
     src.append("  " + "\n  ".join(body))
-    src.append("  xfe acc = xzero();")
-    for slot, (_, c) in enumerate(items):
-        w = f"xmake(c_w[{3 * slot}], c_w[{3 * slot + 1}], c_w[{3 * slot + 2}])"
+    src.append("  AirAcc acc; air_acc_zero(acc);")
+    for j, c in items:
         nm = em.name[id(c)]
         if em.isx[id(c)]:
-            src.append(f"  acc = xadd(acc, xmul({w}, {nm}));")
+            src.append(f"  air_acc_x(acc, c_w + {WTAB_WORDS * j}, {nm});")
         else:
-            src.append(f"  acc = xadd(acc, xmulb({w}, {nm}));")
-    src.append(f"  if (active) air_accumulate_{cat}(a, m, coset, k, acc);")
+            src.append(f"  air_acc_b(acc, c_w + {WTAB_WORDS * j}, {nm});")
+    src.append(f"  if (active) air_accumulate_{cat}(a, m, coset, air_acc_reduce(acc));")
     src.append("}")
-    idxs = [j for j, _ in items]
-    assert idxs == list(range(idxs[0], idxs[0] + len(idxs)))
-    src.append(FOOTER % {"kname": kname, "wstart": idxs[0], "wcount": len(idxs)})
     nops = sum(1 for n in reachable_postorder(roots) if n.kind in "+*")
     return kname, "\n".join(src), nops
 
@@ -205,33 +216,60 @@ def emit_chunk(air, idx, cat, items):
 def main():
     air = build_air()
     chunks = chunk_constraints(air)
+    total_constraints = sum(len(air.constraints[c]) for c in CATEGORIES)
     os.makedirs(OUT_DIR, exist_ok=True)
     for f in os.listdir(OUT_DIR):
         os.remove(os.path.join(OUT_DIR, f))
+    # pack chunks into translation units, balancing the estimated cost (compile time)
+    tus = [[] for _ in range(NUM_TUS)]
+    load = [0.0] * NUM_TUS
     names, total_ops = [], 0
+    order = sorted(range(len(chunks)), key=lambda i: -len(chunks[i][1]))
+    emitted = {}
     for idx, (cat, items) in enumerate(chunks):
-        kname, src, nops = emit_chunk(air, idx, cat, items)
-        names.append((kname, cat, len(items), nops))
-        total_ops += nops
-        with open(os.path.join(OUT_DIR, kname + ".cu"), "w") as f:
-            f.write(src)
+        emitted[idx] = emit_chunk(air, idx, cat, items)
+    for idx in order:
+        t = min(range(NUM_TUS), key=lambda i: load[i])
+        tus[t].append(idx)
+        load[t] += emitted[idx][2] + 20
+    nw = WTAB_WORDS * total_constraints
+    tu_names = []
+    for t, idxs in enumerate(tus):
+        if not idxs:
+            continue
+        idxs.sort()
+        tuname = f"air_tu_{t:02d}"
+        tu_names.append(tuname)
+        parts = [TU_HEADER % {"nw": nw}, "}  // namespace"]
+        launches = []
+        for idx in idxs:
+            kname, src, nops = emitted[idx]
+            cat, items = chunks[idx]
+            names.append((kname, cat, len(items), nops))
+            total_ops += nops
+            parts.append(src)
+            launches.append(f"  {kname}<<<grid, AIR_THREADS, 0, s>>>(a);")
+        parts.append(TU_FOOTER % {"tuname": tuname, "nw": nw, "launches": "\n".join(launches), "nk": len(idxs)})
+        with open(os.path.join(OUT_DIR, tuname + ".cu"), "w") as f:
+            f.write("\n".join(parts))
     unique_ops = sum(sum(1 for n in reachable_postorder(air.constraints[c]) if n.kind in "+*") for c in CATEGORIES)
     with open(os.path.join(OUT_DIR, "air_chunks.inc"), "w") as f:
-        f.write("// GENERATED by airgen/codegen_cuda.py — do not edit.\n")
-        f.write(f"// {len(names)} chunks, {total_ops} binary operations emitted ({unique_ops} unique in the circuit)\n")
-        for kname, cat, ncons, nops in names:
-            f.write(f"TVM_AIR_CHUNK({kname}) // {cat}: {ncons} constraints, {nops} ops\n")
+        f.write("// GENERATED by airgen/codegen_cuda.py - do not edit.\n")
+        f.write(f"// {len(names)} chunk kernels in {len(tu_names)} translation units, {total_ops} binary operations emitted "
+                f"({unique_ops} unique in the circuit), chunk budget {CHUNK_COST_BUDGET:g}\n")
+        for tuname in tu_names:
+            f.write(f"TVM_AIR_TU({tuname})\n")
+        for kname, cat, ncons, nops in sorted(names):
+            f.write(f"// {kname}: {ncons} constraints, {nops} ops\n")
     with open(os.path.join(OUT_DIR, "air_meta.inc"), "w") as f:
-        f.write("// GENERATED by airgen/codegen_cuda.py — constraint degrees in evaluator order\n")
+        f.write("// GENERATED by airgen/codegen_cuda.py - constraint degrees in evaluator order\n")
         f.write("// (the generated *_quotient_degree_bounds of the reference, codegen.rs:222-229).\n")
         for cat in CATEGORIES:
             b = air.builders[cat]
             degs = [b.degree(c) for c in air.constraints[cat]]
             f.write(f"static const int AIR_NUM_{cat.upper()} = {len(degs)};\n")
             f.write(f"static const unsigned char AIR_DEGREES_{cat.upper()}[] = {{{', '.join(map(str, degs))}}};\n")
-    print(f"wrote {len(names)} chunks to {OUT_DIR}: {total_ops} ops emitted, {unique_ops} unique")
-    for n in names:
-        print("  ", n)
+    print(f"wrote {len(names)} chunks in {len(tu_names)} TUs to {OUT_DIR}: {total_ops} ops emitted, {unique_ops} unique")
 
 
 if __name__ == "__main__":

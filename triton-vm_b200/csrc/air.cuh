@@ -15,6 +15,8 @@ namespace tvm {
 static constexpr int AIR_THREADS = TVM_AIR_THREADS;
 static constexpr int AIR_MAX_COSETS = 64;
 
+static constexpr int AIR_WTAB_WORDS = 7;   // per weight w = (b0,b1,b2): b0, b1, b2, -b1, -b2, b0+b2, b1-b2
+
 struct AirArgs {
   const u64 *main;      // main column q at main + q*main_stride
   size_t main_stride;
@@ -24,16 +26,54 @@ struct AirArgs {
   size_t out_stride;
   size_t nrows;         // r * n
   int log_n;            // trace length n = 2^log_n
-  PowTab trace_gen;     // w_n^k
-  u64 trace_gen_inv;    // w_n^-1
-  u64 coset_x[AIR_MAX_COSETS];            // offset * w_{rn}^coset
-  u64 cons_zerofier_inv[AIR_MAX_COSETS];  // 1 / (x^n - 1), constant on a coset
+  // per-row zerofier inverses in memory order (air_zerofier_kernel):
+  const u64 *zi_init;   // 1 / (x - 1)                         (master_table.rs:1194-1202)
+  const u64 *zi_tran;   // (x - w_n^-1) / (x^n - 1)            (1216-1237)
+  const u64 *zi_term;   // 1 / (x - w_n^-1)                    (1239-1252)
+  u64 cons_zerofier_inv[AIR_MAX_COSETS];  // 1 / (x^n - 1), constant on a coset   (1204-1214)
 };
 
-__device__ __forceinline__ u64 air_domain_value(const AirArgs &a, size_t coset, size_t k) {
-  u64 lo = __ldg(a.trace_gen.lo + (k & ((1ULL << a.trace_gen.shift) - 1)));
-  u64 hi = __ldg(a.trace_gen.hi + (k >> a.trace_gen.shift));
-  return fmul(a.coset_x[coset], fmul(lo, hi));
+// ---- unreduced accumulation of  sum_j w_j * c_j ------------------------------------------------
+// (c * w)_0 = c0 b0 - c1 b2 - c2 b1;  (c * w)_1 = c0 b1 + c1 (b0 + b2) + c2 (b1 - b2);
+// (c * w)_2 = c0 b2 + c1 b1 + c2 (b0 + b2)           (X^3 = X - 1)
+// Each coordinate sums 128-bit products of Montgomery words; `ov` counts carries out of bit 128.
+struct AirAcc {
+  u64 lo[3], hi[3];
+  u32 ov[3];
+};
+__device__ __forceinline__ void air_acc_zero(AirAcc &c) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) { c.lo[i] = 0; c.hi[i] = 0; c.ov[i] = 0; }
+}
+__device__ __forceinline__ void air_mac(u64 &lo, u64 &hi, u32 &ov, u64 x, u64 y) {
+  u64 plo = x * y, phi = __umul64hi(x, y);
+  asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+      : "+l"(lo), "+l"(hi), "+r"(ov) : "l"(plo), "l"(phi));
+}
+__device__ __forceinline__ void air_acc_b(AirAcc &c, const u64 *w, u64 v) {
+  air_mac(c.lo[0], c.hi[0], c.ov[0], v, w[0]);
+  air_mac(c.lo[1], c.hi[1], c.ov[1], v, w[1]);
+  air_mac(c.lo[2], c.hi[2], c.ov[2], v, w[2]);
+}
+__device__ __forceinline__ void air_acc_x(AirAcc &c, const u64 *w, xfe v) {
+  air_mac(c.lo[0], c.hi[0], c.ov[0], v.c0, w[0]);
+  air_mac(c.lo[0], c.hi[0], c.ov[0], v.c1, w[4]);
+  air_mac(c.lo[0], c.hi[0], c.ov[0], v.c2, w[3]);
+  air_mac(c.lo[1], c.hi[1], c.ov[1], v.c0, w[1]);
+  air_mac(c.lo[1], c.hi[1], c.ov[1], v.c1, w[5]);
+  air_mac(c.lo[1], c.hi[1], c.ov[1], v.c2, w[6]);
+  air_mac(c.lo[2], c.hi[2], c.ov[2], v.c0, w[2]);
+  air_mac(c.lo[2], c.hi[2], c.ov[2], v.c1, w[1]);
+  air_mac(c.lo[2], c.hi[2], c.ov[2], v.c2, w[5]);
+}
+// (lo + 2^64 hi + 2^128 ov) * 2^-64  =  montyred(lo, 0) + hi + ov * 2^64   (mod p)
+__device__ __forceinline__ u64 air_reduce160(u64 lo, u64 hi, u32 ov) {
+  u64 h = hi >= P ? hi - P : hi;
+  return fadd(fadd(montyred(lo, 0), h), (u64)ov * EPS);
+}
+__device__ __forceinline__ xfe air_acc_reduce(const AirAcc &c) {
+  return xmake(air_reduce160(c.lo[0], c.hi[0], c.ov[0]), air_reduce160(c.lo[1], c.hi[1], c.ov[1]),
+               air_reduce160(c.lo[2], c.hi[2], c.ov[2]));
 }
 
 __device__ __forceinline__ void air_add_out(const AirArgs &a, size_t m, xfe v) {
@@ -43,24 +83,17 @@ __device__ __forceinline__ void air_add_out(const AirArgs &a, size_t m, xfe v) {
   o[2 * a.out_stride] = fadd(o[2 * a.out_stride], v.c2);
 }
 
-// initial: zerofier x - 1 (master_table.rs:1194-1202)
-__device__ __forceinline__ void air_accumulate_init(const AirArgs &a, size_t m, size_t coset, size_t k, xfe acc) {
-  u64 x = air_domain_value(a, coset, k);
-  air_add_out(a, m, xmulb(acc, finv(fsub(x, MONT_ONE))));
+__device__ __forceinline__ void air_accumulate_init(const AirArgs &a, size_t m, size_t, xfe acc) {
+  air_add_out(a, m, xmulb(acc, a.zi_init[m]));
 }
-// consistency: zerofier x^n - 1 (1204-1214)
-__device__ __forceinline__ void air_accumulate_cons(const AirArgs &a, size_t m, size_t coset, size_t, xfe acc) {
+__device__ __forceinline__ void air_accumulate_cons(const AirArgs &a, size_t m, size_t coset, xfe acc) {
   air_add_out(a, m, xmulb(acc, a.cons_zerofier_inv[coset]));
 }
-// transition: zerofier (x^n - 1) / (x - w_n^-1) (1216-1237)
-__device__ __forceinline__ void air_accumulate_tran(const AirArgs &a, size_t m, size_t coset, size_t k, xfe acc) {
-  u64 x = air_domain_value(a, coset, k);
-  air_add_out(a, m, xmulb(acc, fmul(fsub(x, a.trace_gen_inv), a.cons_zerofier_inv[coset])));
+__device__ __forceinline__ void air_accumulate_tran(const AirArgs &a, size_t m, size_t, xfe acc) {
+  air_add_out(a, m, xmulb(acc, a.zi_tran[m]));
 }
-// terminal: zerofier x - w_n^-1 (1239-1252)
-__device__ __forceinline__ void air_accumulate_term(const AirArgs &a, size_t m, size_t coset, size_t k, xfe acc) {
-  u64 x = air_domain_value(a, coset, k);
-  air_add_out(a, m, xmulb(acc, finv(fsub(x, a.trace_gen_inv))));
+__device__ __forceinline__ void air_accumulate_term(const AirArgs &a, size_t m, size_t, xfe acc) {
+  air_add_out(a, m, xmulb(acc, a.zi_term[m]));
 }
 
 }  // namespace tvm

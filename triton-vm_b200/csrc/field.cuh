@@ -7,6 +7,7 @@
 // p = 2^64 - 2^32 + 1 (triton-vm/src/lib.rs:5-6).  X-field = F_p[X]/(X^3 - X + 1)
 // (specification/src/isa.md:8).
 #pragma once
+#pragma nv_diag_suppress 550  // asm scratch outputs
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -25,13 +26,40 @@ static constexpr u64 EPS = 0xFFFFFFFFULL;               // 2^64 mod p
 
 // ---- 128-bit product + Montgomery reduction -------------------------------------------
 // x = lo + 2^64 hi  ->  x * 2^-64 mod p, result canonical when x < p * 2^64.
+//
+// Device versions are explicit 32-bit carry chains: the kernels that use them (NTT, Tip5, AIR)
+// are bound by the integer-ALU pipe (ncu: pipe_alu ~70 %, pipe_fma ~15 %, profiles/r01a_ncu_ntt_pass_b.md),
+// and the compiler's compare/select sequences for the C versions cost 13 ALU instructions per
+// fmul, 9 per fadd/fsub; the chains below cost 8 / 7 / 5.
 TVM_HD u64 montyred(u64 lo, u64 hi) {
+#ifdef __CUDA_ARCH__
+  u32 x0 = (u32)lo, x1 = (u32)(lo >> 32), x2 = (u32)hi, x3 = (u32)(hi >> 32);
+  u32 a1, b0, b1, r0, r1;
+  // a = lo*(2^32+1) mod 2^64 = (x0, x1+x0), e = carry;  b = a - (a>>32) - e;  r = hi - b (+p on borrow)
+  // (carry chains are kept homogeneous: an add.cc feeding a subc is not translated faithfully by ptxas)
+  asm("{\n\t"
+      ".reg .u32 t;\n\t"
+      "add.u32 %0, %6, %5;\n\t"       // a1 = x1 + x0 (mod 2^32)
+      "sub.cc.u32 t, %0, %5;\n\t"     // borrow <=> a1 < x0 <=> the addition carried (e)
+      "subc.cc.u32 %1, %5, %0;\n\t"   // b0 = a0 - a1 - e
+      "subc.u32 %2, %0, 0;\n\t"       // b1 = a1 - borrow
+      "sub.cc.u32 %3, %7, %1;\n\t"    // r0 = x2 - b0
+      "subc.cc.u32 %4, %8, %2;\n\t"   // r1 = x3 - b1 - borrow
+      "subc.u32 %1, 0, 0;\n\t"        // m = borrow ? 0xffffffff : 0
+      "sub.cc.u32 %3, %3, %1;\n\t"    // r -= eps & m   (== r += p mod 2^64)
+      "subc.u32 %4, %4, 0;\n\t"
+      "}"
+      : "=&r"(a1), "=&r"(b0), "=&r"(b1), "=&r"(r0), "=&r"(r1)
+      : "r"(x0), "r"(x1), "r"(x2), "r"(x3));
+  return ((u64)r1 << 32) | r0;
+#else
   u64 a = lo + (lo << 32);
   u64 e = a < lo;
   u64 b = a - (a >> 32) - e;
   u64 r = hi - b;
   u64 c = hi < b;
   return r - (EPS & (0 - c));
+#endif
 }
 
 TVM_HD u64 fmul(u64 a, u64 b) {
@@ -46,15 +74,41 @@ TVM_HD u64 fmul(u64 a, u64 b) {
 }
 TVM_HD u64 fsqr(u64 a) { return fmul(a, a); }
 
-TVM_HD u64 fadd(u64 a, u64 b) {  // canonical in, canonical out
-  u64 s = a + b;
-  if (s < a || s >= P) s -= P;
-  return s;
-}
-TVM_HD u64 fsub(u64 a, u64 b) {
+TVM_HD u64 fsub(u64 a, u64 b) {  // canonical a, b in [0, p] -> canonical
+#ifdef __CUDA_ARCH__
+  u32 r0, r1, m;
+  asm("{\n\t"
+      "sub.cc.u32 %0, %3, %5;\n\t"
+      "subc.cc.u32 %1, %4, %6;\n\t"
+      "subc.u32 %2, 0, 0;\n\t"        // m = borrow ? 0xffffffff : 0
+      "sub.cc.u32 %0, %0, %2;\n\t"    // += p  (== -= eps mod 2^64)
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1), "=&r"(m)
+      : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+  return ((u64)r1 << 32) | r0;
+#else
   u64 d = a - b;
   if (a < b) d += P;
   return d;
+#endif
+}
+TVM_HD u64 fadd(u64 a, u64 b) {  // canonical in, canonical out
+#ifdef __CUDA_ARCH__
+  // a + b = a - (p - b); p - b in [1, p] is a valid subtrahend for fsub
+  u32 n0, n1;
+  asm("{\n\t"
+      "sub.cc.u32 %0, 1, %2;\n\t"
+      "subc.u32 %1, 0xffffffff, %3;\n\t"
+      "}"
+      : "=&r"(n0), "=&r"(n1)
+      : "r"((u32)b), "r"((u32)(b >> 32)));
+  return fsub(a, ((u64)n1 << 32) | n0);
+#else
+  u64 s = a + b;
+  if (s < a || s >= P) s -= P;
+  return s;
+#endif
 }
 TVM_HD u64 fneg(u64 a) { return a ? P - a : 0; }
 TVM_HD u64 to_mont(u64 canon) { return fmul(canon, MONT_R2); }

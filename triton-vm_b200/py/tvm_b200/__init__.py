@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # triton-vm_b200/
-LIB_PATH = os.path.join(_PKG, "lib", "libtvm_b200.so")
+LIB_PATH = os.environ.get("TVM_B200_LIB") or os.path.join(_PKG, "lib", "libtvm_b200.so")  # override: A/B builds only
 P = (1 << 64) - (1 << 32) + 1
 
 _u64p = ctypes.POINTER(ctypes.c_uint64)
