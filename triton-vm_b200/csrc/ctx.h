@@ -40,6 +40,10 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;   // host<->device staging overlapped with compute (created on first use)
+  std::vector<cudaEvent_t> copy_events; // recycled per-batch "upload done" events
+  cudaStream_t get_copy_stream();
+  cudaEvent_t get_copy_event(size_t i);
   std::string last_error;
   unsigned long long launches = 0;  // kernels launched through this context
 

@@ -240,6 +240,19 @@ u64 root_of_unity_mont(unsigned log2n) {
   return r;
 }
 
+cudaStream_t Ctx::get_copy_stream() {
+  if (!copy_stream) TVM_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  return copy_stream;
+}
+cudaEvent_t Ctx::get_copy_event(size_t i) {
+  while (copy_events.size() <= i) {
+    cudaEvent_t e;
+    TVM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    copy_events.push_back(e);
+  }
+  return copy_events[i];
+}
+
 void *Ctx::pool_alloc(size_t bytes) {
   if (!bytes) bytes = 8;
   auto it = pool_free.lower_bound(bytes);

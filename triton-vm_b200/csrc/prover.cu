@@ -196,16 +196,36 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
 
   // ---- main table: upload, LDE, row hashes, Merkle tree (stark.rs:359-374) -------------------------
   u64 *d_tmp = mem.words(tmp_cols * N);
+  mark();  // (kept for the stage table: uploads are issued asynchronously below)
+  // The trace is uploaded in column batches on the copy stream while the compute stream converts the
+  // batches that have landed to Montgomery form and extends them (host or device source pointers).
   u64 *d_main_trace = mem.words(NM * n + NM * h);
   u64 *d_main_rand = d_main_trace + NM * n;
-  TVM_CUDA(cudaMemcpyAsync(d_main_trace, h_main_trace, NM * n * 8, cudaMemcpyHostToDevice, c.stream));
-  TVM_CUDA(cudaMemcpyAsync(d_main_rand, h_main_rand, NM * h * 8, cudaMemcpyHostToDevice, c.stream));
-  mark();  // H2D(main)
-  to_mont_run(c, d_main_trace, NM * n + NM * h);
   u64 *d_main_coef = mem.words(NM * 2 * n);
   u64 *d_main_lde = mem.words(NM * N);
+  cudaStream_t cs = c.get_copy_stream();
+  size_t nevt = 0;
+  {
+    cudaEvent_t e = c.get_copy_event(nevt++);   // the pool may hand out blocks the compute stream still uses
+    TVM_CUDA(cudaEventRecord(e, c.stream));
+    TVM_CUDA(cudaStreamWaitEvent(cs, e, 0));
+  }
+  TVM_CUDA(cudaMemcpyAsync(d_main_rand, h_main_rand, NM * h * 8, cudaMemcpyDefault, cs));
+  const size_t evt_main0 = nevt;
+  for (size_t c0 = 0; c0 < NM; c0 += tmp_cols) {
+    size_t b = std::min(tmp_cols, NM - c0);
+    TVM_CUDA(cudaMemcpyAsync(d_main_trace + c0 * n, h_main_trace + c0 * n, b * n * 8, cudaMemcpyDefault, cs));
+    TVM_CUDA(cudaEventRecord(c.get_copy_event(nevt++), cs));
+  }
   TVM_CUDA(cudaMemsetAsync(d_main_coef, 0, NM * 2 * n * 8, c.stream));
-  lde_batched(c, d_main_trace, d_main_rand, (unsigned)h, log_n, log_r, off, NM, d_main_coef, d_main_lde, d_tmp, tmp_cols);
+  for (size_t c0 = 0, bi = 0; c0 < NM; c0 += tmp_cols, bi++) {
+    size_t b = std::min(tmp_cols, NM - c0);
+    TVM_CUDA(cudaStreamWaitEvent(c.stream, c.get_copy_event(evt_main0 + bi), 0));
+    if (c0 == 0) to_mont_run(c, d_main_rand, NM * h);
+    to_mont_run(c, d_main_trace + c0 * n, b * n);
+    lde_run(c, d_main_trace + c0 * n, d_main_rand + c0 * h, (unsigned)h, log_n, log_r, off, b, d_main_coef + c0 * 2 * n,
+            d_main_lde + c0 * N, d_tmp);
+  }
   mark();  // 1: main LDE
   u64 *d_main_nodes = mem.words(2 * N * 5);
   TVM_CUDA(cudaMemsetAsync(d_main_nodes, 0, 40, c.stream));
@@ -244,19 +264,37 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   if (!h_aux_trace || !h_aux_rand) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback returned a null buffer"};
   mark();  // extend (caller)
   u64 *d_aux_in = mem.words(NA * n * 3 + NA * h * 3);
-  TVM_CUDA(cudaMemcpyAsync(d_aux_in, h_aux_trace, NA * n * 3 * 8, cudaMemcpyHostToDevice, c.stream));
-  TVM_CUDA(cudaMemcpyAsync(d_aux_in + NA * n * 3, h_aux_rand, NA * h * 3 * 8, cudaMemcpyHostToDevice, c.stream));
-  mark();  // H2D(aux)
-  to_mont_run(c, d_aux_in, NA * n * 3 + NA * h * 3);
   u64 *d_aux_trace = mem.words(NA3 * n + NA3 * h);
   u64 *d_aux_rand = d_aux_trace + NA3 * n;
-  deinterleave3_run(c, d_aux_in, d_aux_trace, n, NA);
-  deinterleave3_run(c, d_aux_in + NA * n * 3, d_aux_rand, h, NA);
-  mem.release(d_aux_in);
   u64 *d_aux_coef = mem.words(NA3 * 2 * n);
   u64 *d_aux_lde = mem.words(NA3 * N);
+  {
+    cudaEvent_t e = c.get_copy_event(nevt++);
+    TVM_CUDA(cudaEventRecord(e, c.stream));
+    TVM_CUDA(cudaStreamWaitEvent(cs, e, 0));
+  }
+  TVM_CUDA(cudaMemcpyAsync(d_aux_in + NA * n * 3, h_aux_rand, NA * h * 3 * 8, cudaMemcpyDefault, cs));
+  const size_t xcols = tmp_cols / 3;   // X-field columns per batch (3 B-field columns each)
+  const size_t evt_aux0 = nevt;
+  for (size_t c0 = 0; c0 < NA; c0 += xcols) {
+    size_t b = std::min(xcols, NA - c0);
+    TVM_CUDA(cudaMemcpyAsync(d_aux_in + c0 * n * 3, h_aux_trace + c0 * n * 3, b * n * 3 * 8, cudaMemcpyDefault, cs));
+    TVM_CUDA(cudaEventRecord(c.get_copy_event(nevt++), cs));
+  }
   TVM_CUDA(cudaMemsetAsync(d_aux_coef, 0, NA3 * 2 * n * 8, c.stream));
-  lde_batched(c, d_aux_trace, d_aux_rand, (unsigned)h, log_n, log_r, off, NA3, d_aux_coef, d_aux_lde, d_tmp, tmp_cols);
+  for (size_t c0 = 0, bi = 0; c0 < NA; c0 += xcols, bi++) {
+    size_t b = std::min(xcols, NA - c0);
+    TVM_CUDA(cudaStreamWaitEvent(c.stream, c.get_copy_event(evt_aux0 + bi), 0));
+    if (c0 == 0) {
+      to_mont_run(c, d_aux_in + NA * n * 3, NA * h * 3);
+      deinterleave3_run(c, d_aux_in + NA * n * 3, d_aux_rand, h, NA);
+    }
+    to_mont_run(c, d_aux_in + c0 * n * 3, b * n * 3);
+    deinterleave3_run(c, d_aux_in + c0 * n * 3, d_aux_trace + 3 * c0 * n, n, b);
+    lde_run(c, d_aux_trace + 3 * c0 * n, d_aux_rand + 3 * c0 * h, (unsigned)h, log_n, log_r, off, 3 * b, d_aux_coef + 3 * c0 * 2 * n,
+            d_aux_lde + 3 * c0 * N, d_tmp);
+  }
+  mem.release(d_aux_in);
   mark();  // 4: aux LDE
   u64 *d_aux_nodes = mem.words(2 * N * 5);
   TVM_CUDA(cudaMemsetAsync(d_aux_nodes, 0, 40, c.stream));
@@ -533,7 +571,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   proof = ps.encode();
   if (timings) {
     TVM_CUDA(cudaStreamSynchronize(c.stream));
-    static const char *names[] = {"H2D(main)", "LDE(main)", "Merkle(main)", "extend(caller)", "H2D(aux)", "LDE(aux)", "Merkle(aux)",
+    static const char *names[] = {"setup", "upload+LDE(main)", "Merkle(main)", "extend(caller)", "upload+LDE(aux)", "Merkle(aux)",
                                   "quotient(AIR)", "quotient LDE", "Merkle(quot)", "OOD rows", "linear combination+DEEP", "LDT(FRI)",
                                   "open"};
     timings->stages.clear();

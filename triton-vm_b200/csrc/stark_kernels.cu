@@ -96,52 +96,86 @@ void xpow_vector_run(Ctx &c, xfe base, u64 *out, size_t stride, size_t len) {
 // Replaces the batched barycentric evaluation of MasterTable::out_of_domain_row
 // (master_table.rs:348-390) and Polynomial::evaluate on segment / combination polynomials
 // (stark.rs:474-494, 566-607): with c'_j = c_j*offset^j stored, f(beta) = sum c'_j (beta/offset)^j.
-// One CTA per column; `nvec` vectors evaluated in the same pass over the column.
+// grid (ncols, split): each CTA covers a slice of one column for all `nvec` vectors; products are
+// accumulated unreduced (128 bits + overflow word per coordinate) and reduced once per thread;
+// a second kernel adds the `split` partial results of a column.
 static constexpr int DOT_THREADS = 256;
+__device__ __forceinline__ void dot_mac(u64 &lo, u64 &hi, u32 &ov, u64 x, u64 y) {
+  u64 plo = x * y, phi = __umul64hi(x, y);
+  asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+      : "+l"(lo), "+l"(hi), "+r"(ov) : "l"(plo), "l"(phi));
+}
+__device__ __forceinline__ u64 dot_reduce160(u64 lo, u64 hi, u32 ov) {
+  // (lo + 2^64 hi + 2^128 ov) * 2^-64 = montyred(lo, 0) + hi + ov * 2^64  (mod p)
+  u64 h = hi >= P ? hi - P : hi;
+  return fadd(fadd(montyred(lo, 0), h), (u64)ov * EPS);
+}
 template <int NVEC>
 __global__ void __launch_bounds__(DOT_THREADS) col_dot_kernel(const u64 *cols, size_t col_stride, size_t len, const u64 *xvec,
-                                                              size_t xvec_stride, size_t xvec_set_stride, u64 *out) {
+                                                              size_t xvec_stride, size_t xvec_set_stride, u64 *partial) {
   const u64 *col = cols + (size_t)blockIdx.x * col_stride;
-  xfe acc[NVEC];
+  const size_t per = (len + gridDim.y - 1) / gridDim.y;
+  const size_t j0 = (size_t)blockIdx.y * per, j1 = min(len, j0 + per);
+  u64 lo[NVEC][3], hi[NVEC][3];
+  u32 ov[NVEC][3];
 #pragma unroll
-  for (int v = 0; v < NVEC; v++) acc[v] = xzero();
-  for (size_t j = threadIdx.x; j < len; j += blockDim.x) {
+  for (int v = 0; v < NVEC; v++)
+#pragma unroll
+    for (int d = 0; d < 3; d++) { lo[v][d] = 0; hi[v][d] = 0; ov[v][d] = 0; }
+  for (size_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
     u64 cv = col[j];
-    if (cv == 0) continue;
 #pragma unroll
     for (int v = 0; v < NVEC; v++) {
       const u64 *xv = xvec + v * xvec_set_stride + j;
-      acc[v] = xadd(acc[v], xmulb(xmake(xv[0], xv[xvec_stride], xv[2 * xvec_stride]), cv));
+#pragma unroll
+      for (int d = 0; d < 3; d++) dot_mac(lo[v][d], hi[v][d], ov[v][d], xv[d * xvec_stride], cv);
     }
   }
   __shared__ u64 red[DOT_THREADS * 3];
 #pragma unroll
   for (int v = 0; v < NVEC; v++) {
-    red[threadIdx.x] = acc[v].c0; red[DOT_THREADS + threadIdx.x] = acc[v].c1; red[2 * DOT_THREADS + threadIdx.x] = acc[v].c2;
+#pragma unroll
+    for (int d = 0; d < 3; d++) red[d * DOT_THREADS + threadIdx.x] = dot_reduce160(lo[v][d], hi[v][d], ov[v][d]);
     __syncthreads();
     for (int s = DOT_THREADS / 2; s > 0; s >>= 1) {
       if ((int)threadIdx.x < s) {
-        red[threadIdx.x] = fadd(red[threadIdx.x], red[threadIdx.x + s]);
-        red[DOT_THREADS + threadIdx.x] = fadd(red[DOT_THREADS + threadIdx.x], red[DOT_THREADS + threadIdx.x + s]);
-        red[2 * DOT_THREADS + threadIdx.x] = fadd(red[2 * DOT_THREADS + threadIdx.x], red[2 * DOT_THREADS + threadIdx.x + s]);
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+          red[d * DOT_THREADS + threadIdx.x] = fadd(red[d * DOT_THREADS + threadIdx.x], red[d * DOT_THREADS + threadIdx.x + s]);
       }
       __syncthreads();
     }
     if (threadIdx.x == 0) {
-      u64 *o = out + ((size_t)blockIdx.x * NVEC + v) * 3;
+      u64 *o = partial + (((size_t)blockIdx.x * gridDim.y + blockIdx.y) * NVEC + v) * 3;
       o[0] = red[0]; o[1] = red[DOT_THREADS]; o[2] = red[2 * DOT_THREADS];
     }
     __syncthreads();
   }
 }
+// out[i] = sum_s partial[(i / w) * split * w + s * w + i % w],  w = nvec*3 words per column
+__global__ void col_dot_finish_kernel(const u64 *partial, unsigned split, unsigned w, size_t total, u64 *out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  size_t col = i / w, r = i - col * w;
+  u64 acc = 0;
+  for (unsigned s = 0; s < split; s++) acc = fadd(acc, partial[(col * split + s) * w + r]);
+  out[i] = acc;
+}
 // out: [ncols][nvec][3]
 void col_dot_run(Ctx &c, const u64 *cols, size_t col_stride, size_t ncols, size_t len, const u64 *xvec, size_t xvec_stride,
                  size_t xvec_set_stride, int nvec, u64 *out) {
   if (!ncols) return;
-  if (nvec == 1) col_dot_kernel<1><<<(unsigned)ncols, DOT_THREADS, 0, c.stream>>>(cols, col_stride, len, xvec, xvec_stride, xvec_set_stride, out);
-  else if (nvec == 2) col_dot_kernel<2><<<(unsigned)ncols, DOT_THREADS, 0, c.stream>>>(cols, col_stride, len, xvec, xvec_stride, xvec_set_stride, out);
-  else throw ApiError{TVM_ERR_INVALID_ARG, "col_dot: nvec must be 1 or 2"};
-  c.launches++;
+  if (nvec != 1 && nvec != 2) throw ApiError{TVM_ERR_INVALID_ARG, "col_dot: nvec must be 1 or 2"};
+  // enough CTAs for ~8 per SM, but at least 4 elements per thread
+  size_t split = std::max<size_t>(1, std::min<size_t>((148 * 8 + ncols - 1) / ncols, len / (4 * DOT_THREADS) + 1));
+  u64 *partial = (u64 *)c.pool_alloc(sizeof(u64) * ncols * split * nvec * 3);   // stream-ordered reuse: released below
+  dim3 grid((unsigned)ncols, (unsigned)split);
+  if (nvec == 1) col_dot_kernel<1><<<grid, DOT_THREADS, 0, c.stream>>>(cols, col_stride, len, xvec, xvec_stride, xvec_set_stride, partial);
+  else col_dot_kernel<2><<<grid, DOT_THREADS, 0, c.stream>>>(cols, col_stride, len, xvec, xvec_stride, xvec_set_stride, partial);
+  size_t total = ncols * nvec * 3;
+  col_dot_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(partial, (unsigned)split, (unsigned)(nvec * 3), total, out);
+  c.launches += 2;
+  c.pool_release(partial);
   TVM_CUDA(cudaGetLastError());
 }
 

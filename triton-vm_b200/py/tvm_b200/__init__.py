@@ -107,6 +107,15 @@ def lib():
     return _lib
 
 
+def _u64_arg(x):
+    """(keepalive, u64 pointer, shape) of a numpy array or a contiguous torch tensor (host or device)."""
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous() and x.element_size() == 8
+        return x, ctypes.cast(x.data_ptr(), _u64p), tuple(x.shape)
+    a, ap = _np_u64(x)
+    return a, ap, tuple(a.shape)
+
+
 def _np_u64(a):
     a = np.ascontiguousarray(a, dtype=np.uint64)
     return a, a.ctypes.data_as(_u64p)
@@ -214,15 +223,17 @@ class Backend:
               padded_height=None):
         """Stark::prove (LdtChoice::Fri).  claim = (program_digest[5], input, output[, version]);
         main_trace [379, n], main_rand [379, h] canonical uint64; aux_provider(challenges [63,3]) ->
-        (aux_trace [91, n, 3], aux_rand [91, h, 3]); quot_rand [(h+1)*5, 3].  Returns the proof words."""
-        mt, mtp = _np_u64(main_trace)
-        mr, mrp = _np_u64(main_rand)
+        (aux_trace [91, n, 3], aux_rand [91, h, 3]); quot_rand [(h+1)*5, 3].  Returns the proof words.
+        The traces may be numpy arrays (host) or contiguous torch int64 tensors (pinned host or CUDA:
+        the C ABI takes either kind of pointer)."""
+        mt, mtp, mt_shape = _u64_arg(main_trace)
+        mr, mrp, mr_shape = _u64_arg(main_rand)
         qr, qrp = _np_u64(quot_rand)
-        n = mt.shape[1]
+        n = mt_shape[1]
         ph = padded_height or n
         dom = derive_domains(security_level, log2_expansion, ph)
         h = dom["num_trace_randomizers"]
-        assert mt.shape == (379, dom["trace_len"]) and mr.shape == (379, h), (mt.shape, mr.shape, dom)
+        assert mt_shape == (379, dom["trace_len"]) and mr_shape == (379, h), (mt_shape, mr_shape, dom)
         assert qr.size == 3 * dom["num_quotient_randomizer_coefficients"]
         digest, inp, out = claim[0], claim[1], claim[2]
         version = claim[3] if len(claim) > 3 else 6
@@ -237,11 +248,12 @@ class Backend:
             try:
                 ch = np.ctypeslib.as_array(ch_p, shape=(63, 3)).copy()
                 t, r = aux_provider(ch)
-                t = np.ascontiguousarray(t, dtype=np.uint64).reshape(91, n, 3)
-                r = np.ascontiguousarray(r, dtype=np.uint64).reshape(91, h, 3)
+                t, tp, ts = _u64_arg(t)
+                r, rp, rs = _u64_arg(r)
+                assert int(np.prod(ts)) == 91 * n * 3 and int(np.prod(rs)) == 91 * h * 3, (ts, rs)
                 keep.extend([t, r])           # redirect to the caller's buffers (zero copy)
-                trace_pp[0] = t.ctypes.data_as(_u64p)
-                rand_pp[0] = r.ctypes.data_as(_u64p)
+                trace_pp[0] = tp
+                rand_pp[0] = rp
                 return 0
             except Exception as e:  # noqa: BLE001 - must not propagate through the C frame
                 err.append(e)
