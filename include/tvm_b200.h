@@ -41,6 +41,25 @@ int tvm_ctx_create(tvm_ctx **out, int cuda_device);
 void tvm_ctx_destroy(tvm_ctx *ctx);
 int tvm_ctx_set_stream(tvm_ctx *ctx, void *cuda_stream /* cudaStream_t, NULL = own stream */);
 int tvm_ctx_synchronize(tvm_ctx *ctx);
+
+/* Multi-GPU: one process (and one context) per GPU.  A proof is sharded by evaluation-domain cosets
+ * (mirroring the reference's own coset decomposition, stark.rs:824-885): rank g of
+ * `world` owns the LDT-domain rows i with (i mod 8) mod world == g; trace columns are interpolated
+ * column-sharded.  The library needs two collectives from the host's communication layer (NCCL through
+ * torch.distributed in this repo, ncclAllGather / ncclAllReduce directly from Rust).  Both operate IN
+ * PLACE on device memory and must be ordered on `cuda_stream` (or complete before returning):
+ *   all_gather:  rank g contributes the bytes_per_rank bytes at dev_buf + g*bytes_per_rank; afterwards
+ *                every rank holds all world*bytes_per_rank bytes;
+ *   all_reduce_sum_u64: element-wise wrapping sum of `count` uint64 over all ranks.
+ * Return 0 on success.  world must be 1, 2, 4 or 8.  Every rank must call tvm_prove with identical
+ * arguments (each rank only reads its own column slice of the traces) and obtains the identical proof. */
+typedef struct tvm_comm {
+  int rank, world;
+  void *user;
+  int (*all_gather)(void *user, void *dev_buf, size_t bytes_per_rank, void *cuda_stream);
+  int (*all_reduce_sum_u64)(void *user, uint64_t *dev_buf, size_t count, void *cuda_stream);
+} tvm_comm;
+int tvm_ctx_set_comm(tvm_ctx *ctx, const tvm_comm *comm /* NULL = single GPU */);
 const char *tvm_strerror(int code);
 const char *tvm_last_error(const tvm_ctx *ctx);
 uint64_t tvm_launch_count(const tvm_ctx *ctx); /* CUDA kernels launched through this ctx */

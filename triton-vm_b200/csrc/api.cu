@@ -69,31 +69,43 @@ void from_mont_run(Ctx &c, u64 *d, size_t n) {
   TVM_CUDA(cudaGetLastError());
 }
 
-void lde_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned num_rand, unsigned log2_trace,
-             unsigned log2_cosets, u64 offset_mont, size_t ncols, u64 *d_coef, u64 *d_out, u64 *d_tmp) {
+// 1) interpolate on the trace domain (offset 1), fold in zerofier*randomizer, pre-scale by offset^j:
+//    d_coef[col*coef_stride + j], j < n + rand_pad (entries num_rand <= j-n < rand_pad are zeroed)
+void lde_interpolate_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned num_rand, unsigned rand_pad, unsigned log2_trace,
+                         u64 offset_mont, size_t ncols, u64 *d_coef, size_t coef_stride, u64 *d_tmp) {
   const size_t n = (size_t)1 << log2_trace;
   if (num_rand > n) throw ApiError{TVM_ERR_INVALID_ARG, "more trace randomizers than trace rows"};
-  // 1) interpolate on the trace domain (offset 1), fold in zerofier*randomizer, pre-scale by offset^j
   NttJob inv{};
   inv.in = d_trace; inv.in_cstride = n;
-  inv.out = d_coef; inv.out_cstride = 2 * n;
+  inv.out = d_coef; inv.out_cstride = coef_stride;
   inv.tmp = d_tmp;
   inv.log_n = (int)log2_trace; inv.ncols = ncols; inv.inverse = true;
   inv.has_post = true;
   inv.post = c.get_pow_tab(offset_mont, (int)log2_trace + 1);
-  inv.rand = d_rand; inv.rand_count = d_rand ? num_rand : 0; inv.rand_pad = inv.rand_count;
-  // the single-pass path has no pass A; force the layout the LDE needs by always using tmp
+  inv.rand = d_rand; inv.rand_count = d_rand ? num_rand : 0; inv.rand_pad = d_rand ? std::max(rand_pad, num_rand) : 0;
   ntt_run(c, inv);
-  // 2) evaluate on the r cosets
+}
+// 2) evaluate pre-scaled coefficient columns on `num_cosets` of the 2^log2_cosets cosets
+//    (domain coset coset_first + coset_step*y for y < num_cosets): d_out[(col*num_cosets + y)*n + k]
+void lde_evaluate_run(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_count, unsigned log2_trace, unsigned log2_cosets,
+                      unsigned coset_first, unsigned coset_step, unsigned num_cosets, size_t ncols, u64 *d_out, u64 *d_tmp) {
+  const size_t n = (size_t)1 << log2_trace;
   NttJob fwd{};
-  fwd.in = d_coef; fwd.in_cstride = 2 * n;
-  fwd.out = d_out; fwd.out_cstride = n;  // per (col*r + coset)
+  fwd.in = d_coef; fwd.in_cstride = coef_stride;
+  fwd.out = d_out; fwd.out_cstride = n;  // per (col*num_cosets + y)
   fwd.tmp = d_tmp;
   fwd.log_n = (int)log2_trace; fwd.ncols = ncols; fwd.inverse = false;
-  fwd.num_cosets = 1 << log2_cosets;
+  fwd.num_cosets = (int)num_cosets; fwd.total_cosets = 1 << log2_cosets;
+  fwd.coset_first = coset_first; fwd.coset_step = coset_step;
   fwd.coset_pre = true;
-  fwd.fold_count = inv.rand_count;
+  fwd.fold_count = fold_count;
   ntt_run(c, fwd);
+}
+void lde_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned num_rand, unsigned log2_trace,
+             unsigned log2_cosets, u64 offset_mont, size_t ncols, u64 *d_coef, u64 *d_out, u64 *d_tmp) {
+  const size_t n = (size_t)1 << log2_trace;
+  lde_interpolate_run(c, d_trace, d_rand, num_rand, num_rand, log2_trace, offset_mont, ncols, d_coef, 2 * n, d_tmp);
+  lde_evaluate_run(c, d_coef, 2 * n, d_rand ? num_rand : 0, log2_trace, log2_cosets, 0, 1, 1u << log2_cosets, ncols, d_out, d_tmp);
 }
 
 }  // namespace tvm
@@ -148,6 +160,17 @@ int tvm_ctx_set_stream(tvm_ctx *ctx, void *stream) {
   if (c__->own_stream) { cudaStreamDestroy(c__->stream); c__->own_stream = false; }
   if (stream) c__->stream = (cudaStream_t)stream;
   else { TVM_CUDA(cudaStreamCreateWithFlags(&c__->stream, cudaStreamNonBlocking)); c__->own_stream = true; }
+  TVM_API_END
+}
+
+int tvm_ctx_set_comm(tvm_ctx *ctx, const tvm_comm *comm) {
+  if (!ctx) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  if (!comm) { c__->comm = tvm_comm{0, 1, nullptr, nullptr, nullptr}; return TVM_OK; }
+  const int w = comm->world;
+  if (!(w == 1 || w == 2 || w == 4 || w == 8) || comm->rank < 0 || comm->rank >= w) throw ApiError{TVM_ERR_INVALID_ARG, "comm: world must be 1, 2, 4 or 8 and 0 <= rank < world"};
+  if (w > 1 && (!comm->all_gather || !comm->all_reduce_sum_u64)) throw ApiError{TVM_ERR_INVALID_ARG, "comm: missing collective callbacks"};
+  c__->comm = *comm;
   TVM_API_END
 }
 
@@ -341,7 +364,7 @@ int tvm_air_quotient_dev(tvm_ctx *ctx, const uint64_t *d_main, size_t main_strid
   u64 *d = (u64 *)c__->scratch_get(3, (nc + nw) * 8);
   TVM_CUDA(cudaMemcpyAsync(d, h.data(), (nc + nw) * 8, cudaMemcpyHostToDevice, c__->stream));
   TVM_CUDA(cudaStreamSynchronize(c__->stream));  // h is a stack-owned staging buffer
-  air_quotient_run(*c__, (const u64 *)d_main, main_stride, (const u64 *)d_aux, aux_stride, d, d + nc, log2_trace, log2_cosets,
+  air_quotient_run(*c__, (const u64 *)d_main, main_stride, (const u64 *)d_aux, aux_stride, d, d + nc, log2_trace, log2_cosets, 0, 1, 1u << log2_cosets,
                    to_mont(offset_canon), (u64 *)d_out, out_stride);
   TVM_API_END
 }

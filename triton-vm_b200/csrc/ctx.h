@@ -40,6 +40,10 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // multi-GPU communication layer supplied by the host (tvm_ctx_set_comm); world == 1: no-ops
+  tvm_comm comm{0, 1, nullptr, nullptr, nullptr};
+  void all_gather(void *dev_buf, size_t bytes_per_rank);
+  void all_reduce_sum(u64 *dev_buf, size_t count);
   cudaStream_t copy_stream = nullptr;   // host<->device staging overlapped with compute (created on first use)
   std::vector<cudaEvent_t> copy_events; // recycled per-batch "upload done" events
   cudaStream_t get_copy_stream();

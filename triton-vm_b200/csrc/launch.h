@@ -20,7 +20,9 @@ struct NttJob {
   size_t ncols;
   bool inverse;
   // coset mode (forward only): evaluate on num_cosets cosets; pre table = w_{num_cosets * n}
-  int num_cosets = 1;
+  int num_cosets = 1;       // cosets evaluated by this job (a shard of the domain's cosets)
+  int total_cosets = 0;     // r: the pre-scale table is w_{r n}; 0 = num_cosets
+  unsigned coset_first = 0, coset_step = 1;   // job coset y is domain coset coset_first + coset_step*y
   bool coset_pre = false;
   unsigned fold_count = 0;
   // output post-processing
@@ -34,13 +36,20 @@ struct NttJob {
 void ntt_run(Ctx &c, const NttJob &job);
 void lde_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned num_rand, unsigned log2_trace,
              unsigned log2_cosets, u64 offset_mont, size_t ncols, u64 *d_coef, u64 *d_out, u64 *d_tmp);
+void lde_interpolate_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned num_rand, unsigned rand_pad, unsigned log2_trace,
+                         u64 offset_mont, size_t ncols, u64 *d_coef, size_t coef_stride, u64 *d_tmp);
+void lde_evaluate_run(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_count, unsigned log2_trace, unsigned log2_cosets,
+                      unsigned coset_first, unsigned coset_step, unsigned num_cosets, size_t ncols, u64 *d_out, u64 *d_tmp);
 void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, unsigned ncols, int log_r, u64 *digests);
 void merkle_run(Ctx &c, u64 *nodes, size_t nleaves);
 void xfe_leaves_run(Ctx &c, const u64 *cw, size_t stride, size_t n, u64 *leaves);
 void to_mont_run(Ctx &c, u64 *d, size_t n);
 void from_mont_run(Ctx &c, u64 *d, size_t n);
+// evaluates on `num_cosets` of the 2^log_r cosets (domain coset coset_first + coset_step*y); tables and
+// output hold only those cosets ([col][y][k])
 void air_quotient_run(Ctx &c, const u64 *d_main, size_t main_stride, const u64 *d_aux, size_t aux_stride,
                       const u64 *d_challenges, const u64 *d_weights, unsigned log_n, unsigned log_r,
+                      unsigned coset_first, unsigned coset_step, unsigned num_cosets,
                       u64 offset_mont, u64 *d_out, size_t out_stride);
 int translate_exception(Ctx *c);
 

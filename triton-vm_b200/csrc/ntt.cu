@@ -135,6 +135,7 @@ struct PassA {
   int has_pre;         // coset pre-scale enabled
   PowTab pre;          // w_{r n}^e
   unsigned fold_count; // #coefficients j < fold_count that receive + w_r^c * in[n + j]
+  unsigned coset_first, coset_step;   // grid.y index y evaluates coset coset_first + coset_step*y (shard of the r cosets)
 };
 
 template <bool INV>
@@ -145,10 +146,10 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_a_kernel(PassA p, const 
   u64 *tw = smem, *tile = smem + N;
   const int log_n1 = p.log_n - p.LT;
   const size_t n = (size_t)1 << p.log_n;
-  const unsigned coset = blockIdx.y, col = blockIdx.z;
+  const unsigned coset = p.coset_first + p.coset_step * blockIdx.y, col = blockIdx.z;
   const unsigned j1_0 = blockIdx.x << p.log_t;
   const u64 *in = p.in + (size_t)col * p.in_cstride;
-  u64 *out = p.out + ((size_t)col * gridDim.y + coset) * n;
+  u64 *out = p.out + ((size_t)col * gridDim.y + blockIdx.y) * n;
 
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = __ldg(tile_tw + i);
   u64 fold_factor = 0;
@@ -238,6 +239,17 @@ u64 root_of_unity_mont(unsigned log2n) {
   u64 r = to_mont(ROOT_2_32_CANON);
   for (unsigned i = log2n; i < 32; i++) r = fmul(r, r);
   return r;
+}
+
+void Ctx::all_gather(void *dev_buf, size_t bytes_per_rank) {
+  if (comm.world <= 1) return;
+  if (!comm.all_gather || comm.all_gather(comm.user, dev_buf, bytes_per_rank, (void *)stream))
+    throw ApiError{TVM_ERR_INVALID_ARG, "all_gather callback failed"};
+}
+void Ctx::all_reduce_sum(u64 *dev_buf, size_t count) {
+  if (comm.world <= 1) return;
+  if (!comm.all_reduce_sum_u64 || comm.all_reduce_sum_u64(comm.user, dev_buf, count, (void *)stream))
+    throw ApiError{TVM_ERR_INVALID_ARG, "all_reduce callback failed"};
 }
 
 cudaStream_t Ctx::get_copy_stream() {
@@ -395,10 +407,12 @@ void ntt_run(Ctx &c, const NttJob &job) {
     a.has_pre = job.coset_pre;
     a.fold_count = job.fold_count;
     if (job.coset_pre || job.fold_count) {
+      const int tot = job.total_cosets ? job.total_cosets : job.num_cosets;
       int lr = 0;
-      while ((1 << lr) < job.num_cosets) lr++;
+      while ((1 << lr) < tot) lr++;
       a.pre = c.get_pow_tab(root_of_unity_mont(L + lr), L + lr);
     }
+    a.coset_first = job.coset_first; a.coset_step = job.coset_step;
     size_t smem = tile_smem_bytes(LA, a.log_t);
     dim3 grid((unsigned)(((size_t)1 << log_n1) >> a.log_t), job.num_cosets, (unsigned)job.ncols);
     const u64 *tw = c.get_tile_tw(LA, job.inverse);

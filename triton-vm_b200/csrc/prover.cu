@@ -130,29 +130,21 @@ std::vector<unsigned> auth_structure_node_indices(size_t num_leafs, const std::v
   return out;
 }
 
-void lde_batched(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned h, unsigned log_n, unsigned log_r, u64 offset_mont, size_t ncols,
-                 u64 *d_coef, u64 *d_lde, u64 *d_tmp, size_t tmp_cols) {
-  const size_t n = (size_t)1 << log_n, N = n << log_r;
-  for (size_t c0 = 0; c0 < ncols; c0 += tmp_cols) {
-    size_t b = std::min(tmp_cols, ncols - c0);
-    lde_run(c, d_trace + c0 * n, d_rand ? d_rand + c0 * h : nullptr, h, log_n, log_r, offset_mont, b, d_coef + c0 * 2 * n,
-            d_lde + c0 * N, d_tmp);
-  }
-}
+// Shard of the evaluation domain owned by this rank: domain coset first + step*y for y < count
+// (SURVEY.md 8(e)); world == 1 owns all r cosets.
+struct Shard {
+  unsigned first, step, count;
+  int log_w;
+};
 
-// forward coset-LDE of already pre-scaled coefficient columns (stride 2n, upper half folded)
-void coef_to_lde(Ctx &c, const u64 *d_coef, size_t ncols, unsigned log_n, unsigned log_r, unsigned fold_count, u64 *d_lde, u64 *d_tmp,
-                 size_t tmp_cols) {
-  const size_t n = (size_t)1 << log_n, N = n << log_r;
+// forward coset-LDE of pre-scaled coefficient columns onto this rank's cosets, in batches that fit d_tmp
+void evaluate_cols(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_count, size_t ncols, unsigned log_n, unsigned log_r,
+                   const Shard &sh, u64 *d_lde, u64 *d_tmp, size_t tmp_cols) {
+  const size_t n = (size_t)1 << log_n, n_loc = n * sh.count;
   for (size_t c0 = 0; c0 < ncols; c0 += tmp_cols) {
     size_t b = std::min(tmp_cols, ncols - c0);
-    NttJob fwd{};
-    fwd.in = d_coef + c0 * 2 * n; fwd.in_cstride = 2 * n;
-    fwd.out = d_lde + c0 * N; fwd.out_cstride = n;
-    fwd.tmp = d_tmp;
-    fwd.log_n = (int)log_n; fwd.ncols = b; fwd.inverse = false;
-    fwd.num_cosets = 1 << log_r; fwd.coset_pre = true; fwd.fold_count = fold_count;
-    ntt_run(c, fwd);
+    lde_evaluate_run(c, d_coef + c0 * coef_stride, coef_stride, fold_count, log_n, log_r, sh.first, sh.step, sh.count, b,
+                     d_lde + c0 * n_loc, d_tmp);
   }
 }
 
@@ -178,6 +170,14 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   const u64 off = to_mont(d.ldt_offset);
   const size_t NM = TVM_NUM_MAIN_COLUMNS, NA = TVM_NUM_AUX_COLUMNS, NA3 = 3 * NA;
   const size_t tmp_cols = 16;
+  // multi-GPU shard (tvm_ctx_set_comm): this rank owns r/W cosets = N/W rows, and 1/W of the columns
+  // for the column-sharded interpolation
+  const unsigned W = (unsigned)c.comm.world, rank = (unsigned)c.comm.rank;
+  if (W > (1u << log_r)) throw ApiError{TVM_ERR_INVALID_ARG, "more ranks than cosets"};
+  const Shard sh{rank, W, (1u << log_r) / W, ilog2(W)};
+  const size_t NL = n * sh.count;                       // rows of the LDT domain held by this rank
+  const size_t hpad = std::min(n, (h + 63) & ~(size_t)63);
+  const size_t cs = n + hpad;                           // stride of a table column's interpolant coefficients
   cudaEvent_t ev[20];
   int nev = 0;
   auto mark = [&]() {
@@ -195,49 +195,87 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   mark();  // 0
 
   // ---- main table: upload, LDE, row hashes, Merkle tree (stark.rs:359-374) -------------------------
-  u64 *d_tmp = mem.words(tmp_cols * N);
+  u64 *d_tmp = mem.words(std::max(tmp_cols * NL, 3 * N));
   mark();  // (kept for the stage table: uploads are issued asynchronously below)
-  // The trace is uploaded in column batches on the copy stream while the compute stream converts the
-  // batches that have landed to Montgomery form and extends them (host or device source pointers).
-  u64 *d_main_trace = mem.words(NM * n + NM * h);
-  u64 *d_main_rand = d_main_trace + NM * n;
-  u64 *d_main_coef = mem.words(NM * 2 * n);
-  u64 *d_main_lde = mem.words(NM * N);
-  cudaStream_t cs = c.get_copy_stream();
+  cudaStream_t cs_copy = c.get_copy_stream();
   size_t nevt = 0;
-  {
-    cudaEvent_t e = c.get_copy_event(nevt++);   // the pool may hand out blocks the compute stream still uses
-    TVM_CUDA(cudaEventRecord(e, c.stream));
-    TVM_CUDA(cudaStreamWaitEvent(cs, e, 0));
-  }
-  TVM_CUDA(cudaMemcpyAsync(d_main_rand, h_main_rand, NM * h * 8, cudaMemcpyDefault, cs));
-  const size_t evt_main0 = nevt;
-  for (size_t c0 = 0; c0 < NM; c0 += tmp_cols) {
-    size_t b = std::min(tmp_cols, NM - c0);
-    TVM_CUDA(cudaMemcpyAsync(d_main_trace + c0 * n, h_main_trace + c0 * n, b * n * 8, cudaMemcpyDefault, cs));
-    TVM_CUDA(cudaEventRecord(c.get_copy_event(nevt++), cs));
-  }
-  TVM_CUDA(cudaMemsetAsync(d_main_coef, 0, NM * 2 * n * 8, c.stream));
-  for (size_t c0 = 0, bi = 0; c0 < NM; c0 += tmp_cols, bi++) {
-    size_t b = std::min(tmp_cols, NM - c0);
-    TVM_CUDA(cudaStreamWaitEvent(c.stream, c.get_copy_event(evt_main0 + bi), 0));
-    if (c0 == 0) to_mont_run(c, d_main_rand, NM * h);
-    to_mont_run(c, d_main_trace + c0 * n, b * n);
-    lde_run(c, d_main_trace + c0 * n, d_main_rand + c0 * h, (unsigned)h, log_n, log_r, off, b, d_main_coef + c0 * 2 * n,
-            d_main_lde + c0 * N, d_tmp);
-  }
-  mark();  // 1: main LDE
-  u64 *d_main_nodes = mem.words(2 * N * 5);
-  TVM_CUDA(cudaMemsetAsync(d_main_nodes, 0, 40, c.stream));
-  hash_rows_run(c, d_main_lde, N, N, (unsigned)NM, (int)log_r, d_main_nodes + 5 * N);
-  merkle_run(c, d_main_nodes, N);
-  {
-    std::vector<u64> root = d2h(c, d_main_nodes + 5, 5);
+  // Upload + interpolate + extend one table.  `xf` = 1: B-field columns [ncols][n]; 3: X-field columns in the ABI's
+  // interleaved layout [ncols][n][3] (de-interleaved into 3 planar columns each).  The trace is uploaded in column
+  // batches on the copy stream while the compute stream converts the batches that have landed to Montgomery form and
+  // transforms them (source pointers may be host or device memory).  With W > 1 ranks each rank uploads and
+  // interpolates only its block of columns; the coefficient blocks are then all-gathered and every rank evaluates
+  // all columns on its own cosets.
+  auto extend_table = [&](const u64 *src_trace, const u64 *src_rand, size_t ncols, int xf, u64 *&d_coef, u64 *&d_lde) {
+    const size_t cpr = (ncols + W - 1) / W;             // columns per rank (the last block may be short)
+    const size_t own0 = std::min(ncols, rank * cpr), own1 = std::min(ncols, own0 + cpr), nown = own1 - own0;
+    const size_t bcols = ncols * xf;                    // B-field columns
+    d_coef = mem.words(cpr * W * xf * cs);
+    d_lde = mem.words(bcols * NL);
+    u64 *d_in = mem.words(std::max<size_t>(1, nown) * xf * n + ncols * xf * h);
+    u64 *d_rand_in = d_in + std::max<size_t>(1, nown) * xf * n;
+    u64 *d_planar = xf == 3 ? mem.words(std::max<size_t>(1, nown) * 3 * n + ncols * 3 * h) : d_in;
+    u64 *d_rand = xf == 3 ? d_planar + std::max<size_t>(1, nown) * 3 * n : d_rand_in;
+    {
+      cudaEvent_t e = c.get_copy_event(nevt++);   // the pool may hand out blocks the compute stream still uses
+      TVM_CUDA(cudaEventRecord(e, c.stream));
+      TVM_CUDA(cudaStreamWaitEvent(cs_copy, e, 0));
+    }
+    TVM_CUDA(cudaMemcpyAsync(d_rand_in, src_rand, ncols * xf * h * 8, cudaMemcpyDefault, cs_copy));
+    const size_t bstep = std::max<size_t>(1, tmp_cols / xf);   // columns per batch
+    const size_t evt0 = nevt;
+    for (size_t c0 = 0; c0 < nown; c0 += bstep) {
+      size_t b = std::min(bstep, nown - c0);
+      TVM_CUDA(cudaMemcpyAsync(d_in + c0 * xf * n, src_trace + (own0 + c0) * xf * n, b * xf * n * 8, cudaMemcpyDefault, cs_copy));
+      TVM_CUDA(cudaEventRecord(c.get_copy_event(nevt++), cs_copy));
+    }
+    if (nown == 0) TVM_CUDA(cudaEventRecord(c.get_copy_event(nevt++), cs_copy));
+    for (size_t c0 = 0, bi = 0; c0 < std::max<size_t>(1, nown); c0 += bstep, bi++) {
+      TVM_CUDA(cudaStreamWaitEvent(c.stream, c.get_copy_event(evt0 + bi), 0));
+      if (c0 == 0) {
+        to_mont_run(c, d_rand_in, ncols * xf * h);
+        if (xf == 3) deinterleave3_run(c, d_rand_in, d_rand, h, ncols);
+      }
+      if (nown == 0) break;
+      size_t b = std::min(bstep, nown - c0);
+      to_mont_run(c, d_in + c0 * xf * n, b * xf * n);
+      if (xf == 3) deinterleave3_run(c, d_in + c0 * 3 * n, d_planar + c0 * 3 * n, n, b);
+      const size_t q0 = (own0 + c0) * xf;               // first B-field column of the batch
+      lde_interpolate_run(c, d_planar + c0 * xf * n, d_rand + q0 * h, (unsigned)h, (unsigned)hpad, log_n, off, b * xf,
+                          d_coef + q0 * cs, cs, d_tmp);
+      if (W == 1) lde_evaluate_run(c, d_coef + q0 * cs, cs, (unsigned)h, log_n, log_r, sh.first, sh.step, sh.count, b * xf,
+                                   d_lde + q0 * NL, d_tmp);
+    }
+    if (W > 1) {
+      c.all_gather(d_coef, cpr * xf * cs * 8);
+      evaluate_cols(c, d_coef, cs, (unsigned)h, bcols, log_n, log_r, sh, d_lde, d_tmp, tmp_cols);
+    }
+    if (xf == 3) mem.release(d_planar);
+    mem.release(d_in);
+  };
+  // Row digests of this rank's rows -> leaves of the full tree (all-gathered across ranks), then the tree.
+  auto commit_rows = [&](const u64 *d_lde, unsigned ncols, u64 *d_nodes) {
+    TVM_CUDA(cudaMemsetAsync(d_nodes, 0, 40, c.stream));
+    if (W == 1) {
+      hash_rows_run(c, d_lde, N, N, ncols, (int)log_r, d_nodes + 5 * N);
+    } else {
+      u64 *d_dig = mem.words(5 * N);                    // [rank][y][k][5]
+      hash_rows_run(c, d_lde, NL, NL, ncols, 0, d_dig + (size_t)rank * NL * 5);
+      c.all_gather(d_dig, NL * 40);
+      shard_digests_to_natural_run(c, d_dig, d_nodes + 5 * N, (int)log_n, (int)log_r, sh.log_w);
+      mem.release(d_dig);
+    }
+    merkle_run(c, d_nodes, N);
+    std::vector<u64> root = d2h(c, d_nodes + 5, 5);
     for (auto &v : root) v = from_mont(v);
     ps.enqueue(ItemKind::MerkleRoot, root);
-  }
+  };
+
+  u64 *d_main_coef = nullptr, *d_main_lde = nullptr;
+  extend_table(h_main_trace, h_main_rand, NM, 1, d_main_coef, d_main_lde);
+  mark();  // 1: main LDE
+  u64 *d_main_nodes = mem.words(2 * N * 5);
+  commit_rows(d_main_lde, (unsigned)NM, d_main_nodes);
   mark();  // 2: main Merkle
-  mem.release(d_main_trace);
 
   // ---- challenges (stark.rs:374-376, challenges.rs:88-135) -------------------------------------------
   std::vector<xfe> ch = ps.sponge.sample_scalars(59);
@@ -263,50 +301,12 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   if (int crc = aux_cb(aux_user, ch_canon.data(), &h_aux_trace, &h_aux_rand)) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback failed: " + std::to_string(crc)};
   if (!h_aux_trace || !h_aux_rand) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback returned a null buffer"};
   mark();  // extend (caller)
-  u64 *d_aux_in = mem.words(NA * n * 3 + NA * h * 3);
-  u64 *d_aux_trace = mem.words(NA3 * n + NA3 * h);
-  u64 *d_aux_rand = d_aux_trace + NA3 * n;
-  u64 *d_aux_coef = mem.words(NA3 * 2 * n);
-  u64 *d_aux_lde = mem.words(NA3 * N);
-  {
-    cudaEvent_t e = c.get_copy_event(nevt++);
-    TVM_CUDA(cudaEventRecord(e, c.stream));
-    TVM_CUDA(cudaStreamWaitEvent(cs, e, 0));
-  }
-  TVM_CUDA(cudaMemcpyAsync(d_aux_in + NA * n * 3, h_aux_rand, NA * h * 3 * 8, cudaMemcpyDefault, cs));
-  const size_t xcols = tmp_cols / 3;   // X-field columns per batch (3 B-field columns each)
-  const size_t evt_aux0 = nevt;
-  for (size_t c0 = 0; c0 < NA; c0 += xcols) {
-    size_t b = std::min(xcols, NA - c0);
-    TVM_CUDA(cudaMemcpyAsync(d_aux_in + c0 * n * 3, h_aux_trace + c0 * n * 3, b * n * 3 * 8, cudaMemcpyDefault, cs));
-    TVM_CUDA(cudaEventRecord(c.get_copy_event(nevt++), cs));
-  }
-  TVM_CUDA(cudaMemsetAsync(d_aux_coef, 0, NA3 * 2 * n * 8, c.stream));
-  for (size_t c0 = 0, bi = 0; c0 < NA; c0 += xcols, bi++) {
-    size_t b = std::min(xcols, NA - c0);
-    TVM_CUDA(cudaStreamWaitEvent(c.stream, c.get_copy_event(evt_aux0 + bi), 0));
-    if (c0 == 0) {
-      to_mont_run(c, d_aux_in + NA * n * 3, NA * h * 3);
-      deinterleave3_run(c, d_aux_in + NA * n * 3, d_aux_rand, h, NA);
-    }
-    to_mont_run(c, d_aux_in + c0 * n * 3, b * n * 3);
-    deinterleave3_run(c, d_aux_in + c0 * n * 3, d_aux_trace + 3 * c0 * n, n, b);
-    lde_run(c, d_aux_trace + 3 * c0 * n, d_aux_rand + 3 * c0 * h, (unsigned)h, log_n, log_r, off, 3 * b, d_aux_coef + 3 * c0 * 2 * n,
-            d_aux_lde + 3 * c0 * N, d_tmp);
-  }
-  mem.release(d_aux_in);
+  u64 *d_aux_coef = nullptr, *d_aux_lde = nullptr;
+  extend_table(h_aux_trace, h_aux_rand, NA, 3, d_aux_coef, d_aux_lde);
   mark();  // 4: aux LDE
   u64 *d_aux_nodes = mem.words(2 * N * 5);
-  TVM_CUDA(cudaMemsetAsync(d_aux_nodes, 0, 40, c.stream));
-  hash_rows_run(c, d_aux_lde, N, N, (unsigned)NA3, (int)log_r, d_aux_nodes + 5 * N);
-  merkle_run(c, d_aux_nodes, N);
-  {
-    std::vector<u64> root = d2h(c, d_aux_nodes + 5, 5);
-    for (auto &v : root) v = from_mont(v);
-    ps.enqueue(ItemKind::MerkleRoot, root);
-  }
+  commit_rows(d_aux_lde, (unsigned)NA3, d_aux_nodes);
   mark();  // 5: aux Merkle
-  mem.release(d_aux_trace);
 
   // ---- quotient codeword (stark.rs:396-411, master_table.rs:1264-1363) ---------------------------------------
   xfe w0 = ps.sponge.sample_scalars(1)[0];
@@ -321,13 +321,15 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   u64 *d_consts = mem.words(consts.size());
   TVM_CUDA(cudaMemcpyAsync(d_consts, consts.data(), consts.size() * 8, cudaMemcpyHostToDevice, c.stream));
   TVM_CUDA(cudaStreamSynchronize(c.stream));
-  u64 *d_quot = mem.words(3 * N);
-  air_quotient_run(c, d_main_lde, N, d_aux_lde, N, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, off, d_quot, N);
+  u64 *d_quot = mem.words(3 * N);   // gather buffer [rank][3][NL]; this rank's rows go to its own block
+  air_quotient_run(c, d_main_lde, NL, d_aux_lde, NL, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, sh.first, sh.step,
+                   sh.count, off, d_quot + (size_t)rank * 3 * NL, NL);
   mark();  // 6: AIR quotient
 
   // interpolate (stark.rs:1224-1231): natural order, iNTT, (coset offset undone inside the segment kernel)
+  c.all_gather(d_quot, 3 * NL * 8);
   u64 *d_qnat = mem.words(3 * N);
-  coset_to_natural_run(c, d_quot, d_qnat, N, N, (int)log_n, (int)log_r, 3);
+  shards_to_natural_run(c, d_quot, d_qnat, 3 * NL, NL, N, (int)log_n, (int)log_r, sh.log_w, 3);
   {
     NttJob inv{};
     inv.in = d_qnat; inv.in_cstride = N; inv.out = d_quot; inv.out_cstride = N; inv.tmp = d_tmp;
@@ -356,18 +358,11 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     for (int i = 0; i < 4; i++) sa.zeta_pow[i] = fpow(zeta, (u64)i);
     segment_chain_run(c, sa);
   }
-  u64 *d_seg_lde = mem.words(15 * N);
-  coef_to_lde(c, d_seg_coef, 15, log_n, log_r, (unsigned)n, d_seg_lde, d_tmp, tmp_cols);
+  u64 *d_seg_lde = mem.words(15 * NL);
+  evaluate_cols(c, d_seg_coef, seg_len, (unsigned)n, 15, log_n, log_r, sh, d_seg_lde, d_tmp, tmp_cols);
   mark();  // 7: quotient LDE
   u64 *d_quot_nodes = mem.words(2 * N * 5);
-  TVM_CUDA(cudaMemsetAsync(d_quot_nodes, 0, 40, c.stream));
-  hash_rows_run(c, d_seg_lde, N, N, 15, (int)log_r, d_quot_nodes + 5 * N);
-  merkle_run(c, d_quot_nodes, N);
-  {
-    std::vector<u64> root = d2h(c, d_quot_nodes + 5, 5);
-    for (auto &v : root) v = from_mont(v);
-    ps.enqueue(ItemKind::MerkleRoot, root);
-  }
+  commit_rows(d_seg_lde, 15, d_quot_nodes);
   mark();  // 8: quotient Merkle
   mem.release(d_qnat);
 
@@ -384,8 +379,8 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   for (int t = 0; t < 4; t++) xpow_vector_run(c, xmulb(pts[t], off_inv), d_pw + (size_t)t * 3 * clen, clen, clen);
   u64 *d_dots = mem.words((NM + NA3 + 15 + 9) * 2 * 3);
   const size_t used = n + h;   // table interpolants have n + h non-zero (pre-scaled) coefficients
-  col_dot_run(c, d_main_coef, clen, NM, used, d_pw, clen, 3 * clen, 2, d_dots);
-  col_dot_run(c, d_aux_coef, clen, NA3, used, d_pw, clen, 3 * clen, 2, d_dots + NM * 6);
+  col_dot_run(c, d_main_coef, cs, NM, used, d_pw, clen, 3 * clen, 2, d_dots);
+  col_dot_run(c, d_aux_coef, cs, NA3, used, d_pw, clen, 3 * clen, 2, d_dots + NM * 6);
   col_dot_run(c, d_seg_coef, seg_len, 15, seg_len, d_pw + 2 * 3 * clen, clen, 3 * clen, 2, d_dots + (NM + NA3) * 6);
   std::vector<u64> dots = d2h(c, d_dots, (NM + NA3 + 15) * 6);
   auto dot_at = [&](size_t col, int v) { const u64 *p = &dots[(col * 2 + v) * 3]; return xmake(p[0], p[1], p[2]); };
@@ -434,8 +429,8 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   TVM_CUDA(cudaStreamSynchronize(c.stream));
   u64 *d_cpr = mem.words(9 * clen);    // combination, p, r polynomials (pre-scaled), 3 planes each
   TVM_CUDA(cudaMemsetAsync(d_cpr, 0, 3 * clen * 8, c.stream));
-  weighted_colsum_run(c, d_main_coef, clen, (unsigned)NM, false, d_wts, used, d_cpr, clen, false);
-  weighted_colsum_run(c, d_aux_coef, clen, (unsigned)NA, true, d_wts + 3 * NM, used, d_cpr, clen, true);
+  weighted_colsum_run(c, d_main_coef, cs, (unsigned)NM, false, d_wts, used, d_cpr, clen, false);
+  weighted_colsum_run(c, d_aux_coef, cs, (unsigned)NA, true, d_wts + 3 * NM, used, d_cpr, clen, true);
   weighted_colsum_run(c, d_seg_coef, seg_len, 5, true, d_wts + 3 * (NM + NA), seg_len, d_cpr + 3 * clen, clen, false);
   weighted_colsum_run(c, d_seg_coef, seg_len, 5, true, d_wts + 3 * (NM + NA + 5), seg_len, d_cpr + 6 * clen, clen, false);
   // values at the out-of-domain points
@@ -448,15 +443,20 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   da.value[1] = combine_planes(dvat(0, 1), dvat(1, 1), dvat(2, 1));
   da.value[2] = combine_planes(dvat(3, 0), dvat(4, 0), dvat(5, 0));
   da.value[3] = combine_planes(dvat(6, 1), dvat(7, 1), dvat(8, 1));
-  u64 *d_cpr_lde = mem.words(9 * N);
-  coef_to_lde(c, d_cpr, 9, log_n, log_r, (unsigned)n, d_cpr_lde, d_tmp, tmp_cols);
+  u64 *d_cpr_lde = mem.words(9 * NL);
+  evaluate_cols(c, d_cpr, clen, (unsigned)n, 9, log_n, log_r, sh, d_cpr_lde, d_tmp, tmp_cols);
+  u64 *d_deep = mem.words(3 * N);   // gather buffer [rank][3][NL]
   u64 *d_fri = mem.words(3 * N);
-  da.cw = d_cpr_lde; da.cw_stride = N; da.out = d_fri; da.out_stride = N;
+  da.cw = d_cpr_lde; da.cw_stride = NL; da.out = d_deep + (size_t)rank * 3 * NL; da.out_stride = NL;
   da.log_n = (int)log_n; da.log_r = (int)log_r;
+  da.coset_first = sh.first; da.coset_step = sh.step; da.num_cosets = sh.count;
   da.dom = c.get_pow_tab(root_of_unity_mont(log_N), (int)log_N);
   da.offset = off;
   for (int t = 0; t < 4; t++) { da.point[t] = pts[t]; da.weight[t] = w_deep[t]; }
   deep_run(c, da);
+  c.all_gather(d_deep, 3 * NL * 8);
+  shards_to_natural_run(c, d_deep, d_fri, 3 * NL, NL, N, (int)log_n, (int)log_r, sh.log_w, 3);
+  mem.release(d_deep);
   mark();  // 10: linear combination + DEEP
 
   // ---- FRI (fri.rs:212-366, 754-772) ------------------------------------------------------------------------------------
@@ -546,7 +546,8 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   // ---- open rows (stark.rs:665-716) ---------------------------------------------------------------------------------------------
   auto open_table = [&](const u64 *table, unsigned ncols, ItemKind kind, const u64 *nodes) {
     TVM_CUDA(cudaMemcpyAsync(d_idx, a_indices.data(), nq * 4, cudaMemcpyHostToDevice, c.stream));
-    gather_rows_run(c, table, N, ncols, d_idx, nq, (int)log_n, (int)log_r, d_gather);
+    gather_rows_run(c, table, NL, ncols, d_idx, nq, (int)log_n, (int)log_r, d_gather, sh.log_w, rank);
+    c.all_reduce_sum(d_gather, (size_t)nq * ncols);
     std::vector<u64> rows = d2h(c, d_gather, (size_t)nq * ncols);
     std::vector<u64> payload;
     payload.push_back(nq);

@@ -71,13 +71,14 @@ __global__ void __launch_bounds__(256) air_zerofier_kernel(ZerofierArgs a) {
 // d_out: 3 planes of r*n words (memory order = coset-major), overwritten.
 void air_quotient_run(Ctx &c, const u64 *d_main, size_t main_stride, const u64 *d_aux, size_t aux_stride,
                       const u64 *d_challenges, const u64 *d_weights, unsigned log_n, unsigned log_r,
+                      unsigned coset_first, unsigned coset_step, unsigned num_cosets,
                       u64 offset_mont, u64 *d_out, size_t out_stride) {
-  if ((1u << log_r) > (unsigned)AIR_MAX_COSETS) throw ApiError{TVM_ERR_UNSUPPORTED, "too many cosets"};
+  if (num_cosets > (unsigned)AIR_MAX_COSETS) throw ApiError{TVM_ERR_UNSUPPORTED, "too many cosets"};
   const unsigned num_weights = AIR_NUM_INIT + AIR_NUM_CONS + AIR_NUM_TRAN + AIR_NUM_TERM;
   AirArgs a{};
   a.main = d_main; a.main_stride = main_stride; a.aux = d_aux; a.aux_stride = aux_stride;
   a.out = d_out; a.out_stride = out_stride;
-  a.nrows = (size_t)1 << (log_n + log_r);
+  a.nrows = (size_t)num_cosets << log_n;
   a.log_n = (int)log_n;
   ZerofierArgs z{};
   z.nrows = a.nrows; z.log_n = a.log_n;
@@ -85,11 +86,10 @@ void air_quotient_run(Ctx &c, const u64 *d_main, size_t main_stride, const u64 *
   z.trace_gen = c.get_pow_tab(wn, (int)log_n);
   z.trace_gen_inv = finv(wn);
   u64 wrn = root_of_unity_mont(log_n + log_r);
-  u64 x = offset_mont;
-  for (unsigned cs = 0; cs < (1u << log_r); cs++) {
-    z.coset_x[cs] = x;
-    z.cons_zerofier_inv[cs] = a.cons_zerofier_inv[cs] = finv(fsub(fpow(x, (u64)1 << log_n), MONT_ONE));
-    x = fmul(x, wrn);
+  for (unsigned y = 0; y < num_cosets; y++) {
+    u64 x = fmul(offset_mont, fpow(wrn, (u64)(coset_first + coset_step * y)));
+    z.coset_x[y] = x;
+    z.cons_zerofier_inv[y] = a.cons_zerofier_inv[y] = finv(fsub(fpow(x, (u64)1 << log_n), MONT_ONE));
   }
   u64 *scratch = (u64 *)c.pool_alloc(sizeof(u64) * (3 * a.nrows + (size_t)AIR_WTAB_WORDS * num_weights));
   z.zi_init = scratch; z.zi_tran = scratch + a.nrows; z.zi_term = scratch + 2 * a.nrows;

@@ -51,11 +51,15 @@ struct SegmentArgs {
 struct DeepArgs {
   const u64 *cw; size_t cw_stride;
   u64 *out; size_t out_stride;
-  int log_n, log_r;
+  int log_n, log_r;                          // trace length 2^log_n, domain of 2^(log_n+log_r) points
+  unsigned coset_first, coset_step, num_cosets;   // local coset y is domain coset coset_first + coset_step*y
   PowTab dom;
   u64 offset;
   xfe point[4], value[4], weight[4];
 };
+void shards_to_natural_run(Ctx &c, const u64 *in, u64 *out, size_t rank_stride, size_t plane_stride, size_t out_stride, int log_n, int log_r,
+                           int log_w, int planes);
+void shard_digests_to_natural_run(Ctx &c, const u64 *in, u64 *out, int log_n, int log_r, int log_w);
 void coset_to_natural_run(Ctx &c, const u64 *in, u64 *out, size_t in_stride, size_t out_stride, int log_n, int log_r, int planes);
 void deinterleave3_run(Ctx &c, const u64 *in, u64 *out, size_t len, size_t ncols);
 void segment_chain_run(Ctx &c, const SegmentArgs &a);
@@ -68,7 +72,7 @@ void deep_run(Ctx &c, const DeepArgs &a);
 void fri_leaves_run(Ctx &c, const u64 *cw, size_t stride, size_t n, u64 *leaves);
 void fri_fold_run(Ctx &c, const u64 *in, size_t in_stride, size_t n, u64 offset_mont, xfe chal, u64 *out, size_t out_stride);
 void gather_rows_run(Ctx &c, const u64 *table, size_t col_stride, unsigned ncols, const unsigned *d_idx, unsigned nidx, int log_n, int log_r,
-                     u64 *d_out);
+                     u64 *d_out, int log_w = 0, unsigned rank = 0);
 void gather_digests_run(Ctx &c, const u64 *nodes, const unsigned *d_idx, unsigned nidx, u64 *d_out);
 void scale_by_powers_run(Ctx &c, u64 *v, size_t stride, int planes, size_t len, PowTab tab);
 

@@ -17,19 +17,43 @@ __device__ __forceinline__ u64 pt(const PowTab &t, u64 e) {
 }
 
 // ---- layout ------------------------------------------------------------------------------
-// coset-major [c][k] (index i = c + r*k) -> natural order, planar vector of `planes` planes
-__global__ void coset_to_natural_kernel(const u64 *in, u64 *out, size_t in_stride, size_t out_stride, int log_n, int log_r,
-                                        int planes) {
-  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Sharded coset-major data -> natural order.  Rank g of `world` owns the domain cosets c with
+// c mod world == g, stored locally as [y][k], y = c div world; after an all-gather the buffer is
+// [rank][...local block...].  Natural index i = c + r*k.
+//   planar variant: element (rank, plane d, y, k) at in[rank*rank_stride + d*plane_stride + y*n + k]
+__global__ void shards_to_natural_kernel(const u64 *in, u64 *out, size_t rank_stride, size_t plane_stride, size_t out_stride, int log_n,
+                                         int log_r, int log_w, int planes) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)1 << (log_n + log_r);
-  if (m >= total) return;
-  size_t c = m >> log_n, k = m & (((size_t)1 << log_n) - 1);
-  size_t i = c + (k << log_r);
-  for (int d = 0; d < planes; d++) out[d * out_stride + i] = in[d * in_stride + m];
+  if (i >= total) return;
+  size_t c = i & (((size_t)1 << log_r) - 1), k = i >> log_r;
+  size_t rank = c & (((size_t)1 << log_w) - 1), y = c >> log_w;
+  const u64 *src = in + rank * rank_stride + (y << log_n) + k;
+  for (int d = 0; d < planes; d++) out[d * out_stride + i] = src[d * plane_stride];
+}
+void shards_to_natural_run(Ctx &c, const u64 *in, u64 *out, size_t rank_stride, size_t plane_stride, size_t out_stride, int log_n, int log_r,
+                           int log_w, int planes) {
+  shards_to_natural_kernel<<<ew_grid((size_t)1 << (log_n + log_r)), EW_THREADS, 0, c.stream>>>(in, out, rank_stride, plane_stride,
+                                                                                                  out_stride, log_n, log_r, log_w, planes);
+  c.launches++;
+  TVM_CUDA(cudaGetLastError());
 }
 void coset_to_natural_run(Ctx &c, const u64 *in, u64 *out, size_t in_stride, size_t out_stride, int log_n, int log_r, int planes) {
-  coset_to_natural_kernel<<<ew_grid((size_t)1 << (log_n + log_r)), EW_THREADS, 0, c.stream>>>(in, out, in_stride, out_stride, log_n,
-                                                                                             log_r, planes);
+  shards_to_natural_run(c, in, out, 0, in_stride, out_stride, log_n, log_r, 0, planes);
+}
+//   record variant (row digests): record of row (rank, y, k) at in[(rank*rows_per_rank + y*n + k)*5 .. +5]
+__global__ void shard_digests_to_natural_kernel(const u64 *in, u64 *out, int log_n, int log_r, int log_w) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)5 << (log_n + log_r);
+  if (t >= total) return;
+  size_t i = t / 5, e = t - 5 * i;
+  size_t c = i & (((size_t)1 << log_r) - 1), k = i >> log_r;
+  size_t rank = c & (((size_t)1 << log_w) - 1), y = c >> log_w;
+  size_t rows_per_rank = (size_t)1 << (log_n + log_r - log_w);
+  out[t] = in[(rank * rows_per_rank + (y << log_n) + k) * 5 + e];
+}
+void shard_digests_to_natural_run(Ctx &c, const u64 *in, u64 *out, int log_n, int log_r, int log_w) {
+  shard_digests_to_natural_kernel<<<ew_grid((size_t)5 << (log_n + log_r)), EW_THREADS, 0, c.stream>>>(in, out, log_n, log_r, log_w);
   c.launches++;
   TVM_CUDA(cudaGetLastError());
 }
@@ -209,14 +233,14 @@ void weighted_colsum_run(Ctx &c, const u64 *cols, size_t col_stride, unsigned nc
 }
 
 // ---- DEEP combination (stark.rs:545-639, 1360-1379, 2096-2103) --------------------------------------
-// in: 3 X-field codewords (main&aux combination, p, r) as 9 coset-major planes; out: the
-// combination codeword in NATURAL order (planar), ready for FRI.
+// in: 3 X-field codewords (main&aux combination, p, r) as 9 coset-major planes holding this rank's
+// cosets; out: the combination codeword in the same (local coset-major, planar) order.
 __global__ void deep_kernel(DeepArgs a) {
   size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = (size_t)1 << (a.log_n + a.log_r);
+  size_t total = (size_t)a.num_cosets << a.log_n;
   if (m >= total) return;
-  size_t c = m >> a.log_n, k = m & (((size_t)1 << a.log_n) - 1);
-  size_t i = c + (k << a.log_r);
+  size_t y = m >> a.log_n, k = m & (((size_t)1 << a.log_n) - 1);
+  size_t i = (a.coset_first + a.coset_step * y) + (k << a.log_r);
   u64 x = fmul(a.offset, pt(a.dom, i));
   const u64 *p = a.cw + m;
   xfe f[3];
@@ -242,10 +266,10 @@ __global__ void deep_kernel(DeepArgs a) {
     xfe term = xmul(xsub(f[src[t]], a.value[t]), dinv);
     acc = xadd(acc, xmul(term, a.weight[t]));
   }
-  a.out[i] = acc.c0; a.out[a.out_stride + i] = acc.c1; a.out[2 * a.out_stride + i] = acc.c2;
+  a.out[m] = acc.c0; a.out[a.out_stride + m] = acc.c1; a.out[2 * a.out_stride + m] = acc.c2;
 }
 void deep_run(Ctx &c, const DeepArgs &a) {
-  deep_kernel<<<ew_grid((size_t)1 << (a.log_n + a.log_r)), EW_THREADS, 0, c.stream>>>(a);
+  deep_kernel<<<ew_grid((size_t)a.num_cosets << a.log_n), EW_THREADS, 0, c.stream>>>(a);
   c.launches++;
   TVM_CUDA(cudaGetLastError());
 }
@@ -290,18 +314,27 @@ void fri_fold_run(Ctx &c, const u64 *in, size_t in_stride, size_t n, u64 offset_
 
 // ---- gathers (MasterTable::reveal_rows, master_table.rs:548-555; authentication structures) ----
 // rows[t][q] = table[q][mem_index(idx[t])], canonical output
+// Sharded tables (log_w > 0): a row this rank does not own is written as zeros, so that the
+// wrapping sum over ranks (all_reduce_sum_u64) reassembles the rows exactly.
 __global__ void gather_rows_kernel(const u64 *table, size_t col_stride, unsigned ncols, const unsigned *idx, unsigned nidx, int log_n,
-                                   int log_r, u64 *out) {
+                                   int log_r, int log_w, unsigned rank, u64 *out) {
   size_t t = blockIdx.x;
   if (t >= nidx) return;
   size_t i = idx[t];
-  size_t m = log_r >= 0 ? ((i & (((size_t)1 << log_r) - 1)) << log_n) + (i >> log_r) : i;
-  for (unsigned q = threadIdx.x; q < ncols; q += blockDim.x) out[t * ncols + q] = from_mont(table[(size_t)q * col_stride + m]);
+  size_t m = i;
+  bool mine = true;
+  if (log_r >= 0) {
+    size_t c = i & (((size_t)1 << log_r) - 1), k = i >> log_r;
+    mine = (c & (((size_t)1 << log_w) - 1)) == rank;
+    m = ((c >> log_w) << log_n) + k;
+  }
+  for (unsigned q = threadIdx.x; q < ncols; q += blockDim.x)
+    out[t * ncols + q] = mine ? from_mont(table[(size_t)q * col_stride + m]) : 0;
 }
 void gather_rows_run(Ctx &c, const u64 *table, size_t col_stride, unsigned ncols, const unsigned *d_idx, unsigned nidx, int log_n, int log_r,
-                     u64 *d_out) {
+                     u64 *d_out, int log_w, unsigned rank) {
   if (!nidx) return;
-  gather_rows_kernel<<<nidx, 128, 0, c.stream>>>(table, col_stride, ncols, d_idx, nidx, log_n, log_r, d_out);
+  gather_rows_kernel<<<nidx, 128, 0, c.stream>>>(table, col_stride, ncols, d_idx, nidx, log_n, log_r, log_w, rank, d_out);
   c.launches++;
   TVM_CUDA(cudaGetLastError());
 }

@@ -57,6 +57,15 @@ class ClaimStruct(ctypes.Structure):
 
 
 AUX_CALLBACK = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _u64p, ctypes.POINTER(_u64p), ctypes.POINTER(_u64p))
+ALL_GATHER_CB = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, ctypes.c_size_t, _vp)
+ALL_REDUCE_CB = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _u64p, ctypes.c_size_t, _vp)
+
+
+class CommStruct(ctypes.Structure):   # tvm_comm
+    _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int), ("user", _vp), ("all_gather", ALL_GATHER_CB),
+                ("all_reduce_sum_u64", ALL_REDUCE_CB)]
+
+
 LDT_FRI = 1
 
 _lib = None
@@ -67,6 +76,7 @@ _SIGNATURES = {
     "tvm_ctx_destroy": (None, [_vp]),
     "tvm_ctx_set_stream": (ctypes.c_int, [_vp, _vp]),
     "tvm_ctx_synchronize": (ctypes.c_int, [_vp]),
+    "tvm_ctx_set_comm": (ctypes.c_int, [_vp, ctypes.POINTER(CommStruct)]),
     "tvm_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "tvm_last_error": (ctypes.c_char_p, [_vp]),
     "tvm_launch_count": (ctypes.c_uint64, [_vp]),
@@ -271,6 +281,17 @@ class Backend:
             raise err[0]
         self._chk(rc)
         return buf[:cap.value].copy()
+
+    def set_comm(self, comm):
+        """Attach a communication layer (tvm_b200.dist.TorchDistComm) so that prove() shards one proof over
+        the ranks of its process group; None detaches."""
+        if comm is None:
+            self._chk(self._l.tvm_ctx_set_comm(self._h, None))
+            self._comm = None
+            return
+        cs = comm.as_struct()
+        self._chk(self._l.tvm_ctx_set_comm(self._h, ctypes.byref(cs)))
+        self._comm = (comm, cs)   # keep the callbacks alive
 
     def last_prove_timings(self):
         names = (ctypes.c_char_p * 20)()
