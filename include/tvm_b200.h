@@ -134,13 +134,20 @@ int tvm_air_quotient_dev(tvm_ctx *ctx, const uint64_t *d_main, size_t main_strid
 typedef struct tvm_params {
   uint32_t security_level;            /* Stark::default(): 160 */
   uint32_t log2_ldt_expansion_factor; /* Stark::default(): 2   */
-  uint32_t ldt_choice;                /* 1 = FRI (LdtChoice::Fri); 0 (auto) and 2 (STIR) -> TVM_ERR_UNSUPPORTED for now */
+  uint32_t ldt_choice;                /* 0 = the reference's heuristic (Stark::default(): FRI below padded height 2^16,
+                                         STIR from there on, stark.rs:1942-1957); 1 = LdtChoice::Fri; 2 = LdtChoice::Stir */
 } tvm_params;
 typedef struct tvm_domains {
   uint64_t padded_height, num_trace_randomizers, randomized_trace_len, trace_len, quotient_len, ldt_len;
   uint64_t ldt_offset;                /* canonical; trace and randomized-trace domains have offset 1 */
   uint64_t num_collinearity_checks, fri_num_rounds, fri_last_round_max_degree;
   uint64_t num_quotient_randomizer_coefficients; /* (h + 1) * 5 X-field coefficients, stark.rs:1320-1322 */
+  /* low-degree test actually used and its round structure (stir.rs:437-567) */
+  uint64_t ldt;                       /* 1 = FRI, 2 = STIR */
+  uint64_t num_first_round_queries;   /* rows opened from each table; h = this + 4*3*2 + 1 (stark.rs:2083-2089) */
+  uint64_t stir_num_rounds;           /* full rounds (0 for FRI) */
+  uint64_t stir_in_domain_queries[16], stir_out_of_domain_queries[16];
+  uint64_t stir_final_num_queries, stir_final_degree;
 } tvm_domains;
 int tvm_derive_domains(const tvm_params *params, uint64_t padded_height, tvm_domains *out);
 

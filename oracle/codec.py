@@ -44,6 +44,15 @@ def enc_vec_xfe(xs):
     return [len(xs)] + enc_xfes(xs)
 
 
+def enc_vec_vec_xfe(vs):
+    """Vec<Vec<XFE>>: count, then each (dynamically sized) element prefixed with its encoded length"""
+    out = [len(vs)]
+    for v in vs:
+        e = enc_vec_xfe(v)
+        out += [len(e)] + e
+    return out
+
+
 def enc_vec_digest(ds):
     out = [len(ds)]
     for d in ds:
@@ -86,6 +95,9 @@ def encode_payload(kind, payload):
     if kind == "FriResponse":                  # fri.rs:99-107 {queried_leaves, auth_structure}
         leaves, auth = payload
         return enc_struct([(enc_vec_xfe(leaves), True), (enc_vec_digest(auth), True)])
+    if kind == "StirResponse":                 # stir.rs:149-158 {queried_leafs: Vec<Vec<XFE>>, auth_structure}
+        leafs, auth = payload
+        return enc_struct([(enc_vec_vec_xfe(leafs), True), (enc_vec_digest(auth), True)])
     raise ValueError(kind)
 
 
@@ -185,6 +197,24 @@ def decode_payload(kind, words, num_main=379, num_aux=91, num_seg=5):
             got[nm] = sub.vec_xfe() if nm == "leaves" else sub.vec_digest()
             if not sub.done(): raise ValueError("field length mismatch")
         out = (got["leaves"], got["auth"])
+    elif kind == "StirResponse":
+        names = ["leafs", "auth"]
+        order = list(reversed(names)) if STRUCT_FIELDS_REVERSED else names
+        got = {}
+        for nm in order:
+            ln = r.one()
+            sub = _Reader(r.take(ln))
+            if nm == "leafs":
+                vs = []
+                for _ in range(sub.one()):
+                    inner = _Reader(sub.take(sub.one()))
+                    vs.append(inner.vec_xfe())
+                    if not inner.done(): raise ValueError("inner length mismatch")
+                got[nm] = vs
+            else:
+                got[nm] = sub.vec_digest()
+            if not sub.done(): raise ValueError("field length mismatch")
+        out = (got["leafs"], got["auth"])
     else:
         raise ValueError(kind)
     if not r.done():

@@ -1,4 +1,4 @@
-"""CPU restatement of `Stark::prove` / `Stark::verify` with the FRI low-degree test.
+"""CPU restatement of `Stark::prove` / `Stark::verify` with the FRI or STIR low-degree test.
 
 Follows the reference file by file:
   parameters      triton-vm/src/stark.rs:1885-2089, low_degree_test/mod.rs:215-360, fri.rs:799-924
@@ -6,6 +6,7 @@ Follows the reference file by file:
   prover          stark.rs:331-719 (+721-798 cached quotient path, 1224-1379 helpers)
   master tables   table/master_table.rs:258-609, 1194-1363
   FRI             low_degree_test/fri.rs:212-366, 393-735, 754-772
+  STIR            low_degree_test/stir.rs (oracle/stir.py)
   verifier        stark.rs:1388-1763
   transcript      oracle/codec.py
 
@@ -15,15 +16,15 @@ randomizer coefficients and the quotient-segment randomizer are inputs.
 Heavy loops run in the C oracle (oracle/c) — still a plain sequential restatement.  Tables are
 numpy uint64 arrays in canonical form: main [379, n]; aux [91, n, 3]; X-field codewords [N, 3].
 
-Not restated yet: STIR (`Stark::default()` picks it for padded heights >= 2^16,
-stark.rs:1942-1958); this oracle therefore corresponds to `stark.with_ldt_choice(LdtChoice::Fri)`.
+`Stark(ldt=None)` follows the reference's heuristic (`Stark::default()`: FRI below padded height 2^16,
+STIR from there on, stark.rs:1942-1958); `ldt="fri"` / `"stir"` is `with_ldt_choice`.
 
 TEST INFRASTRUCTURE ONLY."""
 import math
 
 import numpy as np
 
-from . import codec, corc, field as F, merkle, tip5
+from . import codec, corc, field as F, merkle, stir as stir_mod, tip5
 from .field import P
 
 NUM_MAIN_COLUMNS = 379
@@ -65,12 +66,19 @@ def constraint_degrees():
 
 # ---- parameters ------------------------------------------------------------------------------------
 class Stark:
-    """stark.rs:113-145 — (security_level, log2 expansion factor); FRI only, proven regime."""
+    """stark.rs:113-145 — (security_level, log2 expansion factor, LDT choice); proven regime.
+    `ldt`: "fri", "stir" or None = the reference's heuristic (stark.rs:1942-1957: FRI below padded
+    height 2^16, STIR from there on)."""
 
-    def __init__(self, security_level=160, log2_expansion_factor=2):
+    def __init__(self, security_level=160, log2_expansion_factor=2, ldt=None):
         assert log2_expansion_factor >= 1
+        assert ldt in (None, "fri", "stir")
         self.security_level = security_level
         self.log2_expansion = log2_expansion_factor
+        self.ldt = ldt
+
+    def ldt_choice(self, padded_height):
+        return self.ldt or ("fri" if next_pow2(padded_height).bit_length() - 1 < 16 else "stir")
 
     # low_degree_test/mod.rs:250-300 (ProximityRegime::Proven), fri.rs:832-836
     def num_collinearity_checks(self):
@@ -96,13 +104,20 @@ class Stark:
         padded_height = next_pow2(padded_height)
         log2_ph = padded_height.bit_length() - 1
         checks = self.num_collinearity_checks()
-        h = self.num_trace_randomizers_for(checks)
         expansion = 1 << self.log2_expansion
-        rtl = self.randomized_trace_len(padded_height, h)
+        ldt = self.ldt_choice(padded_height)
+        stir_params = None
         hdb = log2_ph
-        while True:                                               # stark.rs:1975-1984
+        while True:                                               # stark.rs:1972-2060
             hdb += 1
             ldt_len = 1 << (hdb + self.log2_expansion)
+            if ldt == "stir":
+                stir_params = stir_mod.derive(self.security_level, 2, self.log2_expansion, hdb)
+                first_round = stir_params["num_first_round_queries"]
+            else:
+                first_round = checks
+            h = self.num_trace_randomizers_for(first_round)
+            rtl = self.randomized_trace_len(padded_height, h)
             if ldt_len >= rtl * expansion:
                 break
         interpolant_degree = rtl - 1
@@ -120,7 +135,8 @@ class Stark:
                     trace_len=rtl // 2, quotient_len=quotient_len, ldt_len=ldt_len, ldt_offset=F.GENERATOR,
                     num_collinearity_checks=checks, fri_num_rounds=num_rounds,
                     fri_last_round_max_degree=fri_max_degree >> num_rounds,
-                    num_quotient_randomizer_coefficients=self.num_quotient_table_randomizers(h), max_degree=max_degree)
+                    num_quotient_randomizer_coefficients=self.num_quotient_table_randomizers(h), max_degree=max_degree,
+                    ldt=ldt, stir=stir_params, num_first_round_queries=first_round)
 
 
 class Claim:
@@ -499,7 +515,10 @@ def prove(stark, claim, main_trace, main_rand, aux_provider, quot_rand, padded_h
             acc = F.xadd(acc, F.xmul(comps[k][i], w_deep[k]))
         combination[i] = acc
 
-    revealed, fri_rounds = fri_prove(ps, combination, d)
+    if d["ldt"] == "stir":
+        revealed, fri_rounds = stir_mod.prove(ps, [tuple(int(t) for t in v) for v in combination], d["stir"]), []
+    else:
+        revealed, fri_rounds = fri_prove(ps, combination, d)
 
     # zero-knowledge guard (stark.rs:648-663)
     if alpha_pow[1] == 0 and alpha_pow[2] == 0:
@@ -596,8 +615,8 @@ def verify(stark, claim, proof_words, check_air=True):
     for e, w in zip(ood_p, w_quot[:-1]): ood_p_value = F.xadd(ood_p_value, F.xmul(e, w))
     for e, w in zip(ood_r, w_quot[1:]): ood_r_value = F.xadd(ood_r_value, F.xmul(e, w))
 
-    indices, ldt_values = fri_verify(ps, d)
-    q = d["num_collinearity_checks"]
+    indices, ldt_values = stir_mod.verify(ps, d["stir"]) if d["ldt"] == "stir" else fri_verify(ps, d)
+    q = d["num_first_round_queries"]                            # ldt.num_first_round_queries(), stark.rs:1581-1586
     if len(indices) != q or len(ldt_values) != q:
         raise ValueError("IncorrectNumberOfRowIndices")
 

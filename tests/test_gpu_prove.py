@@ -54,3 +54,34 @@ def test_proof_depends_on_every_input(backend):
     again = backend.prove((claim.program_digest, claim.input, claim.output), main, mrand, aux_provider, qrand,
                           security_level=4, log2_expansion=2, padded_height=16)
     assert np.array_equal(base, again)   # deterministic: all randomness is an input
+
+
+def synthetic_stir_instance(security, padded_height, seed):
+    st = S.Stark(security, 2, "stir")
+    d = st.derive(padded_height)
+    rng = np.random.default_rng(seed)
+    n, h = d["trace_len"], d["num_trace_randomizers"]
+    main, mrand = rand_bfes(rng, (379, n)), rand_bfes(rng, (379, h))
+    qrand = rand_bfes(rng, (d["num_quotient_randomizer_coefficients"], 3))
+
+    def aux_provider(challenges):
+        s = int(np.asarray(challenges, dtype=np.uint64).reshape(-1)[:8].sum() % (1 << 32))
+        r = np.random.default_rng(seed * 1000003 + s)
+        return rand_bfes(r, (91, n, 3)), rand_bfes(r, (91, h, 3))
+
+    return st, d, S.Claim([11, 22, 33, 44, 55], [1, 2, 3], [4, 5]), main, mrand, aux_provider, qrand
+
+
+@pytest.mark.parametrize("security,padded_height,seed", [(8, 64, 11), (6, 256, 12), (10, 1024, 13)])
+def test_stir_proof_is_bit_exact_vs_oracle(backend, security, padded_height, seed):
+    """LdtChoice::Stir (what Stark::default() selects from padded height 2^16 on): 0, 2 and 3 full rounds."""
+    import tvm_b200
+    st, d, claim, main, mrand, aux_provider, qrand = synthetic_stir_instance(security, padded_height, seed)
+    assert d["ldt"] == "stir"
+    want, _ = S.prove(st, claim, main, mrand, aux_provider, qrand, padded_height=padded_height)
+    got = backend.prove((claim.program_digest, claim.input, claim.output), main, mrand, aux_provider, qrand,
+                        security_level=security, log2_expansion=2, padded_height=padded_height, ldt_choice=tvm_b200.LDT_STIR)
+    got = [int(v) for v in got]
+    assert len(got) == len(want)
+    assert got == want
+    assert S.verify(st, claim, got, check_air=False)

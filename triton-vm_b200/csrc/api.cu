@@ -371,15 +371,22 @@ int tvm_air_quotient_dev(tvm_ctx *ctx, const uint64_t *d_main, size_t main_strid
 
 int tvm_derive_domains(const tvm_params *p, uint64_t padded_height, tvm_domains *out) {
   if (!p || !out) return TVM_ERR_INVALID_ARG;
-  if (p->ldt_choice != 1) return TVM_ERR_UNSUPPORTED;
   StarkDerived d{};
-  int rc = stark_derive(StarkParams{p->security_level, p->log2_ldt_expansion_factor}, padded_height, d);
+  int rc = stark_derive(StarkParams{p->security_level, p->log2_ldt_expansion_factor, p->ldt_choice}, padded_height, d);
   if (rc) return rc;
   out->padded_height = d.padded_height; out->num_trace_randomizers = d.num_trace_randomizers;
   out->randomized_trace_len = d.randomized_trace_len; out->trace_len = d.trace_len; out->quotient_len = d.quotient_len;
   out->ldt_len = d.ldt_len; out->ldt_offset = d.ldt_offset; out->num_collinearity_checks = d.num_collinearity_checks;
   out->fri_num_rounds = d.fri_num_rounds; out->fri_last_round_max_degree = d.fri_last_round_max_degree;
   out->num_quotient_randomizer_coefficients = d.num_quotient_randomizer_coefficients;
+  out->ldt = (uint64_t)d.ldt; out->num_first_round_queries = d.num_first_round_queries;
+  out->stir_num_rounds = d.ldt == 2 ? (uint64_t)d.stir.num_rounds : 0;
+  for (int i = 0; i < 16; i++) {
+    out->stir_in_domain_queries[i] = d.ldt == 2 && i < d.stir.num_rounds ? d.stir.in_domain[i] : 0;
+    out->stir_out_of_domain_queries[i] = d.ldt == 2 && i < d.stir.num_rounds ? d.stir.out_of_domain[i] : 0;
+  }
+  out->stir_final_num_queries = d.ldt == 2 ? d.stir.final_num_in_domain_queries : 0;
+  out->stir_final_degree = d.ldt == 2 ? d.stir.final_degree : 0;
   return TVM_OK;
 }
 
@@ -387,11 +394,11 @@ int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, ui
               const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user, const uint64_t *quot_rand, uint64_t *proof_out,
               size_t *proof_len) {
   if (!ctx || !params || !claim || !main_trace || !main_rand || !aux_cb || !quot_rand || !proof_len) return TVM_ERR_INVALID_ARG;
-  if (params->ldt_choice != 1) return TVM_ERR_UNSUPPORTED;
+  if (params->ldt_choice > 2) return TVM_ERR_INVALID_ARG;
   TVM_API_BEGIN(ctx)
   ClaimView cv{claim->program_digest, claim->version, claim->input, claim->num_input, claim->output, claim->num_output};
   std::vector<u64> proof;
-  stark_prove(*c__, StarkParams{params->security_level, params->log2_ldt_expansion_factor}, cv, padded_height, (const u64 *)main_trace,
+  stark_prove(*c__, StarkParams{params->security_level, params->log2_ldt_expansion_factor, params->ldt_choice}, cv, padded_height, (const u64 *)main_trace,
               (const u64 *)main_rand, (AuxCallback)aux_cb, aux_user, (const u64 *)quot_rand, proof, &ctx->timings);
   size_t cap = *proof_len;
   *proof_len = proof.size();

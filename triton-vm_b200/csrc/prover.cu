@@ -17,6 +17,7 @@
 #include "launch.h"
 #include "stark.h"
 #include "transcript.h"
+#include "prove_common.h"
 
 namespace tvm {
 #include "air_gen/air_meta.inc"
@@ -32,26 +33,98 @@ static int ilog2(size_t x) {
   return l;
 }
 
+// ---- STIR round structure: StirParameters::try_into_stir (stir.rs:437-567), ProximityRegime::Proven.
+// All f64 expressions keep the reference's operation order (mod.rs:250-300, stir.rs:633-869).
+namespace {
+double rs_rate(unsigned log2_exp) { return 1.0 / (double)(1u << log2_exp); }
+double rs_margin(unsigned log2_exp) { return std::sqrt(rs_rate(log2_exp)); }
+double rs_slackness(unsigned log2_exp) { return rs_margin(log2_exp) / 20.0; }
+double rs_proximity_parameter(unsigned log2_exp) { return 1.0 - rs_margin(log2_exp) - rs_slackness(log2_exp); }
+double rs_log2_list_size(unsigned log2_exp) { return std::log2(1.0 / (2.0 * std::sqrt(rs_rate(log2_exp)) * rs_slackness(log2_exp))); }
+double log2_binomial_coefficient(unsigned long long a, unsigned long long b) {   // stir.rs:854-869 (Kahan-Babuska)
+  double log2_binom = 0.0, compensation = 0.0;
+  unsigned long long m = std::min(b, a - b);
+  for (unsigned long long i = 0; i < m; i++) {
+    double summand = std::log2((double)(a - i)) - std::log2((double)(i + 1));
+    double corrected = summand - compensation;
+    double next = log2_binom + corrected;
+    compensation = (next - log2_binom) - corrected;
+    log2_binom = next;
+  }
+  return log2_binom;
+}
+size_t stir_num_in_domain_queries(unsigned security, unsigned log2_domain_size, unsigned log2_exp) {   // stir.rs:597-609
+  double nq = -(double)security / std::log2(1.0 - rs_proximity_parameter(log2_exp));
+  unsigned long long uniques = (unsigned long long)std::ceil(nq);
+  uniques = std::min(uniques, 1ULL << log2_domain_size);
+  // num_total_in_domain_queries (stir.rs:758-776)
+  unsigned long long k_minus_1 = uniques - 1;
+  unsigned long long domain_len = 1ULL << log2_domain_size;
+  unsigned long long l = std::min(k_minus_1, domain_len / 2);
+  double log2_u_choose_l = log2_binomial_coefficient(domain_len, l);
+  double log2_k_minus_1 = k_minus_1 ? std::max(std::log2((double)k_minus_1), 0.0) : 0.0;
+  double total = ((double)security + log2_k_minus_1 + log2_u_choose_l) / ((double)log2_domain_size - log2_k_minus_1);
+  return (size_t)std::ceil(total);
+}
+size_t stir_num_ood_queries(unsigned security, unsigned log2_poly_degree, unsigned log2_exp) {          // stir.rs:831-842
+  double n = ((double)security - 1.0 + 2.0 * rs_log2_list_size(log2_exp)) / (double)(192u - log2_poly_degree);
+  return (size_t)std::ceil(n);
+}
+}  // namespace
+
+int stir_derive(unsigned security, unsigned log2_ff, unsigned log2_initial_exp, unsigned log2_hdb, StirDerived &out) {
+  if (log2_ff < 2 || log2_initial_exp == 0 || log2_hdb < log2_ff || log2_hdb + log2_initial_exp > 32) return TVM_ERR_LDT_PARAMS;
+  out = StirDerived{};
+  out.folding_factor = (size_t)1 << log2_ff;
+  size_t folded_poly_degree = (((size_t)1 << log2_hdb) - 1) / out.folding_factor;
+  unsigned log2_exp = log2_initial_exp;
+  unsigned log2_folded_domain_size = log2_hdb + log2_initial_exp - log2_ff;
+  while (folded_poly_degree > out.folding_factor) {
+    size_t in_domain = stir_num_in_domain_queries(security, log2_folded_domain_size, log2_exp);
+    unsigned log2_next_exp = log2_exp + log2_ff - 1;
+    size_t ood = stir_num_ood_queries(security, (unsigned)ilog2(folded_poly_degree), log2_next_exp);
+    size_t next_deg = folded_poly_degree / out.folding_factor;
+    if (in_domain + ood > next_deg) break;
+    if (out.num_rounds >= STIR_MAX_ROUNDS) return TVM_ERR_LDT_PARAMS;
+    out.in_domain[out.num_rounds] = in_domain; out.out_of_domain[out.num_rounds] = ood; out.num_rounds++;
+    folded_poly_degree = next_deg;
+    log2_exp = log2_next_exp;
+    log2_folded_domain_size -= 1;
+  }
+  out.final_num_in_domain_queries = stir_num_in_domain_queries(security, log2_folded_domain_size, log2_exp);
+  out.final_degree = folded_poly_degree;
+  return TVM_OK;
+}
+
 int stark_derive(const StarkParams &sp, size_t padded_height, StarkDerived &d) {
-  if (sp.log2_expansion == 0 || sp.log2_expansion > 8 || sp.security_level == 0) return TVM_ERR_LDT_PARAMS;
+  if (sp.log2_expansion == 0 || sp.log2_expansion > 8 || sp.security_level == 0 || sp.ldt_choice > 2) return TVM_ERR_LDT_PARAMS;
   padded_height = next_pow2(padded_height ? padded_height : 1);
   if (padded_height > ((size_t)1 << 31)) return TVM_ERR_DOMAIN;
   const int log2_ph = ilog2(padded_height);
+  d = StarkDerived{};
+  d.ldt = sp.ldt_choice ? (int)sp.ldt_choice : (log2_ph < 16 ? 1 : 2);      // stark.rs:1942-1951 (proven regime)
   // low_degree_test/mod.rs:250-300 (ProximityRegime::Proven) and fri.rs:832-836
   const double rate = 1.0 / (double)(1u << sp.log2_expansion);
   const double margin = std::sqrt(rate);
   const double proximity_parameter = 1.0 - margin - margin / 20.0;
   const size_t checks = (size_t)std::ceil(-(double)sp.security_level / std::log2(1.0 - proximity_parameter));
-  const size_t h = checks + NUM_QUOTIENT_SEGMENTS * 3 * 2 + 1;           // stark.rs:2083-2089
-  const size_t nqr = (h + 1) * NUM_RANDOMIZED_QUOTIENT_SEGMENTS;         // stark.rs:1894-1896
   const size_t expansion = (size_t)1 << sp.log2_expansion;
-  size_t rtl = next_pow2(std::max(std::max(padded_height + h, 2 * h + 1), nqr));   // stark.rs:1885-1890
+  size_t h = 0, nqr = 0, rtl = 0, ldt_len = 0;
   int hdb = log2_ph;
-  size_t ldt_len;
-  for (;;) {                                                             // stark.rs:1975-1984
+  for (;;) {                                                             // stark.rs:1972-2060
     hdb++;
     if (hdb + (int)sp.log2_expansion > 32) return TVM_ERR_LDT_PARAMS;
     ldt_len = (size_t)1 << (hdb + sp.log2_expansion);
+    size_t first_round = checks;
+    if (d.ldt == 2) {
+      int rc = stir_derive(sp.security_level, STIR_LOG2_FOLDING_FACTOR, sp.log2_expansion, (unsigned)hdb, d.stir);
+      if (rc) return rc;
+      first_round = d.stir.num_rounds ? d.stir.in_domain[0] : d.stir.final_num_in_domain_queries;   // stir.rs:878-883
+    }
+    d.num_first_round_queries = first_round;
+    h = first_round + NUM_QUOTIENT_SEGMENTS * 3 * 2 + 1;                 // stark.rs:2083-2089
+    nqr = (h + 1) * NUM_RANDOMIZED_QUOTIENT_SEGMENTS;                    // stark.rs:1894-1896
+    rtl = next_pow2(std::max(std::max(padded_height + h, 2 * h + 1), nqr));   // stark.rs:1885-1890
     if (ldt_len >= rtl * expansion) break;
   }
   const long long interpolant_degree = (long long)rtl - 1;
@@ -83,51 +156,10 @@ int stark_derive(const StarkParams &sp, size_t padded_height, StarkDerived &d) {
 
 namespace {
 
-struct DevMem {   // RAII device buffers of one prove() call, recycled through the context's block pool
-  Ctx &c;
-  std::vector<void *> ptrs;
-  explicit DevMem(Ctx &ctx) : c(ctx) {}
-  ~DevMem() {
-    cudaStreamSynchronize(c.stream);
-    for (void *p : ptrs) c.pool_release(p);
-  }
-  u64 *words(size_t n) {
-    void *p = c.pool_alloc((n ? n : 1) * sizeof(u64));
-    ptrs.push_back(p);
-    return (u64 *)p;
-  }
-  void release(void *p) {   // stream-ordered reuse: later kernels on the same stream see earlier ones complete
-    for (size_t i = 0; i < ptrs.size(); i++)
-      if (ptrs[i] == p) { c.pool_release(p); ptrs.erase(ptrs.begin() + i); return; }
-  }
-};
-
-xfe xmul_by_X(xfe a) { return xmake(fneg(a.c2), fadd(a.c0, a.c2), a.c1); }   // X^3 = X - 1
-// value of an X-field column stored as 3 planar B-field columns from the 3 per-plane dot products
-xfe combine_planes(xfe r0, xfe r1, xfe r2) { return xadd(r0, xadd(xmul_by_X(r1), xmul_by_X(xmul_by_X(r2)))); }
-
 xfe eval_arg_terminal(const u64 *symbols_canon, size_t n, xfe challenge) {  // cross_table_argument.rs:60-73
   xfe acc = xone();
   for (size_t i = 0; i < n; i++) acc = xaddb(xmul(challenge, acc), to_mont(symbols_canon[i] % P));
   return acc;
-}
-
-std::vector<unsigned> auth_structure_node_indices(size_t num_leafs, const std::vector<uint32_t> &leaf_indices) {
-  // twenty-first MerkleTree::authentication_structure: needed-but-not-computable
-  // sibling nodes, descending node index
-  std::set<size_t> needed, computable;
-  for (uint32_t li : leaf_indices) {
-    size_t node = (size_t)li + num_leafs;
-    while (node > 1) {
-      computable.insert(node);
-      needed.insert(node ^ 1);
-      node >>= 1;
-    }
-  }
-  std::vector<unsigned> out;
-  for (auto it = needed.rbegin(); it != needed.rend(); ++it)
-    if (!computable.count(*it)) out.push_back((unsigned)*it);
-  return out;
 }
 
 // Shard of the evaluation domain owned by this rank: domain coset first + step*y for y < count
@@ -146,13 +178,6 @@ void evaluate_cols(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_
     lde_evaluate_run(c, d_coef + c0 * coef_stride, coef_stride, fold_count, log_n, log_r, sh.first, sh.step, sh.count, b,
                      d_lde + c0 * n_loc, d_tmp);
   }
-}
-
-std::vector<u64> d2h(Ctx &c, const u64 *d, size_t n) {
-  std::vector<u64> h(n);
-  TVM_CUDA(cudaMemcpyAsync(h.data(), d, n * sizeof(u64), cudaMemcpyDeviceToHost, c.stream));
-  TVM_CUDA(cudaStreamSynchronize(c.stream));
-  return h;
 }
 
 }  // namespace
@@ -459,7 +484,15 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   mem.release(d_deep);
   mark();  // 10: linear combination + DEEP
 
-  // ---- FRI (fri.rs:212-366, 754-772) ------------------------------------------------------------------------------------
+  // ---- low-degree test of the combination codeword (stark.rs:641-646) -------------------------------------------------
+  std::vector<uint32_t> a_indices;
+  const size_t max_open = std::max<size_t>(d.num_first_round_queries, 1);
+  unsigned *d_idx = (unsigned *)mem.words(max_open * 64 + 64);
+  u64 *d_gather = mem.words(max_open * 400 + max_open * 5 * 40 + 64);
+  if (d.ldt == 2) {
+    a_indices = stir_prove_run(c, mem, ps, d_fri, N, off, d.stir, d_tmp);
+  } else {
+  // FRI (fri.rs:212-366, 754-772)
   struct Round { u64 *cw; size_t len; u64 *nodes; u64 offset; };
   std::vector<Round> rounds;
   {
@@ -507,10 +540,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
       for (int dd = 0; dd < 3; dd++) payload.push_back(from_mont(co[dd * last.len + i]));
     ps.enqueue(ItemKind::Polynomial, payload);
   }
-  std::vector<uint32_t> a_indices = ps.sponge.sample_indices((uint32_t)N, d.num_collinearity_checks);
-  const unsigned nq = (unsigned)a_indices.size();
-  unsigned *d_idx = (unsigned *)mem.words(nq * 64 + 64);
-  u64 *d_gather = mem.words((size_t)nq * 400 + (size_t)nq * 5 * 40 + 64);
+  a_indices = ps.sponge.sample_indices((uint32_t)N, d.num_collinearity_checks);
   auto reveal = [&](const Round &rd, const std::vector<uint32_t> &idx) {
     TVM_CUDA(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, c.stream));
     gather_rows_run(c, rd.cw, rd.len, 3, d_idx, (unsigned)idx.size(), 0, -1, d_gather);
@@ -531,6 +561,8 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     reveal(rounds[r], b);
   }
   ps.sponge.sample_scalars(1);   // fri.rs:764-769
+  }
+  const unsigned nq = (unsigned)a_indices.size();
   mark();  // 11: FRI
 
   // ---- zero-knowledge guard (stark.rs:648-663) -----------------------------------------------------------------------------

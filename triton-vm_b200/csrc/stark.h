@@ -9,15 +9,29 @@ namespace tvm {
 static constexpr int NUM_QUOTIENT_SEGMENTS = 4;              // stark.rs:66 (= air::TARGET_DEGREE)
 static constexpr int NUM_RANDOMIZED_QUOTIENT_SEGMENTS = 5;   // stark.rs:75
 
-struct StarkParams {          // stark.rs:113-145 (proven regime, FRI)
+struct StarkParams {          // stark.rs:113-145 (proven regime)
   unsigned security_level;
   unsigned log2_expansion;
+  unsigned ldt_choice;        // 0 = heuristic (stark.rs:1942-1957), 1 = FRI, 2 = STIR
+};
+static constexpr int STIR_MAX_ROUNDS = 16;
+static constexpr unsigned STIR_LOG2_FOLDING_FACTOR = 2;      // stark.rs:2023
+struct StirDerived {          // stir.rs:112-147
+  size_t folding_factor;
+  int num_rounds;
+  size_t in_domain[STIR_MAX_ROUNDS], out_of_domain[STIR_MAX_ROUNDS];
+  size_t final_num_in_domain_queries, final_degree;
 };
 struct StarkDerived {
   size_t padded_height, num_trace_randomizers, randomized_trace_len, trace_len, quotient_len, ldt_len;
   u64 ldt_offset;  // canonical
   size_t num_collinearity_checks, fri_num_rounds, fri_last_round_max_degree, num_quotient_randomizer_coefficients;
+  int ldt;                    // 1 = FRI, 2 = STIR
+  size_t num_first_round_queries;
+  StirDerived stir;
 };
+int stir_derive(unsigned security_level, unsigned log2_folding_factor, unsigned log2_initial_expansion, unsigned log2_high_degree_bound,
+                StirDerived &out);
 int stark_derive(const StarkParams &sp, size_t padded_height, StarkDerived &d);
 
 struct ClaimView {            // proof.rs:68-88, canonical words

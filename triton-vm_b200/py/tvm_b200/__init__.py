@@ -45,10 +45,18 @@ class Domains(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in (
         "padded_height", "num_trace_randomizers", "randomized_trace_len", "trace_len", "quotient_len", "ldt_len",
         "ldt_offset", "num_collinearity_checks", "fri_num_rounds", "fri_last_round_max_degree",
-        "num_quotient_randomizer_coefficients")]
+        "num_quotient_randomizer_coefficients", "ldt", "num_first_round_queries", "stir_num_rounds")] + [
+        ("stir_in_domain_queries", ctypes.c_uint64 * 16), ("stir_out_of_domain_queries", ctypes.c_uint64 * 16),
+        ("stir_final_num_queries", ctypes.c_uint64), ("stir_final_degree", ctypes.c_uint64)]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+        d = {}
+        for n, t in self._fields_:
+            v = getattr(self, n)
+            d[n] = int(v) if t is ctypes.c_uint64 else [int(x) for x in v]
+        k = d["stir_num_rounds"]
+        d["stir_round_queries"] = list(zip(d.pop("stir_in_domain_queries")[:k], d.pop("stir_out_of_domain_queries")[:k]))
+        return d
 
 
 class ClaimStruct(ctypes.Structure):
@@ -66,7 +74,7 @@ class CommStruct(ctypes.Structure):   # tvm_comm
                 ("all_reduce_sum_u64", ALL_REDUCE_CB)]
 
 
-LDT_FRI = 1
+LDT_AUTO, LDT_FRI, LDT_STIR = 0, 1, 2      # tvm_params.ldt_choice
 
 _lib = None
 
@@ -230,8 +238,8 @@ class Backend:
         return (root, nodes) if want_nodes else root
 
     def prove(self, claim, main_trace, main_rand, aux_provider, quot_rand, security_level=160, log2_expansion=2,
-              padded_height=None):
-        """Stark::prove (LdtChoice::Fri).  claim = (program_digest[5], input, output[, version]);
+              padded_height=None, ldt_choice=LDT_FRI):
+        """Stark::prove; `ldt_choice` LDT_FRI / LDT_STIR / LDT_AUTO (the reference's heuristic).  claim = (program_digest[5], input, output[, version]);
         main_trace [379, n], main_rand [379, h] canonical uint64; aux_provider(challenges [63,3]) ->
         (aux_trace [91, n, 3], aux_rand [91, h, 3]); quot_rand [(h+1)*5, 3].  Returns the proof words.
         The traces may be numpy arrays (host) or contiguous torch int64 tensors (pinned host or CUDA:
@@ -241,7 +249,7 @@ class Backend:
         qr, qrp = _np_u64(quot_rand)
         n = mt_shape[1]
         ph = padded_height or n
-        dom = derive_domains(security_level, log2_expansion, ph)
+        dom = derive_domains(security_level, log2_expansion, ph, ldt_choice)
         h = dom["num_trace_randomizers"]
         assert mt_shape == (379, dom["trace_len"]) and mr_shape == (379, h), (mt_shape, mr_shape, dom)
         assert qr.size == 3 * dom["num_quotient_randomizer_coefficients"]
@@ -269,10 +277,15 @@ class Backend:
                 err.append(e)
                 return 1
 
-        p = Params(security_level, log2_expansion, LDT_FRI)
+        p = Params(security_level, log2_expansion, ldt_choice)
         cap = ctypes.c_size_t(0)
-        est = 64 + dom["num_collinearity_checks"] * (379 + 273 + 15 + 3 * 40 * (dom["fri_num_rounds"] + 4)) + \
+        nfq = dom["num_first_round_queries"]
+        est = 64 + nfq * (379 + 273 + 15 + 3 * 40 * (dom["fri_num_rounds"] + 4)) + \
             3 * (dom["ldt_len"] >> dom["fri_num_rounds"]) * 2 + 3 * 470 * 2 + 4096
+        if dom["ldt"] == LDT_STIR:   # per round: stacked leaves (4 XFE + framing) and authentication paths of every query
+            height = dom["ldt_len"].bit_length()
+            est += sum(q * (16 + 5 * height) + 64 for q, _ in dom["stir_round_queries"]) + \
+                dom["stir_final_num_queries"] * (16 + 5 * height) + 3 * (dom["stir_final_degree"] + 2) + 1024
         buf = np.empty(est, dtype=np.uint64)
         cap.value = est
         rc = self._l.tvm_prove(self._h, ctypes.byref(p), ctypes.byref(cs), ph, mtp, mrp, AUX_CALLBACK(cb), None, qrp,
