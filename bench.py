@@ -148,7 +148,9 @@ def run_gpu(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
-    dom = tvm_b200.derive_domains(160, 2, 1 << args.log2_height)
+    ldt_choice = {"auto": tvm_b200.LDT_AUTO, "fri": tvm_b200.LDT_FRI, "stir": tvm_b200.LDT_STIR}[args.ldt]
+    dom = tvm_b200.derive_domains(160, 2, 1 << args.log2_height, ldt_choice)
+    ldt_name = {tvm_b200.LDT_FRI: "FRI", tvm_b200.LDT_STIR: "STIR"}[dom["ldt"]]
     n, h = dom["trace_len"], dom["num_trace_randomizers"]
     nqr = dom["num_quotient_randomizer_coefficients"]
 
@@ -188,11 +190,11 @@ def run_gpu(args):
     d_aux_trace, d_aux_rand = keep[2].to(dev), keep[3].to(dev)
 
     def step_host():
-        return b.prove(claim, main_trace, main_rand, aux_provider, quot_rand, 160, 2, 1 << args.log2_height)
+        return b.prove(claim, main_trace, main_rand, aux_provider, quot_rand, 160, 2, 1 << args.log2_height, ldt_choice)
 
     def step_dev():
         return b.prove(claim, d_main_trace, d_main_rand, lambda _c: (d_aux_trace, d_aux_rand), quot_rand, 160, 2,
-                       1 << args.log2_height)
+                       1 << args.log2_height, ldt_choice)
 
     def timed(step):
         """W warm-up steps, then exactly K timed steps: barrier + synchronize on both sides, max over ranks."""
@@ -239,8 +241,10 @@ def run_gpu(args):
         "ms_per_step": device_ms, "higher_is_better": False, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": f"Stark::prove (LdtChoice::Fri, security 160, expansion 4) at padded height 2^{args.log2_height}: "
-                               f"379 main + 91 aux columns, trace domain 2^{args.log2_height}, LDT domain 2^{args.log2_height + 3}",
+        "config": {"workload": f"Stark::prove (Stark::default(): security 160, expansion 4, low-degree test {ldt_name}"
+                               f"{' as the reference selects at this height' if args.ldt == 'auto' else ' (forced)'}) at padded height "
+                               f"2^{args.log2_height}: 379 main + 91 aux columns, {dom['num_trace_randomizers']} trace randomizers, "
+                               f"trace domain 2^{args.log2_height}, LDT domain 2^{args.log2_height + 3}",
                    "parallelism": "single GPU" if world == 1 else
                    f"one proof sharded over {world} GPUs by evaluation-domain cosets (NCCL all-gathers: "
                    f"{comm.calls['all_gather'] // max(1, 2 * (args.steps + args.warmup))} per proof)",
@@ -299,6 +303,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2-height", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ldt", default="auto", choices=["auto", "fri", "stir"],
+                    help="low-degree test; auto = the reference's own choice (STIR from padded height 2^16 on)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

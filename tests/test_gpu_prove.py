@@ -40,7 +40,7 @@ def test_proof_is_bit_exact_vs_oracle(backend, security, log2_exp, padded_height
     assert got == want
     assert S.verify(st, claim, got, check_air=False)
     stages = dict(backend.last_prove_timings())
-    assert "LDT(FRI)" in stages and "quotient(AIR)" in stages
+    assert "low-degree test" in stages and "quotient(AIR)" in stages
 
 
 def test_proof_depends_on_every_input(backend):

@@ -9,7 +9,7 @@ import pytest
 import torch
 import torch.multiprocessing as mp
 
-from test_gpu_prove import synthetic_instance
+from test_gpu_prove import synthetic_instance, synthetic_stir_instance
 
 pytestmark = pytest.mark.gpu
 
@@ -28,10 +28,14 @@ def _worker(rank, world, port, params, q):
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl" if one_gpu_each else "gloo", rank=rank, world_size=world)
     try:
-        security, log2_exp, padded_height, seed = params
-        st, d, claim, main, mrand, aux_provider, qrand = synthetic_instance(security, log2_exp, padded_height, seed)
+        security, log2_exp, padded_height, seed, ldt = params
+        if ldt == "stir":
+            st, d, claim, main, mrand, aux_provider, qrand = synthetic_stir_instance(security, padded_height, seed)
+        else:
+            st, d, claim, main, mrand, aux_provider, qrand = synthetic_instance(security, log2_exp, padded_height, seed)
         args = ((claim.program_digest, claim.input, claim.output), main, mrand, aux_provider, qrand)
-        kw = dict(security_level=security, log2_expansion=log2_exp, padded_height=padded_height)
+        kw = dict(security_level=security, log2_expansion=log2_exp, padded_height=padded_height,
+                  ldt_choice=tvm_b200.LDT_STIR if ldt == "stir" else tvm_b200.LDT_FRI)
         b = tvm_b200.Backend(dev)
         single = b.prove(*args, **kw)
         comm = TorchDistComm(f"cuda:{dev}")
@@ -50,7 +54,8 @@ def _worker(rank, world, port, params, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,params", [(2, (8, 2, 64, 2)), (4, (32, 2, 256, 3)), (8, (8, 2, 64, 7))])
+@pytest.mark.parametrize("world,params", [(2, (8, 2, 64, 2, "fri")), (4, (32, 2, 256, 3, "fri")), (8, (8, 2, 64, 7, "fri")),
+                                          (2, (6, 2, 256, 12, "stir"))])
 def test_sharded_proof_equals_single_gpu_proof(world, params):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

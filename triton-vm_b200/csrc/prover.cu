@@ -605,7 +605,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   if (timings) {
     TVM_CUDA(cudaStreamSynchronize(c.stream));
     static const char *names[] = {"setup", "upload+LDE(main)", "Merkle(main)", "extend(caller)", "upload+LDE(aux)", "Merkle(aux)",
-                                  "quotient(AIR)", "quotient LDE", "Merkle(quot)", "OOD rows", "linear combination+DEEP", "LDT(FRI)",
+                                  "quotient(AIR)", "quotient LDE", "Merkle(quot)", "OOD rows", "linear combination+DEEP", "low-degree test",
                                   "open"};
     timings->stages.clear();
     for (int i = 1; i < nev; i++) {
