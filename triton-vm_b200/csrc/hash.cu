@@ -187,6 +187,122 @@ __device__ __forceinline__ void tip5_perm_quad(u64 (&s)[4], int l, int group_bas
   }
 }
 
+// ---- two rows per lane quad ---------------------------------------------------------------------
+// The round of one state is a long FMA-pipe stretch (MDS: 128 IMAD.WIDE per lane) followed by
+// ALU-pipe stretches (reductions, S-box bookkeeping); with every warp of an SM running the same
+// stream the two pipes are used alternately rather than concurrently (ncu r01b: issue 54 %,
+// `math_pipe_throttle` the top stall).  Each quad therefore carries two independent rows, half a
+// round out of phase: the MDS of one state is scheduled together with the S-box of the other.
+__device__ __forceinline__ void quad_sbox(u64 (&s)[4], const unsigned char *lut) {
+  {  // slot 0: split-and-lookup
+    u64 v = s[0], o = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) o |= (u64)lut[(unsigned)((v >> (8 * b)) & 0xFF)] << (8 * b);
+    s[0] = o;
+  }
+#pragma unroll
+  for (int i = 1; i < 4; i++) {
+    u64 x = s[i], x2 = fmul(x, x), x3 = fmul(x2, x), x4 = fmul(x2, x2);
+    s[i] = fmul(x3, x4);
+  }
+}
+__device__ __forceinline__ void quad_mds_rc(u64 (&s)[4], int l, int group_base, const u64 *rc_smem, int rnd) {
+  constexpr unsigned short MDS[16] = TVM_MDS_COL;
+  u64 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int wrap = (((l - k) & 3) + (k & 3)) >> 2;          // 0 or 1
+    const u64 provide = wrap ? s[((k >> 2) + 1) & 3] : s[k >> 2];
+    const u64 X = shfl64(provide, group_base + ((k + l) & 3));
+    const u64 xl = X & 0xFFFFFFFFULL, xh = X >> 32;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const u64 m = MDS[(4 * i - k) & 15];
+      lo[i] += m * xl;
+      hi[i] += m * xh;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    u64 lsum = lo[i] + (hi[i] << 32);
+    u64 carry = lsum < lo[i];
+    u64 h = (hi[i] >> 32) + carry;
+    s[i] = fadd(reduce96(lsum, h), rc_smem[16 * rnd + l + 4 * i]);
+  }
+}
+__device__ __forceinline__ void tip5_perm_quad2(u64 (&a)[4], u64 (&b)[4], int l, int group_base, const unsigned char *lut,
+                                                const u64 *rc_smem) {
+  quad_sbox(a, lut);
+#pragma unroll 1
+  for (int rnd = 0; rnd < TIP5_ROUNDS - 1; rnd++) {
+    quad_mds_rc(a, l, group_base, rc_smem, rnd);
+    quad_sbox(b, lut);
+    quad_mds_rc(b, l, group_base, rc_smem, rnd);
+    quad_sbox(a, lut);
+  }
+  quad_mds_rc(a, l, group_base, rc_smem, TIP5_ROUNDS - 1);
+  quad_sbox(b, lut);
+  quad_mds_rc(b, l, group_base, rc_smem, TIP5_ROUNDS - 1);
+}
+
+static constexpr int HASHQ2_THREADS = 128;   // 32 quads, 64 rows per CTA
+__global__ void __launch_bounds__(HASHQ2_THREADS) tip5_hash_rows_quad2_kernel(HashRowsParams p) {
+  __shared__ unsigned char lut[256];
+  __shared__ u64 rc[80];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
+  for (int i = threadIdx.x; i < 80; i += blockDim.x) rc[i] = c_tip5_rc[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l = lane & 3, group_base = lane & ~3;
+  constexpr int QUADS = HASHQ2_THREADS / 4;
+  size_t mrow[2];
+  bool active[2];
+  const u64 *base[2];
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    size_t m = (size_t)blockIdx.x * (2 * QUADS) + (threadIdx.x >> 2) + (size_t)t * QUADS;
+    active[t] = m < p.nrows;
+    if (!active[t]) m = p.nrows - 1;                              // keep the quad alive for the shuffles
+    mrow[t] = m;
+    base[t] = p.table + m;
+  }
+  u64 a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  unsigned c = 0;
+  for (; c + 10 <= p.ncols; c += 10) {
+    a[0] = base[0][(size_t)(c + l) * p.col_stride];
+    b[0] = base[1][(size_t)(c + l) * p.col_stride];
+    a[1] = base[0][(size_t)(c + l + 4) * p.col_stride];
+    b[1] = base[1][(size_t)(c + l + 4) * p.col_stride];
+    if (l < 2) {
+      a[2] = base[0][(size_t)(c + l + 8) * p.col_stride];
+      b[2] = base[1][(size_t)(c + l + 8) * p.col_stride];
+    }
+    tip5_perm_quad2(a, b, l, group_base, lut, rc);
+  }
+  unsigned rem = p.ncols - c;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    unsigned e = (unsigned)(l + 4 * i);
+    if (e < 10) {
+      u64 va = 0, vb = 0;
+      if (e < rem) { va = base[0][(size_t)(c + e) * p.col_stride]; vb = base[1][(size_t)(c + e) * p.col_stride]; }
+      else if (e == rem) { va = MONT_ONE; vb = MONT_ONE; }
+      a[i] = va; b[i] = vb;
+    }
+  }
+  tip5_perm_quad2(a, b, l, group_base, lut, rc);
+  const size_t per = p.nrows >> p.log_r;
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    if (!active[t]) continue;
+    size_t m = mrow[t];
+    size_t coset = m / per, k = m - coset * per;
+    u64 *d = p.digests + (coset + (k << p.log_r)) * 5;
+    const u64 *s = t ? b : a;
+    d[l] = s[0];
+    if (l == 0) d[4] = s[1];
+  }
+}
+
 static constexpr int HASHQ_THREADS = 128;
 __global__ void __launch_bounds__(HASHQ_THREADS) tip5_hash_rows_quad_kernel(HashRowsParams p) {
   __shared__ unsigned char lut[256];
@@ -235,10 +351,14 @@ void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, un
   if (use_thread_per_row) {
     unsigned grid = (unsigned)((nrows + HASH_THREADS - 1) / HASH_THREADS);
     tip5_hash_rows_kernel<<<grid, HASH_THREADS, 0, c.stream>>>(p);
-  } else {
+  } else if (getenv("TVM_TIP5_ONE_ROW_PER_QUAD")) {
     size_t threads = nrows * 4;
     unsigned grid = (unsigned)((threads + HASHQ_THREADS - 1) / HASHQ_THREADS);
     tip5_hash_rows_quad_kernel<<<grid, HASHQ_THREADS, 0, c.stream>>>(p);
+  } else {
+    const size_t rows_per_cta = HASHQ2_THREADS / 2;
+    unsigned grid = (unsigned)((nrows + rows_per_cta - 1) / rows_per_cta);
+    tip5_hash_rows_quad2_kernel<<<grid, HASHQ2_THREADS, 0, c.stream>>>(p);
   }
   c.launches++;
   TVM_CUDA(cudaGetLastError());
