@@ -303,6 +303,110 @@ __global__ void __launch_bounds__(HASHQ2_THREADS) tip5_hash_rows_quad2_kernel(Ha
   }
 }
 
+// ---- two lanes per row ------------------------------------------------------------------------------
+// Measured cost model (tools/microbench/field_ops.cu, SMSP-clocks per warp instruction group): the MDS step
+// of the 4-lane layout costs 635 per round against 355 for the three x^7 - its 32 shuffles (4 clocks
+// each) and 32 selects are paid by every lane for a quarter of a state.  With two lanes per row, lane l
+// holding elements {l, l+2, ..., l+14} (slots 0,1 = split-and-lookup, slots 2..7 = x^7, again
+// divergence-free), the rotated gather X[k] = x_{(k+l) mod 16} needs the partner only for odd k:
+// 16 shuffles + 16 selects per lane for HALF a state, and the IMAD count per state is unchanged.
+__device__ __forceinline__ void pair_sbox(u64 (&s)[8], const unsigned char *lut) {
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    u64 v = s[j], o = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) o |= (u64)lut[(unsigned)((v >> (8 * b)) & 0xFF)] << (8 * b);
+    s[j] = o;
+  }
+#pragma unroll
+  for (int j = 2; j < 8; j++) {
+    u64 x = s[j], x2 = fmul(x, x), x3 = fmul(x2, x), x4 = fmul(x2, x2);
+    s[j] = fmul(x3, x4);
+  }
+}
+__device__ __forceinline__ void pair_mds_rc(u64 (&s)[8], int l, const u64 *rc_smem, int rnd) {
+  constexpr unsigned short MDS[16] = TVM_MDS_COL;
+  u64 lo[8], hi[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { lo[i] = 0; hi[i] = 0; }
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    u64 X;
+    if ((k & 1) == 0) {
+      X = s[k >> 1];                                           // own element k + l
+    } else {
+      // the partner wants x_{(k + l') mod 16}: lane 1 serves lane 0 with slot (k-1)/2, lane 0 serves lane 1
+      // with slot ((k+1) mod 16)/2
+      const u64 provide = l ? s[(k - 1) >> 1] : s[((k + 1) & 15) >> 1];
+      unsigned plo = __shfl_xor_sync(0xffffffffu, (unsigned)provide, 1);
+      unsigned phi = __shfl_xor_sync(0xffffffffu, (unsigned)(provide >> 32), 1);
+      X = ((u64)phi << 32) | plo;
+    }
+    const u64 xl = X & 0xFFFFFFFFULL, xh = X >> 32;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const u64 m = MDS[(2 * i - k) & 15];
+      lo[i] += m * xl;
+      hi[i] += m * xh;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u64 lsum = lo[i] + (hi[i] << 32);
+    u64 carry = lsum < lo[i];
+    u64 h = (hi[i] >> 32) + carry;
+    s[i] = fadd(reduce96(lsum, h), rc_smem[16 * rnd + l + 2 * i]);
+  }
+}
+__device__ __forceinline__ void tip5_perm_pair(u64 (&s)[8], int l, const unsigned char *lut, const u64 *rc_smem) {
+#pragma unroll 1
+  for (int rnd = 0; rnd < TIP5_ROUNDS; rnd++) {
+    pair_sbox(s, lut);
+    pair_mds_rc(s, l, rc_smem, rnd);
+  }
+}
+
+static constexpr int HASHP_THREADS = 128;    // 64 rows per CTA
+__global__ void __launch_bounds__(HASHP_THREADS) tip5_hash_rows_pair_kernel(HashRowsParams p) {
+  __shared__ unsigned char lut[256];
+  __shared__ u64 rc[80];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
+  for (int i = threadIdx.x; i < 80; i += blockDim.x) rc[i] = c_tip5_rc[i];
+  __syncthreads();
+  const int l = threadIdx.x & 1;
+  size_t m = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;   // one row per 2 lanes
+  const bool active = m < p.nrows;
+  if (!active) m = p.nrows - 1;                                     // keep the pair alive for the shuffles
+  const u64 *base = p.table + m;
+  u64 s[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) s[j] = 0;
+  unsigned c = 0;
+  for (; c + 10 <= p.ncols; c += 10) {
+#pragma unroll
+    for (int j = 0; j < 5; j++) s[j] = base[(size_t)(c + l + 2 * j) * p.col_stride];
+    tip5_perm_pair(s, l, lut, rc);
+  }
+  const unsigned rem = p.ncols - c;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const unsigned e = (unsigned)(l + 2 * j);
+    u64 v = 0;
+    if (e < rem) v = base[(size_t)(c + e) * p.col_stride];
+    else if (e == rem) v = MONT_ONE;
+    s[j] = v;
+  }
+  tip5_perm_pair(s, l, lut, rc);
+  if (active) {
+    const size_t per = p.nrows >> p.log_r;
+    const size_t coset = m / per, k = m - coset * per;
+    u64 *d = p.digests + (coset + (k << p.log_r)) * 5;
+    d[l] = s[0];
+    d[l + 2] = s[1];
+    if (l == 0) d[4] = s[2];
+  }
+}
+
 static constexpr int HASHQ_THREADS = 128;
 __global__ void __launch_bounds__(HASHQ_THREADS) tip5_hash_rows_quad_kernel(HashRowsParams p) {
   __shared__ unsigned char lut[256];
@@ -355,6 +459,9 @@ void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, un
     size_t threads = nrows * 4;
     unsigned grid = (unsigned)((threads + HASHQ_THREADS - 1) / HASHQ_THREADS);
     tip5_hash_rows_quad_kernel<<<grid, HASHQ_THREADS, 0, c.stream>>>(p);
+  } else if (getenv("TVM_TIP5_TWO_LANES")) {   // A/B switch: measured 3 % slower than the default below at 2^20
+    unsigned grid = (unsigned)((nrows * 2 + HASHP_THREADS - 1) / HASHP_THREADS);
+    tip5_hash_rows_pair_kernel<<<grid, HASHP_THREADS, 0, c.stream>>>(p);
   } else {
     const size_t rows_per_cta = HASHQ2_THREADS / 2;
     unsigned grid = (unsigned)((nrows + rows_per_cta - 1) / rows_per_cta);
