@@ -82,6 +82,59 @@ __global__ void stir_quotient_kernel(const u64 *F, const u64 *A, const u64 *Z, s
   out[j] = res.c0; out[len + j] = res.c1; out[2 * len + j] = res.c2;
 }
 
+// Zerofier and Lagrange interpolant of m <= blockDim.x points in one CTA (Polynomial::zerofier / ::interpolate,
+// stir.rs:958-960).  pts/vals: [m][3] interleaved; Q: m*m X-field scratch (3 planes of m*m words);
+// out_ans: [3][m] planar, out_z: [3][m+1] planar.
+__global__ void stir_interpolate_kernel(const u64 *pts, const u64 *vals, unsigned m, u64 *Q, u64 *out_ans, u64 *out_z) {
+  extern __shared__ u64 sm[];           // z[3][m+1], s[3][m]
+  u64 *z = sm, *sc = sm + 3 * (m + 1);
+  const unsigned t = threadIdx.x;
+  const size_t mm = (size_t)m * m;
+  // zerofier: multiply by (X - p_i) one point at a time; coefficient k is owned by thread k
+  for (unsigned k = t; k <= m; k += blockDim.x) { z[k] = k == 0 ? MONT_ONE : 0; z[(m + 1) + k] = 0; z[2 * (m + 1) + k] = 0; }
+  __syncthreads();
+  for (unsigned i = 0; i < m; i++) {
+    const xfe p = xmake(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    xfe nv = xzero();
+    const bool mine = t <= i + 1 && t <= m;
+    if (mine) {
+      xfe cur = xmake(z[t], z[(m + 1) + t], z[2 * (m + 1) + t]);
+      xfe prev = t ? xmake(z[t - 1], z[(m + 1) + t - 1], z[2 * (m + 1) + t - 1]) : xzero();
+      nv = xsub(prev, xmul(cur, p));
+    }
+    __syncthreads();
+    if (mine) { z[t] = nv.c0; z[(m + 1) + t] = nv.c1; z[2 * (m + 1) + t] = nv.c2; }
+    __syncthreads();
+  }
+  for (unsigned k = t; k <= m; k += blockDim.x)
+    for (int d = 0; d < 3; d++) out_z[d * (m + 1) + k] = z[d * (m + 1) + k];
+  // q_i = z / (X - x_i) by synthetic division; s_i = y_i / q_i(x_i)
+  if (t < m) {
+    const xfe x = xmake(pts[3 * t], pts[3 * t + 1], pts[3 * t + 2]);
+    xfe acc = xzero();
+    for (unsigned k = m; k >= 1; k--) {
+      acc = xadd(xmake(z[k], z[(m + 1) + k], z[2 * (m + 1) + k]), xmul(acc, x));
+      Q[(size_t)t * m + (k - 1)] = acc.c0; Q[mm + (size_t)t * m + (k - 1)] = acc.c1; Q[2 * mm + (size_t)t * m + (k - 1)] = acc.c2;
+    }
+    xfe den = xzero();
+    for (unsigned k = m; k-- > 0;) {
+      xfe qk = xmake(Q[(size_t)t * m + k], Q[mm + (size_t)t * m + k], Q[2 * mm + (size_t)t * m + k]);
+      den = xadd(xmul(den, x), qk);
+    }
+    xfe sv = xmul(xmake(vals[3 * t], vals[3 * t + 1], vals[3 * t + 2]), xinv(den));
+    sc[t] = sv.c0; sc[m + t] = sv.c1; sc[2 * m + t] = sv.c2;
+  }
+  __syncthreads();
+  if (t < m) {      // coefficient t of the interpolant: sum_i s_i q_i[t]
+    xfe acc = xzero();
+    for (unsigned i = 0; i < m; i++) {
+      xfe qi = xmake(Q[(size_t)i * m + t], Q[mm + (size_t)i * m + t], Q[2 * mm + (size_t)i * m + t]);
+      acc = xadd(acc, xmul(xmake(sc[i], sc[m + i], sc[2 * m + i]), qi));
+    }
+    out_ans[t] = acc.c0; out_ans[m + t] = acc.c1; out_ans[2 * m + t] = acc.c2;
+  }
+}
+
 // ---- small host-side X-field polynomial arithmetic (Montgomery form, little-endian coefficients) ----
 typedef std::vector<xfe> XPoly;
 xfe xp_eval(const XPoly &c, xfe x) {
@@ -270,23 +323,42 @@ std::vector<uint32_t> stir_prove_run(Ctx &c, DevMem &mem, ProofStream &ps, const
       }
       for (size_t t = 0; t < num_ood; t++) { points.push_back(ood_queries[t]); answers.push_back(ood_values[t]); }
     }
-    const XPoly zf = xp_zerofier(points);
-    const XPoly ans = xp_interpolate(points, answers, zf);
-    const xfe rho = ps.sponge.sample_scalars(1)[0];       // degree-correction randomness
-
-    // next round's polynomial (stir.rs:958-972)
-    {
-      const size_t m = points.size();
+    const size_t m = points.size();
+    // Ans and Zerofier (stir.rs:958-960): on the device when the point set fits one CTA, else on the host
+    u64 *d_small = mem.words(3 * (2 * m + 1));      // ans [3][m] followed by zerofier [3][m+1]
+    if (m < 1024) {
+      std::vector<u64> hp(6 * m);
+      for (size_t k = 0; k < m; k++) {
+        hp[3 * k] = points[k].c0; hp[3 * k + 1] = points[k].c1; hp[3 * k + 2] = points[k].c2;
+        hp[3 * m + 3 * k] = answers[k].c0; hp[3 * m + 3 * k + 1] = answers[k].c1; hp[3 * m + 3 * k + 2] = answers[k].c2;
+      }
+      u64 *d_pv = mem.words(6 * m);
+      u64 *d_Q = mem.words(3 * m * m);
+      TVM_CUDA(cudaMemcpyAsync(d_pv, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, c.stream));
+      unsigned threads = 32;
+      while (threads < m + 1) threads <<= 1;
+      size_t smem = sizeof(u64) * (3 * (m + 1) + 3 * m);
+      stir_interpolate_kernel<<<1, threads, smem, c.stream>>>(d_pv, d_pv + 3 * m, (unsigned)m, d_Q, d_small, d_small + 3 * m);
+      launch_check(1);
+      TVM_CUDA(cudaStreamSynchronize(c.stream));     // `hp` goes out of scope
+      mem.release(d_pv); mem.release(d_Q);
+    } else {
+      const XPoly zf = xp_zerofier(points);
+      const XPoly ans = xp_interpolate(points, answers, zf);
       std::vector<u64> host(3 * (2 * m + 1));
       for (size_t k = 0; k < m; k++) { host[k] = ans[k].c0; host[m + k] = ans[k].c1; host[2 * m + k] = ans[k].c2; }
       u64 *hz = host.data() + 3 * m;
       for (size_t k = 0; k <= m; k++) { hz[k] = zf[k].c0; hz[(m + 1) + k] = zf[k].c1; hz[2 * (m + 1) + k] = zf[k].c2; }
-      u64 *d_small = mem.words(host.size());
       TVM_CUDA(cudaMemcpyAsync(d_small, host.data(), host.size() * 8, cudaMemcpyHostToDevice, c.stream));
+      TVM_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    const xfe rho = ps.sponge.sample_scalars(1)[0];       // degree-correction randomness
+
+    // next round's polynomial (stir.rs:958-972)
+    {
       u64 *d_A = mem.words(3 * n_len), *d_Z = mem.words(3 * n_len);
       evaluate(d_small, m, n_off, n_len, d_A, d_scratch);
       evaluate(d_small + 3 * m, m + 1, n_off, n_len, d_Z, d_scratch);
-      TVM_CUDA(cudaStreamSynchronize(c.stream));           // `host` goes out of scope below
       stir_quotient_kernel<<<st_grid(n_len), ST_THREADS, 0, c.stream>>>(d_fe, d_A, d_Z, n_len, n_off,
                                                                         c.get_pow_tab(root_of_unity_mont((unsigned)ilog2s(n_len)), ilog2s(n_len)),
                                                                         rho, (unsigned)(m + 1), d_scratch);
