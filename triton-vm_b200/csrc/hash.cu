@@ -487,6 +487,26 @@ void merkle_run(Ctx &c, u64 *nodes, size_t nleaves) {
   TVM_CUDA(cudaGetLastError());
 }
 
+// Multi-GPU: rank g builds only the subtree rooted at node W + g (its 1/W of every level of width >= W); the W
+// subtree roots are all-gathered in place (node W + g sits at nodes + 5*(W + g)) and the top of the tree is built by
+// every rank.  Node ownership for the authentication paths: gather_digests_run(log_w, rank).
+void merkle_run_sharded(Ctx &c, u64 *nodes, size_t nleaves, unsigned rank, unsigned W) {
+  if (W <= 1 || nleaves < 2 * (size_t)W) { merkle_run(c, nodes, nleaves); return; }
+  for (size_t w = nleaves / 2; w >= W; w >>= 1) {
+    const size_t cnt = w / W;
+    unsigned grid = (unsigned)((cnt + HASH_THREADS - 1) / HASH_THREADS);
+    merkle_level_kernel<<<grid, HASH_THREADS, 0, c.stream>>>(nodes, w + rank * cnt, cnt);
+    c.launches++;
+  }
+  TVM_CUDA(cudaGetLastError());
+  c.all_gather(nodes + 5 * (size_t)W, 40);
+  if (W >= 2) {
+    merkle_top_kernel<<<1, HASH_THREADS, 0, c.stream>>>(nodes, W / 2);
+    c.launches++;
+  }
+  TVM_CUDA(cudaGetLastError());
+}
+
 void xfe_leaves_run(Ctx &c, const u64 *cw, size_t stride, size_t n, u64 *leaves) {
   xfe_leaves_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(cw, stride, n, leaves);
   c.launches++;

@@ -42,6 +42,7 @@ void lde_evaluate_run(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fo
                       unsigned coset_first, unsigned coset_step, unsigned num_cosets, size_t ncols, u64 *d_out, u64 *d_tmp);
 void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, unsigned ncols, int log_r, u64 *digests);
 void merkle_run(Ctx &c, u64 *nodes, size_t nleaves);
+void merkle_run_sharded(Ctx &c, u64 *nodes, size_t nleaves, unsigned rank, unsigned world);
 void xfe_leaves_run(Ctx &c, const u64 *cw, size_t stride, size_t n, u64 *leaves);
 void to_mont_run(Ctx &c, u64 *d, size_t n);
 void from_mont_run(Ctx &c, u64 *d, size_t n);

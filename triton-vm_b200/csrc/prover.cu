@@ -289,7 +289,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
       shard_digests_to_natural_run(c, d_dig, d_nodes + 5 * N, (int)log_n, (int)log_r, sh.log_w);
       mem.release(d_dig);
     }
-    merkle_run(c, d_nodes, N);
+    merkle_run_sharded(c, d_nodes, N, rank, W);
     std::vector<u64> root = d2h(c, d_nodes + 5, 5);
     for (auto &v : root) v = from_mont(v);
     ps.enqueue(ItemKind::MerkleRoot, root);
@@ -404,10 +404,30 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   for (int t = 0; t < 4; t++) xpow_vector_run(c, xmulb(pts[t], off_inv), d_pw + (size_t)t * 3 * clen, clen, clen);
   u64 *d_dots = mem.words((NM + NA3 + 15 + 9) * 2 * 3);
   const size_t used = n + h;   // table interpolants have n + h non-zero (pre-scaled) coefficients
-  col_dot_run(c, d_main_coef, cs, NM, used, d_pw, clen, 3 * clen, 2, d_dots);
-  col_dot_run(c, d_aux_coef, cs, NA3, used, d_pw, clen, 3 * clen, 2, d_dots + NM * 6);
-  col_dot_run(c, d_seg_coef, seg_len, 15, seg_len, d_pw + 2 * 3 * clen, clen, 3 * clen, 2, d_dots + (NM + NA3) * 6);
-  std::vector<u64> dots = d2h(c, d_dots, (NM + NA3 + 15) * 6);
+  std::vector<u64> dots;
+  if (W == 1) {
+    col_dot_run(c, d_main_coef, cs, NM, used, d_pw, clen, 3 * clen, 2, d_dots);
+    col_dot_run(c, d_aux_coef, cs, NA3, used, d_pw, clen, 3 * clen, 2, d_dots + NM * 6);
+    col_dot_run(c, d_seg_coef, seg_len, 15, seg_len, d_pw + 2 * 3 * clen, clen, 3 * clen, 2, d_dots + (NM + NA3) * 6);
+    dots = d2h(c, d_dots, (NM + NA3 + 15) * 6);
+  } else {
+    // every rank holds all coefficients; each evaluates its block of columns, the (tiny) results are all-gathered
+    auto sharded_dots = [&](const u64 *d_coef, size_t ncols) {
+      const size_t cpr = (ncols + W - 1) / W, own0 = std::min(ncols, rank * cpr), own1 = std::min(ncols, own0 + cpr);
+      u64 *d_blk = mem.words(cpr * W * 6);
+      col_dot_run(c, d_coef + own0 * cs, cs, own1 - own0, used, d_pw, clen, 3 * clen, 2, d_blk + rank * cpr * 6);
+      c.all_gather(d_blk, cpr * 6 * 8);
+      std::vector<u64> v = d2h(c, d_blk, ncols * 6);
+      mem.release(d_blk);
+      return v;
+    };
+    dots = sharded_dots(d_main_coef, NM);
+    std::vector<u64> da = sharded_dots(d_aux_coef, NA3);
+    dots.insert(dots.end(), da.begin(), da.end());
+    col_dot_run(c, d_seg_coef, seg_len, 15, seg_len, d_pw + 2 * 3 * clen, clen, 3 * clen, 2, d_dots);
+    std::vector<u64> dsg = d2h(c, d_dots, 15 * 6);
+    dots.insert(dots.end(), dsg.begin(), dsg.end());
+  }
   auto dot_at = [&](size_t col, int v) { const u64 *p = &dots[(col * 2 + v) * 3]; return xmake(p[0], p[1], p[2]); };
   for (int v = 0; v < 2; v++) {
     std::vector<u64> row;
@@ -590,7 +610,8 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     auth.push_back(an.size());
     if (!an.empty()) {
       TVM_CUDA(cudaMemcpyAsync(d_idx, an.data(), an.size() * 4, cudaMemcpyHostToDevice, c.stream));
-      gather_digests_run(c, nodes, d_idx, (unsigned)an.size(), d_gather);
+      gather_digests_run(c, nodes, d_idx, (unsigned)an.size(), d_gather, sh.log_w, rank);
+      c.all_reduce_sum(d_gather, an.size() * 5);
       std::vector<u64> dg = d2h(c, d_gather, an.size() * 5);
       auth.insert(auth.end(), dg.begin(), dg.end());
     }

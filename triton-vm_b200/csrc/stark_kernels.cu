@@ -338,14 +338,24 @@ void gather_rows_run(Ctx &c, const u64 *table, size_t col_stride, unsigned ncols
   c.launches++;
   TVM_CUDA(cudaGetLastError());
 }
-__global__ void gather_digests_kernel(const u64 *nodes, const unsigned *idx, unsigned nidx, u64 *out) {
+// Sharded trees (log_w > 0, merkle_run_sharded): a node of a level at least 2^log_w wide belongs to the rank whose
+// subtree contains it; the replicated top levels are contributed by rank 0 only; everything else is written as zeros
+// so that all_reduce_sum_u64 reassembles the digests.
+__global__ void gather_digests_kernel(const u64 *nodes, const unsigned *idx, unsigned nidx, u64 *out, int log_w, unsigned rank) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nidx * 5) return;
-  out[t] = from_mont(nodes[(size_t)idx[t / 5] * 5 + t % 5]);
+  const unsigned i = idx[t / 5];
+  bool mine = true;
+  if (log_w > 0) {
+    const int level = 31 - __clz(i);                       // node i is at level floor(log2 i), width 2^level
+    if (level >= log_w) mine = ((i - (1u << level)) >> (level - log_w)) == rank;
+    else mine = rank == 0;
+  }
+  out[t] = mine ? from_mont(nodes[(size_t)i * 5 + t % 5]) : 0;
 }
-void gather_digests_run(Ctx &c, const u64 *nodes, const unsigned *d_idx, unsigned nidx, u64 *d_out) {
+void gather_digests_run(Ctx &c, const u64 *nodes, const unsigned *d_idx, unsigned nidx, u64 *d_out, int log_w, unsigned rank) {
   if (!nidx) return;
-  gather_digests_kernel<<<ew_grid((size_t)nidx * 5), EW_THREADS, 0, c.stream>>>(nodes, d_idx, nidx, d_out);
+  gather_digests_kernel<<<ew_grid((size_t)nidx * 5), EW_THREADS, 0, c.stream>>>(nodes, d_idx, nidx, d_out, log_w, rank);
   c.launches++;
   TVM_CUDA(cudaGetLastError());
 }
