@@ -177,6 +177,8 @@ def run_gpu(args):
     quot_rand = fill((nqr, 3))
     claim = ([1, 2, 3, 4, 5], [7, 8, 9], [10])
     b = tvm_b200.Backend(local_rank)
+    if args.low_memory is not None:
+        b.set_low_memory(args.low_memory)
     comm = None
     if world > 1:
         from tvm_b200.dist import TorchDistComm
@@ -251,6 +253,7 @@ def run_gpu(args):
                    f"one proof sharded over {world} GPUs by evaluation-domain cosets (NCCL all-gathers: "
                    f"{comm.calls['all_gather'] // max(1, 2 * (args.steps + args.warmup))} per proof)",
                    "l2": "inputs (GBs) larger than L2",
+                   "lde_tables": "just-in-time (low-memory mode)" if b.last_prove_low_memory else "cached in HBM",
                    "value_leg": "traces resident in HBM (device pointers through tvm_prove)",
                    "e2e_leg": "traces in pinned host memory, uploads overlapped with the LDE inside tvm_prove"},
         "e2e": {"value": e2e_ms, "unit": "ms",
@@ -305,6 +308,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2-height", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--low-memory", type=int, default=None, choices=[0, 1, 2],
+                    help="tvm_ctx_set_low_memory: 0 auto (default), 1 always just-in-time LDE, 2 always cache")
     ap.add_argument("--ldt", default="auto", choices=["auto", "fri", "stir"],
                     help="low-degree test; auto = the reference's own choice (STIR from padded height 2^16 on)")
     args = ap.parse_args()

@@ -41,6 +41,13 @@ int tvm_ctx_create(tvm_ctx **out, int cuda_device);
 void tvm_ctx_destroy(tvm_ctx *ctx);
 int tvm_ctx_set_stream(tvm_ctx *ctx, void *cuda_stream /* cudaStream_t, NULL = own stream */);
 int tvm_ctx_synchronize(tvm_ctx *ctx);
+/* Memory mode of tvm_prove.  The reference either caches the low-degree-extended tables or recomputes them just in
+ * time (TVM_LDE_TRACE / MasterTable::maybe_low_degree_extend_all_columns, master_table.rs:258-322; JIT branch
+ * stark.rs:805-1006).  0 = decide from the free device memory (default), 1 = always just in time (the extended
+ * main/aux tables are never stored: every coset is re-evaluated for row hashing, for the AIR and for the openings),
+ * 2 = always cache.  The proof is identical in both modes. */
+int tvm_ctx_set_low_memory(tvm_ctx *ctx, int mode);
+int tvm_last_prove_low_memory(const tvm_ctx *ctx); /* 1 if the last tvm_prove ran just in time */
 
 /* Multi-GPU: one process (and one context) per GPU.  A proof is sharded by evaluation-domain cosets
  * (mirroring the reference's own coset decomposition, stark.rs:824-885): rank g of

@@ -85,3 +85,26 @@ def test_stir_proof_is_bit_exact_vs_oracle(backend, security, padded_height, see
     assert len(got) == len(want)
     assert got == want
     assert S.verify(st, claim, got, check_air=False)
+
+
+@pytest.mark.parametrize("ldt", ["fri", "stir"])
+def test_low_memory_mode_produces_the_same_proof(backend, ldt):
+    """Just-in-time LDE (tables never stored, every coset re-evaluated for hashing, AIR and openings) vs cached tables."""
+    import tvm_b200
+    if ldt == "stir":
+        st, d, claim, main, mrand, aux_provider, qrand = synthetic_stir_instance(6, 256, 21)
+        kw = dict(security_level=6, log2_expansion=2, padded_height=256, ldt_choice=tvm_b200.LDT_STIR)
+    else:
+        st, d, claim, main, mrand, aux_provider, qrand = synthetic_instance(32, 2, 256, 22)
+        kw = dict(security_level=32, log2_expansion=2, padded_height=256)
+    args = ((claim.program_digest, claim.input, claim.output), main, mrand, aux_provider, qrand)
+    try:
+        backend.set_low_memory(2)
+        cached = backend.prove(*args, **kw)
+        assert not backend.last_prove_low_memory
+        backend.set_low_memory(1)
+        jit = backend.prove(*args, **kw)
+        assert backend.last_prove_low_memory
+    finally:
+        backend.set_low_memory(0)
+    assert np.array_equal(cached, jit)

@@ -44,6 +44,9 @@ def _worker(rank, world, port, params, q):
         assert not comm.errors, comm.errors
         assert comm.calls["all_gather"] >= 12 and comm.calls["all_reduce"] == 6, comm.calls
         assert np.array_equal(single, sharded), "sharded proof differs from the single-GPU proof"
+        b.set_low_memory(1)                      # sharded AND just-in-time LDE
+        assert np.array_equal(single, b.prove(*args, **kw)), "sharded low-memory proof differs"
+        b.set_low_memory(0)
         b.set_comm(None)
         assert np.array_equal(single, b.prove(*args, **kw))
         q.put((rank, "ok", len(single)))

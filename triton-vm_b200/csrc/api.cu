@@ -174,6 +174,13 @@ int tvm_ctx_set_comm(tvm_ctx *ctx, const tvm_comm *comm) {
   TVM_API_END
 }
 
+int tvm_ctx_set_low_memory(tvm_ctx *ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 2) return TVM_ERR_INVALID_ARG;
+  ctx->c.low_memory_mode = mode;
+  return TVM_OK;
+}
+int tvm_last_prove_low_memory(const tvm_ctx *ctx) { return ctx && ctx->timings.low_memory ? 1 : 0; }
+
 int tvm_ctx_synchronize(tvm_ctx *ctx) {
   if (!ctx) return TVM_ERR_INVALID_ARG;
   TVM_API_BEGIN(ctx)

@@ -44,6 +44,7 @@ struct Ctx {
   tvm_comm comm{0, 1, nullptr, nullptr, nullptr};
   void all_gather(void *dev_buf, size_t bytes_per_rank);
   void all_reduce_sum(u64 *dev_buf, size_t count);
+  int low_memory_mode = 0;              // 0 = automatic, 1 = always just-in-time LDE, 2 = never (tvm_ctx_set_low_memory)
   cudaStream_t copy_stream = nullptr;   // host<->device staging overlapped with compute (created on first use)
   std::vector<cudaEvent_t> copy_events; // recycled per-batch "upload done" events
   cudaStream_t get_copy_stream();

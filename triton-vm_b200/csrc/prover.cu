@@ -203,6 +203,19 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   const size_t NL = n * sh.count;                       // rows of the LDT domain held by this rank
   const size_t hpad = std::min(n, (h + 63) & ~(size_t)63);
   const size_t cs = n + hpad;                           // stride of a table column's interpolant coefficients
+  // Low-memory mode (the reference's just-in-time LDE, stark.rs:805-1006, master_table.rs:470-503, 557-606): the
+  // extended main/aux tables are never stored; every use (row hashing, AIR, openings) re-evaluates one coset at a
+  // time from the interpolant coefficients.  Chosen automatically when the cached tables would not fit.
+  bool jit = c.low_memory_mode == 1;
+  if (c.low_memory_mode == 0) {
+    size_t free_b = 0, total_b = 0;
+    TVM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t pooled = 0;
+    for (auto &kv : c.pool_free) pooled += kv.first;
+    const double need = 8.0 * ((double)(NM + NA3) * (NL + cs) + 40.0 * N) * 1.15;
+    jit = need > (double)(free_b + pooled);
+  }
+  if (timings) timings->low_memory = jit;
   cudaEvent_t ev[20];
   int nev = 0;
   auto mark = [&]() {
@@ -235,7 +248,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     const size_t own0 = std::min(ncols, rank * cpr), own1 = std::min(ncols, own0 + cpr), nown = own1 - own0;
     const size_t bcols = ncols * xf;                    // B-field columns
     d_coef = mem.words(cpr * W * xf * cs);
-    d_lde = mem.words(bcols * NL);
+    d_lde = jit ? nullptr : mem.words(bcols * NL);
     u64 *d_in = mem.words(std::max<size_t>(1, nown) * xf * n + ncols * xf * h);
     u64 *d_rand_in = d_in + std::max<size_t>(1, nown) * xf * n;
     u64 *d_planar = xf == 3 ? mem.words(std::max<size_t>(1, nown) * 3 * n + ncols * 3 * h) : d_in;
@@ -267,20 +280,36 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
       const size_t q0 = (own0 + c0) * xf;               // first B-field column of the batch
       lde_interpolate_run(c, d_planar + c0 * xf * n, d_rand + q0 * h, (unsigned)h, (unsigned)hpad, log_n, off, b * xf,
                           d_coef + q0 * cs, cs, d_tmp);
-      if (W == 1) lde_evaluate_run(c, d_coef + q0 * cs, cs, (unsigned)h, log_n, log_r, sh.first, sh.step, sh.count, b * xf,
-                                   d_lde + q0 * NL, d_tmp);
+      if (W == 1 && !jit) lde_evaluate_run(c, d_coef + q0 * cs, cs, (unsigned)h, log_n, log_r, sh.first, sh.step, sh.count, b * xf,
+                                           d_lde + q0 * NL, d_tmp);
     }
     if (W > 1) {
       c.all_gather(d_coef, cpr * xf * cs * 8);
-      evaluate_cols(c, d_coef, cs, (unsigned)h, bcols, log_n, log_r, sh, d_lde, d_tmp, tmp_cols);
+      if (!jit) evaluate_cols(c, d_coef, cs, (unsigned)h, bcols, log_n, log_r, sh, d_lde, d_tmp, tmp_cols);
     }
     if (xf == 3) mem.release(d_planar);
     mem.release(d_in);
   };
   // Row digests of this rank's rows -> leaves of the full tree (all-gathered across ranks), then the tree.
-  auto commit_rows = [&](const u64 *d_lde, unsigned ncols, u64 *d_nodes) {
+  // one local coset y of a table, evaluated from its coefficients (low-memory mode): [ncols][n]
+  auto evaluate_coset = [&](const u64 *d_coef, unsigned ncols, unsigned y, u64 *d_out) {
+    const Shard one{sh.first + sh.step * y, sh.step, 1, sh.log_w};
+    evaluate_cols(c, d_coef, cs, (unsigned)h, ncols, log_n, log_r, one, d_out, d_tmp, tmp_cols);
+  };
+  auto commit_rows = [&](const u64 *d_lde, const u64 *d_coef, unsigned ncols, u64 *d_nodes) {
     TVM_CUDA(cudaMemsetAsync(d_nodes, 0, 40, c.stream));
-    if (W == 1) {
+    if (!d_lde) {                                       // low-memory mode: hash coset by coset
+      u64 *d_dig = mem.words(5 * N);                    // [rank][y][k][5]
+      u64 *d_coset = mem.words((size_t)ncols * n);
+      for (unsigned y = 0; y < sh.count; y++) {
+        evaluate_coset(d_coef, ncols, y, d_coset);
+        hash_rows_run(c, d_coset, n, n, ncols, 0, d_dig + ((size_t)rank * NL + (size_t)y * n) * 5);
+      }
+      mem.release(d_coset);
+      c.all_gather(d_dig, NL * 40);
+      shard_digests_to_natural_run(c, d_dig, d_nodes + 5 * N, (int)log_n, (int)log_r, sh.log_w);
+      mem.release(d_dig);
+    } else if (W == 1) {
       hash_rows_run(c, d_lde, N, N, ncols, (int)log_r, d_nodes + 5 * N);
     } else {
       u64 *d_dig = mem.words(5 * N);                    // [rank][y][k][5]
@@ -299,7 +328,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   extend_table(h_main_trace, h_main_rand, NM, 1, d_main_coef, d_main_lde);
   mark();  // 1: main LDE
   u64 *d_main_nodes = mem.words(2 * N * 5);
-  commit_rows(d_main_lde, (unsigned)NM, d_main_nodes);
+  commit_rows(d_main_lde, d_main_coef, (unsigned)NM, d_main_nodes);
   mark();  // 2: main Merkle
 
   // ---- challenges (stark.rs:374-376, challenges.rs:88-135) -------------------------------------------
@@ -330,7 +359,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   extend_table(h_aux_trace, h_aux_rand, NA, 3, d_aux_coef, d_aux_lde);
   mark();  // 4: aux LDE
   u64 *d_aux_nodes = mem.words(2 * N * 5);
-  commit_rows(d_aux_lde, (unsigned)NA3, d_aux_nodes);
+  commit_rows(d_aux_lde, d_aux_coef, (unsigned)NA3, d_aux_nodes);
   mark();  // 5: aux Merkle
 
   // ---- quotient codeword (stark.rs:396-411, master_table.rs:1264-1363) ---------------------------------------
@@ -347,8 +376,19 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   TVM_CUDA(cudaMemcpyAsync(d_consts, consts.data(), consts.size() * 8, cudaMemcpyHostToDevice, c.stream));
   TVM_CUDA(cudaStreamSynchronize(c.stream));
   u64 *d_quot = mem.words(3 * N);   // gather buffer [rank][3][NL]; this rank's rows go to its own block
-  air_quotient_run(c, d_main_lde, NL, d_aux_lde, NL, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, sh.first, sh.step,
-                   sh.count, off, d_quot + (size_t)rank * 3 * NL, NL);
+  if (jit) {
+    u64 *d_mc = mem.words(NM * n), *d_ac = mem.words(NA3 * n);
+    for (unsigned y = 0; y < sh.count; y++) {
+      evaluate_coset(d_main_coef, (unsigned)NM, y, d_mc);
+      evaluate_coset(d_aux_coef, (unsigned)NA3, y, d_ac);
+      air_quotient_run(c, d_mc, n, d_ac, n, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, sh.first + sh.step * y, sh.step, 1,
+                       off, d_quot + (size_t)rank * 3 * NL + (size_t)y * n, NL);
+    }
+    mem.release(d_mc); mem.release(d_ac);
+  } else {
+    air_quotient_run(c, d_main_lde, NL, d_aux_lde, NL, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, sh.first, sh.step,
+                     sh.count, off, d_quot + (size_t)rank * 3 * NL, NL);
+  }
   mark();  // 6: AIR quotient
 
   // interpolate (stark.rs:1224-1231): natural order, iNTT, (coset offset undone inside the segment kernel)
@@ -387,7 +427,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   evaluate_cols(c, d_seg_coef, seg_len, (unsigned)n, 15, log_n, log_r, sh, d_seg_lde, d_tmp, tmp_cols);
   mark();  // 7: quotient LDE
   u64 *d_quot_nodes = mem.words(2 * N * 5);
-  commit_rows(d_seg_lde, 15, d_quot_nodes);
+  commit_rows(d_seg_lde, nullptr, 15, d_quot_nodes);
   mark();  // 8: quotient Merkle
   mem.release(d_qnat);
 
@@ -596,9 +636,27 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   }
 
   // ---- open rows (stark.rs:665-716) ---------------------------------------------------------------------------------------------
-  auto open_table = [&](const u64 *table, unsigned ncols, ItemKind kind, const u64 *nodes) {
-    TVM_CUDA(cudaMemcpyAsync(d_idx, a_indices.data(), nq * 4, cudaMemcpyHostToDevice, c.stream));
-    gather_rows_run(c, table, NL, ncols, d_idx, nq, (int)log_n, (int)log_r, d_gather, sh.log_w, rank);
+  auto open_table = [&](const u64 *table, const u64 *d_coef, unsigned ncols, ItemKind kind, const u64 *nodes) {
+    if (table) {
+      TVM_CUDA(cudaMemcpyAsync(d_idx, a_indices.data(), nq * 4, cudaMemcpyHostToDevice, c.stream));
+      gather_rows_run(c, table, NL, ncols, d_idx, nq, (int)log_n, (int)log_r, d_gather, sh.log_w, rank);
+    } else {
+      // low-memory mode: re-evaluate the cosets that contain opened rows (master_table.rs:557-606)
+      TVM_CUDA(cudaMemsetAsync(d_gather, 0, (size_t)nq * ncols * 8, c.stream));
+      u64 *d_coset = mem.words((size_t)ncols * n);
+      for (unsigned y = 0; y < sh.count; y++) {
+        const unsigned coset = sh.first + sh.step * y;
+        std::vector<unsigned> kt;                       // (k, t) pairs of the queries that fall into this coset
+        for (unsigned t = 0; t < nq; t++)
+          if ((a_indices[t] & ((1u << log_r) - 1)) == coset) { kt.push_back(a_indices[t] >> log_r); kt.push_back(t); }
+        if (kt.empty()) continue;
+        evaluate_coset(d_coef, ncols, y, d_coset);
+        TVM_CUDA(cudaMemcpyAsync(d_idx, kt.data(), kt.size() * 4, cudaMemcpyHostToDevice, c.stream));
+        gather_rows_scatter_run(c, d_coset, n, ncols, d_idx, (unsigned)(kt.size() / 2), d_gather);
+        TVM_CUDA(cudaStreamSynchronize(c.stream));      // `kt` goes out of scope
+      }
+      mem.release(d_coset);
+    }
     c.all_reduce_sum(d_gather, (size_t)nq * ncols);
     std::vector<u64> rows = d2h(c, d_gather, (size_t)nq * ncols);
     std::vector<u64> payload;
@@ -617,9 +675,9 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     }
     ps.enqueue(ItemKind::AuthenticationStructure, auth);
   };
-  open_table(d_main_lde, (unsigned)NM, ItemKind::MasterMainTableRows, d_main_nodes);
-  open_table(d_aux_lde, (unsigned)NA3, ItemKind::MasterAuxTableRows, d_aux_nodes);
-  open_table(d_seg_lde, 15, ItemKind::QuotientSegmentsElements, d_quot_nodes);
+  open_table(d_main_lde, d_main_coef, (unsigned)NM, ItemKind::MasterMainTableRows, d_main_nodes);
+  open_table(d_aux_lde, d_aux_coef, (unsigned)NA3, ItemKind::MasterAuxTableRows, d_aux_nodes);
+  open_table(d_seg_lde, nullptr, 15, ItemKind::QuotientSegmentsElements, d_quot_nodes);
   mark();  // 12: open
 
   proof = ps.encode();

@@ -341,6 +341,19 @@ void gather_rows_run(Ctx &c, const u64 *table, size_t col_stride, unsigned ncols
 // Sharded trees (log_w > 0, merkle_run_sharded): a node of a level at least 2^log_w wide belongs to the rank whose
 // subtree contains it; the replicated top levels are contributed by rank 0 only; everything else is written as zeros
 // so that all_reduce_sum_u64 reassembles the digests.
+// low-memory mode: rows of ONE coset table [ncols][n]; kt = (k, t) pairs: out[t][q] = table[q][k]
+__global__ void gather_rows_scatter_kernel(const u64 *table, size_t col_stride, unsigned ncols, const unsigned *kt, unsigned count, u64 *out) {
+  unsigned j = blockIdx.x;
+  if (j >= count) return;
+  const size_t k = kt[2 * j], t = kt[2 * j + 1];
+  for (unsigned q = threadIdx.x; q < ncols; q += blockDim.x) out[t * ncols + q] = from_mont(table[(size_t)q * col_stride + k]);
+}
+void gather_rows_scatter_run(Ctx &c, const u64 *table, size_t col_stride, unsigned ncols, const unsigned *d_kt, unsigned count, u64 *d_out) {
+  if (!count) return;
+  gather_rows_scatter_kernel<<<count, 128, 0, c.stream>>>(table, col_stride, ncols, d_kt, count, d_out);
+  c.launches++;
+  TVM_CUDA(cudaGetLastError());
+}
 __global__ void gather_digests_kernel(const u64 *nodes, const unsigned *idx, unsigned nidx, u64 *out, int log_w, unsigned rank) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nidx * 5) return;

@@ -85,6 +85,8 @@ _SIGNATURES = {
     "tvm_ctx_set_stream": (ctypes.c_int, [_vp, _vp]),
     "tvm_ctx_synchronize": (ctypes.c_int, [_vp]),
     "tvm_ctx_set_comm": (ctypes.c_int, [_vp, ctypes.POINTER(CommStruct)]),
+    "tvm_ctx_set_low_memory": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "tvm_last_prove_low_memory": (ctypes.c_int, [_vp]),
     "tvm_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "tvm_last_error": (ctypes.c_char_p, [_vp]),
     "tvm_launch_count": (ctypes.c_uint64, [_vp]),
@@ -294,6 +296,14 @@ class Backend:
             raise err[0]
         self._chk(rc)
         return buf[:cap.value].copy()
+
+    def set_low_memory(self, mode):
+        """0 = automatic, 1 = always just-in-time LDE (tables never stored), 2 = always cache."""
+        self._chk(self._l.tvm_ctx_set_low_memory(self._h, int(mode)))
+
+    @property
+    def last_prove_low_memory(self):
+        return bool(self._l.tvm_last_prove_low_memory(self._h))
 
     def set_comm(self, comm):
         """Attach a communication layer (tvm_b200.dist.TorchDistComm) so that prove() shards one proof over
