@@ -9,11 +9,11 @@ from oracle import corc, field as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("log2n", [0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 12, 13, 14, 16, 17])
+@pytest.mark.parametrize("log2n", [0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 12, 13, 14, 16, 17, 20, 25])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_ntt_matches_oracle(backend, log2n, inverse):
     rng = np.random.default_rng(100 + log2n)
-    ncols = 3 if log2n >= 13 else 5
+    ncols = 1 if log2n >= 20 else 3 if log2n >= 13 else 5
     x = rand_bfes(rng, (ncols, 1 << log2n))
     got = backend.ntt(x, inverse=inverse)
     for c in range(ncols):

@@ -90,5 +90,53 @@ def report(src, dst):
             f.write("\n")
 
 
+def table(src, dst):
+    """one row per kernel name of an all-kernels `--set full` capture: time, achieved DRAM GB/s, issue utilisation"""
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    lines = [l for l in out.splitlines(True) if l.startswith('"')]
+    rd = list(csv.reader(io.StringIO("".join(lines))))
+    header, units = rd[0], rd[1]
+    u = dict(zip(header, units))
+
+    def num(d, k, default=0.0):
+        try:
+            return float(d.get(k, "").replace(",", ""))
+        except ValueError:
+            return default
+
+    def to_bytes(v, unit):
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
+
+    def to_ns(v, unit):
+        return v * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1, "usecond": 1e3, "msecond": 1e6, "second": 1e9}.get(unit, 1)
+
+    agg = OrderedDict()
+    for row in rd[2:]:
+        d = dict(zip(header, row))
+        name = short(d.get("Kernel Name", "?"))
+        if name.startswith("air_chunk_"):
+            name = "air_chunk_* (generated AIR kernels)"
+        a = agg.setdefault(name, dict(n=0, ns=0.0, rd=0.0, wr=0.0, issue=0.0, alu=0.0, fma=0.0, occ=0.0, regs=0))
+        t = to_ns(num(d, "gpu__time_duration.sum"), u.get("gpu__time_duration.sum", "ns"))
+        a["n"] += 1; a["ns"] += t
+        a["rd"] += to_bytes(num(d, "dram__bytes_read.sum"), u.get("dram__bytes_read.sum", "byte"))
+        a["wr"] += to_bytes(num(d, "dram__bytes_write.sum"), u.get("dram__bytes_write.sum", "byte"))
+        a["issue"] += t * num(d, "smsp__issue_active.avg.pct_of_peak_sustained_active")
+        a["alu"] += t * num(d, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")
+        a["fma"] += t * num(d, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active")
+        a["occ"] += t * num(d, "sm__warps_active.avg.pct_of_peak_sustained_active")
+        a["regs"] = max(a["regs"], int(num(d, "launch__registers_per_thread")))
+    total = sum(a["ns"] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# every kernel of one prove(), `ncu --set full`\n\nsource: `{src}` (kept in gpurun_out/, not tracked); "
+                "durations are ncu's serialised cold-cache per-launch times; pipe / issue figures are time-weighted means\n\n")
+        f.write("| kernel | launches | ms | share | DRAM GB/s (rd+wr) | issue % | ALU pipe % | FMA pipe % | warps active % | regs |\n"
+                "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ns"]):
+            t = a["ns"] or 1.0
+            f.write(f"| `{k}` | {a['n']} | {a['ns']/1e6:.3f} | {100*a['ns']/total:.1f}% | {(a['rd']+a['wr'])/t:.0f} | "
+                    f"{a['issue']/t:.0f} | {a['alu']/t:.0f} | {a['fma']/t:.0f} | {a['occ']/t:.0f} | {a['regs']} |\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "report": report, "table": table}[sys.argv[1]](sys.argv[2], sys.argv[3])

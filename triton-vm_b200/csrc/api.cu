@@ -226,8 +226,8 @@ int tvm_ntt_bfe_dev(tvm_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, uint64_
   size_t n = (size_t)1 << log2n;
   j.in = (const u64 *)d_in; j.in_cstride = n; j.out = (u64 *)d_out; j.out_cstride = n; j.tmp = (u64 *)d_tmp;
   j.log_n = (int)log2n; j.ncols = ncols; j.inverse = inverse != 0;
-  if (log2n > 12 && !d_tmp) throw ApiError{TVM_ERR_INVALID_ARG, "tvm_ntt_bfe_dev: d_tmp required for log2n > 12"};
-  if (log2n > 24) throw ApiError{TVM_ERR_UNSUPPORTED, "tvm_ntt_bfe_dev: log2n > 24 not supported"};
+  if (log2n > 13 && !d_tmp) throw ApiError{TVM_ERR_INVALID_ARG, "tvm_ntt_bfe_dev: d_tmp required for log2n > 13"};
+  if (log2n > 26) throw ApiError{TVM_ERR_UNSUPPORTED, "tvm_ntt_bfe_dev: log2n > 26 not supported"};
   ntt_run(*c__, j);
   TVM_API_END
 }
@@ -253,7 +253,7 @@ int tvm_ntt_bfe(tvm_ctx *ctx, uint64_t *host, unsigned log2n, size_t ncols, int 
 int tvm_lde_bfe_dev(tvm_ctx *ctx, const uint64_t *d_trace, const uint64_t *d_rand, unsigned num_rand, unsigned log2_trace,
                     unsigned log2_cosets, uint64_t offset_canon, size_t ncols, uint64_t *d_coef, uint64_t *d_out, uint64_t *d_tmp) {
   if (!ctx || !d_trace || !d_coef || !d_out || !d_tmp) return TVM_ERR_INVALID_ARG;
-  if (log2_trace > 24 || log2_cosets > 6 || offset_canon >= P || offset_canon == 0) return TVM_ERR_DOMAIN;
+  if (log2_trace > 26 || log2_cosets > 6 || offset_canon >= P || offset_canon == 0) return TVM_ERR_DOMAIN;
   TVM_API_BEGIN(ctx)
   if (!ncols) return TVM_OK;
   lde_run(*c__, (const u64 *)d_trace, (const u64 *)d_rand, num_rand, log2_trace, log2_cosets, to_mont(offset_canon), ncols,

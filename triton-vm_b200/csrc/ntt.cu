@@ -25,7 +25,7 @@
 namespace tvm {
 
 static constexpr int NTT_THREADS = 512;
-static constexpr int LT_MAX = 12;
+static constexpr int LT_MAX = 13;   // two passes cover transforms up to 2^26 (LDT domain of padded height 2^23)
 
 __device__ __forceinline__ u64 powtab_get(const PowTab &t, u64 e) {
   u64 lo = __ldg(t.lo + (e & ((1ULL << t.shift) - 1)));
@@ -370,7 +370,8 @@ static int pick_log_t(int LT) {
   // T interleaved rows per tile: keep the tile <= 128 KB of shared memory
   if (LT <= 10) return 3;
   if (LT == 11) return 3;
-  return 2;
+  if (LT == 12) return 2;
+  return 1;
 }
 static size_t tile_smem_bytes(int LT, int log_t) {
   size_t N = (size_t)1 << LT;
