@@ -143,6 +143,7 @@ typedef struct tvm_params {
   uint32_t log2_ldt_expansion_factor; /* Stark::default(): 2   */
   uint32_t ldt_choice;                /* 0 = the reference's heuristic (Stark::default(): FRI below padded height 2^16,
                                          STIR from there on, stark.rs:1942-1957); 1 = LdtChoice::Fri; 2 = LdtChoice::Stir */
+  uint32_t soundness;                 /* ProximityRegime (low_degree_test/mod.rs:60-80): 0 = Proven (default), 1 = Conjectured */
 } tvm_params;
 typedef struct tvm_domains {
   uint64_t padded_height, num_trace_randomizers, randomized_trace_len, trace_len, quotient_len, ldt_len;

@@ -70,21 +70,21 @@ class Stark:
     `ldt`: "fri", "stir" or None = the reference's heuristic (stark.rs:1942-1957: FRI below padded
     height 2^16, STIR from there on)."""
 
-    def __init__(self, security_level=160, log2_expansion_factor=2, ldt=None):
+    def __init__(self, security_level=160, log2_expansion_factor=2, ldt=None, soundness="proven"):
         assert log2_expansion_factor >= 1
-        assert ldt in (None, "fri", "stir")
+        assert ldt in (None, "fri", "stir") and soundness in ("proven", "conjectured")
         self.security_level = security_level
         self.log2_expansion = log2_expansion_factor
         self.ldt = ldt
+        self.soundness = soundness                                # ProximityRegime (mod.rs:60-80)
 
     def ldt_choice(self, padded_height):
-        return self.ldt or ("fri" if next_pow2(padded_height).bit_length() - 1 < 16 else "stir")
+        threshold = 16 if self.soundness == "proven" else 17      # stark.rs:1944-1949
+        return self.ldt or ("fri" if next_pow2(padded_height).bit_length() - 1 < threshold else "stir")
 
     # low_degree_test/mod.rs:250-300 (ProximityRegime::Proven), fri.rs:832-836
     def num_collinearity_checks(self):
-        rate = 1.0 / float(1 << self.log2_expansion)
-        margin = math.sqrt(rate)
-        proximity_parameter = 1.0 - margin - margin / 20.0
+        proximity_parameter = stir_mod.rs_proximity_parameter(self.log2_expansion, self.soundness)
         return int(math.ceil(-float(self.security_level) / math.log2(1.0 - proximity_parameter)))
 
     @staticmethod
@@ -112,7 +112,7 @@ class Stark:
             hdb += 1
             ldt_len = 1 << (hdb + self.log2_expansion)
             if ldt == "stir":
-                stir_params = stir_mod.derive(self.security_level, 2, self.log2_expansion, hdb)
+                stir_params = stir_mod.derive(self.security_level, 2, self.log2_expansion, hdb, self.soundness)
                 first_round = stir_params["num_first_round_queries"]
             else:
                 first_round = checks

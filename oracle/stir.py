@@ -23,25 +23,39 @@ LOG2_FIELD_SIZE_U32 = 8 * 8 * 3          # StirParameters::LOG2_FIELD_SIZE (stir
 LOG2_DOMAIN_SHRINKAGE = 1                # stir.rs:422
 
 
-# ---- Reed-Solomon code parameters (mod.rs:212-300), ProximityRegime::Proven -----------------------
+# ---- Reed-Solomon code parameters (mod.rs:212-300) ------------------------------------------------
+RS_LOG2_FIELD_SIZE = 191.99999999899228  # ReedSolomonCode::LOG2_FIELD_SIZE (mod.rs:227)
+
+
 def rs_rate(log2_expansion):
     return 1.0 / float(1 << log2_expansion)
 
 
-def rs_proximity_margin(log2_expansion):
-    return math.sqrt(rs_rate(log2_expansion))
+def rs_q_ary_entropy(log2_expansion):                    # mod.rs:258-264
+    rate = rs_rate(log2_expansion)
+    rate_log_rate = rate * -float(log2_expansion)
+    one_m = (1.0 - rate) * math.log2(1.0 - rate)
+    return rate - (rate_log_rate + one_m) / RS_LOG2_FIELD_SIZE
 
 
-def rs_slackness(log2_expansion):
-    return rs_proximity_margin(log2_expansion) / 20.0
+def rs_proximity_margin(log2_expansion, soundness="proven"):
+    return math.sqrt(rs_rate(log2_expansion)) if soundness == "proven" else rs_q_ary_entropy(log2_expansion)
 
 
-def rs_proximity_parameter(log2_expansion):
-    return 1.0 - rs_proximity_margin(log2_expansion) - rs_slackness(log2_expansion)
+def rs_slackness(log2_expansion, soundness="proven"):
+    return rs_proximity_margin(log2_expansion, soundness) / 20.0
 
 
-def rs_log2_list_size(log2_expansion):
-    return math.log2(1.0 / (2.0 * math.sqrt(rs_rate(log2_expansion)) * rs_slackness(log2_expansion)))
+def rs_proximity_parameter(log2_expansion, soundness="proven"):
+    return 1.0 - rs_proximity_margin(log2_expansion, soundness) - rs_slackness(log2_expansion, soundness)
+
+
+def rs_log2_list_size(log2_expansion, soundness="proven", log2_poly_degree=0):     # mod.rs:274-287
+    if soundness == "proven":
+        ls = 1.0 / (2.0 * math.sqrt(rs_rate(log2_expansion)) * rs_slackness(log2_expansion, soundness))
+    else:
+        ls = math.pow(2.0, float(log2_poly_degree)) / (rs_q_ary_entropy(log2_expansion) * rs_slackness(log2_expansion, soundness))
+    return math.log2(ls)
 
 
 def log2_binomial_coefficient(a, b):     # stir.rs:854-869 (Kahan-Babuska summation, same order)
@@ -56,8 +70,8 @@ def log2_binomial_coefficient(a, b):     # stir.rs:854-869 (Kahan-Babuska summat
     return log2_binom
 
 
-def num_unique_in_domain_queries(security, log2_expansion):      # stir.rs:633-639
-    return int(math.ceil(-float(security) / math.log2(1.0 - rs_proximity_parameter(log2_expansion))))
+def num_unique_in_domain_queries(security, log2_expansion, soundness="proven"):      # stir.rs:633-639
+    return int(math.ceil(-float(security) / math.log2(1.0 - rs_proximity_parameter(log2_expansion, soundness))))
 
 
 def num_total_in_domain_queries(security, log2_domain_len, num_uniques):   # stir.rs:758-776
@@ -71,17 +85,17 @@ def num_total_in_domain_queries(security, log2_domain_len, num_uniques):   # sti
     return int(math.ceil(n))
 
 
-def num_in_domain_queries(security, log2_domain_size, log2_expansion):     # stir.rs:597-609
-    uniques = min(num_unique_in_domain_queries(security, log2_expansion), 1 << log2_domain_size)
+def num_in_domain_queries(security, log2_domain_size, log2_expansion, soundness="proven"):     # stir.rs:597-609
+    uniques = min(num_unique_in_domain_queries(security, log2_expansion, soundness), 1 << log2_domain_size)
     return num_total_in_domain_queries(security, log2_domain_size, uniques)
 
 
-def num_ood_queries(security, log2_poly_degree, log2_expansion):            # stir.rs:831-842
-    return int(math.ceil((float(security) - 1.0 + 2.0 * rs_log2_list_size(log2_expansion))
+def num_ood_queries(security, log2_poly_degree, log2_expansion, soundness="proven"):            # stir.rs:831-842
+    return int(math.ceil((float(security) - 1.0 + 2.0 * rs_log2_list_size(log2_expansion, soundness, log2_poly_degree))
                          / float(LOG2_FIELD_SIZE_U32 - log2_poly_degree)))
 
 
-def derive(security, log2_folding_factor, log2_initial_expansion, log2_high_degree_bound):
+def derive(security, log2_folding_factor, log2_initial_expansion, log2_high_degree_bound, soundness="proven"):
     """StirParameters::try_into_stir (stir.rs:437-567) -> dict"""
     if log2_folding_factor < 2: raise ValueError("TooSmallLog2FoldingFactor")
     if log2_initial_expansion == 0: raise ValueError("TooSmallInitialExpansionFactor")
@@ -94,9 +108,9 @@ def derive(security, log2_folding_factor, log2_initial_expansion, log2_high_degr
     log2_folded_domain_size = log2_domain_len - log2_folding_factor
     rounds = []
     while folded_poly_degree > folding_factor:
-        in_domain = num_in_domain_queries(security, log2_folded_domain_size, log2_expansion)
+        in_domain = num_in_domain_queries(security, log2_folded_domain_size, log2_expansion, soundness)
         log2_next_expansion = log2_expansion + log2_folding_factor - LOG2_DOMAIN_SHRINKAGE
-        ood = num_ood_queries(security, folded_poly_degree.bit_length() - 1, log2_next_expansion)
+        ood = num_ood_queries(security, folded_poly_degree.bit_length() - 1, log2_next_expansion, soundness)
         next_deg = folded_poly_degree // folding_factor
         if in_domain + ood > next_deg:
             break
@@ -104,7 +118,7 @@ def derive(security, log2_folding_factor, log2_initial_expansion, log2_high_degr
         folded_poly_degree = next_deg
         log2_expansion = log2_next_expansion
         log2_folded_domain_size -= LOG2_DOMAIN_SHRINKAGE
-    final_in = num_in_domain_queries(security, log2_folded_domain_size, log2_expansion)
+    final_in = num_in_domain_queries(security, log2_folded_domain_size, log2_expansion, soundness)
     return dict(initial_domain_len=1 << log2_domain_len, initial_offset=F.GENERATOR, folding_factor=folding_factor,
                 round_queries=rounds, final_num_in_domain_queries=final_in, final_degree=folded_poly_degree,
                 num_first_round_queries=rounds[0][0] if rounds else final_in)

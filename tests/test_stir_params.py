@@ -37,13 +37,20 @@ def test_round_structure_at_the_baseline_heights():      # SURVEY.md §8 table (
     assert S.Stark(160, 2).derive(1 << 10)["ldt"] == "fri"
 
 
+def test_q_ary_entropy_reference_values():               # mod.rs:406-423 (computed with sage there)
+    for want, e in [(0.505208333333361, 1), (0.254225406898247, 2), (0.127831064808346, 3), (0.064256719096972, 4),
+                    (0.032294907939134, 5), (0.016229766017215, 6), (0.008155804230956, 7), (0.004098304720073, 8)]:
+        assert abs(stir.rs_q_ary_entropy(e) - want) < 1e-4
+
+
 @pytest.mark.parametrize("security,log2_exp", [(160, 2), (80, 2), (42, 3), (16, 1), (8, 2), (6, 2)])
 @pytest.mark.parametrize("choice", [0, 1, 2])
-def test_host_derivation_matches_oracle(security, log2_exp, choice):
-    for log2_ph in (4, 8, 10, 13, 16, 18, 20, 22):
-        st = S.Stark(security, log2_exp, {0: None, 1: "fri", 2: "stir"}[choice])
+@pytest.mark.parametrize("soundness", ["proven", "conjectured"])
+def test_host_derivation_matches_oracle(security, log2_exp, choice, soundness):
+    for log2_ph in (4, 8, 10, 13, 16, 17, 18, 20, 22):
+        st = S.Stark(security, log2_exp, {0: None, 1: "fri", 2: "stir"}[choice], soundness)
         want = st.derive(1 << log2_ph)
-        got = tvm_b200.derive_domains(security, log2_exp, 1 << log2_ph, choice)
+        got = tvm_b200.derive_domains(security, log2_exp, 1 << log2_ph, choice, conjectured=soundness == "conjectured")
         for k in ("padded_height", "num_trace_randomizers", "randomized_trace_len", "trace_len", "quotient_len", "ldt_len",
                   "num_collinearity_checks", "num_quotient_randomizer_coefficients", "num_first_round_queries"):
             assert got[k] == want[k], (k, log2_ph, got[k], want[k])

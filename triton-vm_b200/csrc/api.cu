@@ -379,7 +379,7 @@ int tvm_air_quotient_dev(tvm_ctx *ctx, const uint64_t *d_main, size_t main_strid
 int tvm_derive_domains(const tvm_params *p, uint64_t padded_height, tvm_domains *out) {
   if (!p || !out) return TVM_ERR_INVALID_ARG;
   StarkDerived d{};
-  int rc = stark_derive(StarkParams{p->security_level, p->log2_ldt_expansion_factor, p->ldt_choice}, padded_height, d);
+  int rc = stark_derive(StarkParams{p->security_level, p->log2_ldt_expansion_factor, p->ldt_choice, p->soundness}, padded_height, d);
   if (rc) return rc;
   out->padded_height = d.padded_height; out->num_trace_randomizers = d.num_trace_randomizers;
   out->randomized_trace_len = d.randomized_trace_len; out->trace_len = d.trace_len; out->quotient_len = d.quotient_len;
@@ -405,7 +405,7 @@ int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, ui
   TVM_API_BEGIN(ctx)
   ClaimView cv{claim->program_digest, claim->version, claim->input, claim->num_input, claim->output, claim->num_output};
   std::vector<u64> proof;
-  stark_prove(*c__, StarkParams{params->security_level, params->log2_ldt_expansion_factor, params->ldt_choice}, cv, padded_height, (const u64 *)main_trace,
+  stark_prove(*c__, StarkParams{params->security_level, params->log2_ldt_expansion_factor, params->ldt_choice, params->soundness}, cv, padded_height, (const u64 *)main_trace,
               (const u64 *)main_rand, (AuxCallback)aux_cb, aux_user, (const u64 *)quot_rand, proof, &ctx->timings);
   size_t cap = *proof_len;
   *proof_len = proof.size();

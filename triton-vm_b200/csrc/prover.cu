@@ -37,10 +37,21 @@ static int ilog2(size_t x) {
 // All f64 expressions keep the reference's operation order (mod.rs:250-300, stir.rs:633-869).
 namespace {
 double rs_rate(unsigned log2_exp) { return 1.0 / (double)(1u << log2_exp); }
-double rs_margin(unsigned log2_exp) { return std::sqrt(rs_rate(log2_exp)); }
-double rs_slackness(unsigned log2_exp) { return rs_margin(log2_exp) / 20.0; }
-double rs_proximity_parameter(unsigned log2_exp) { return 1.0 - rs_margin(log2_exp) - rs_slackness(log2_exp); }
-double rs_log2_list_size(unsigned log2_exp) { return std::log2(1.0 / (2.0 * std::sqrt(rs_rate(log2_exp)) * rs_slackness(log2_exp))); }
+double rs_q_ary_entropy(unsigned log2_exp) {                         // mod.rs:258-264
+  const double rate = rs_rate(log2_exp);
+  const double rate_log_rate = rate * -(double)log2_exp;
+  const double one_m = (1.0 - rate) * std::log2(1.0 - rate);
+  return rate - (rate_log_rate + one_m) / 191.99999999899228;         // ReedSolomonCode::LOG2_FIELD_SIZE
+}
+// `conj`: ProximityRegime::Conjectured instead of ::Proven (mod.rs:60-80, 243-287)
+double rs_margin(unsigned log2_exp, bool conj) { return conj ? rs_q_ary_entropy(log2_exp) : std::sqrt(rs_rate(log2_exp)); }
+double rs_slackness(unsigned log2_exp, bool conj) { return rs_margin(log2_exp, conj) / 20.0; }
+double rs_proximity_parameter(unsigned log2_exp, bool conj) { return 1.0 - rs_margin(log2_exp, conj) - rs_slackness(log2_exp, conj); }
+double rs_log2_list_size(unsigned log2_exp, bool conj, unsigned log2_poly_degree) {
+  const double ls = conj ? std::pow(2.0, (double)log2_poly_degree) / (rs_q_ary_entropy(log2_exp) * rs_slackness(log2_exp, conj))
+                         : 1.0 / (2.0 * std::sqrt(rs_rate(log2_exp)) * rs_slackness(log2_exp, conj));
+  return std::log2(ls);
+}
 double log2_binomial_coefficient(unsigned long long a, unsigned long long b) {   // stir.rs:854-869 (Kahan-Babuska)
   double log2_binom = 0.0, compensation = 0.0;
   unsigned long long m = std::min(b, a - b);
@@ -53,8 +64,8 @@ double log2_binomial_coefficient(unsigned long long a, unsigned long long b) {  
   }
   return log2_binom;
 }
-size_t stir_num_in_domain_queries(unsigned security, unsigned log2_domain_size, unsigned log2_exp) {   // stir.rs:597-609
-  double nq = -(double)security / std::log2(1.0 - rs_proximity_parameter(log2_exp));
+size_t stir_num_in_domain_queries(unsigned security, unsigned log2_domain_size, unsigned log2_exp, bool conj) {   // stir.rs:597-609
+  double nq = -(double)security / std::log2(1.0 - rs_proximity_parameter(log2_exp, conj));
   unsigned long long uniques = (unsigned long long)std::ceil(nq);
   uniques = std::min(uniques, 1ULL << log2_domain_size);
   // num_total_in_domain_queries (stir.rs:758-776)
@@ -66,13 +77,13 @@ size_t stir_num_in_domain_queries(unsigned security, unsigned log2_domain_size, 
   double total = ((double)security + log2_k_minus_1 + log2_u_choose_l) / ((double)log2_domain_size - log2_k_minus_1);
   return (size_t)std::ceil(total);
 }
-size_t stir_num_ood_queries(unsigned security, unsigned log2_poly_degree, unsigned log2_exp) {          // stir.rs:831-842
-  double n = ((double)security - 1.0 + 2.0 * rs_log2_list_size(log2_exp)) / (double)(192u - log2_poly_degree);
+size_t stir_num_ood_queries(unsigned security, unsigned log2_poly_degree, unsigned log2_exp, bool conj) {          // stir.rs:831-842
+  double n = ((double)security - 1.0 + 2.0 * rs_log2_list_size(log2_exp, conj, log2_poly_degree)) / (double)(192u - log2_poly_degree);
   return (size_t)std::ceil(n);
 }
 }  // namespace
 
-int stir_derive(unsigned security, unsigned log2_ff, unsigned log2_initial_exp, unsigned log2_hdb, StirDerived &out) {
+int stir_derive(unsigned security, unsigned log2_ff, unsigned log2_initial_exp, unsigned log2_hdb, bool conj, StirDerived &out) {
   if (log2_ff < 2 || log2_initial_exp == 0 || log2_hdb < log2_ff || log2_hdb + log2_initial_exp > 32) return TVM_ERR_LDT_PARAMS;
   out = StirDerived{};
   out.folding_factor = (size_t)1 << log2_ff;
@@ -80,9 +91,9 @@ int stir_derive(unsigned security, unsigned log2_ff, unsigned log2_initial_exp, 
   unsigned log2_exp = log2_initial_exp;
   unsigned log2_folded_domain_size = log2_hdb + log2_initial_exp - log2_ff;
   while (folded_poly_degree > out.folding_factor) {
-    size_t in_domain = stir_num_in_domain_queries(security, log2_folded_domain_size, log2_exp);
+    size_t in_domain = stir_num_in_domain_queries(security, log2_folded_domain_size, log2_exp, conj);
     unsigned log2_next_exp = log2_exp + log2_ff - 1;
-    size_t ood = stir_num_ood_queries(security, (unsigned)ilog2(folded_poly_degree), log2_next_exp);
+    size_t ood = stir_num_ood_queries(security, (unsigned)ilog2(folded_poly_degree), log2_next_exp, conj);
     size_t next_deg = folded_poly_degree / out.folding_factor;
     if (in_domain + ood > next_deg) break;
     if (out.num_rounds >= STIR_MAX_ROUNDS) return TVM_ERR_LDT_PARAMS;
@@ -91,22 +102,21 @@ int stir_derive(unsigned security, unsigned log2_ff, unsigned log2_initial_exp, 
     log2_exp = log2_next_exp;
     log2_folded_domain_size -= 1;
   }
-  out.final_num_in_domain_queries = stir_num_in_domain_queries(security, log2_folded_domain_size, log2_exp);
+  out.final_num_in_domain_queries = stir_num_in_domain_queries(security, log2_folded_domain_size, log2_exp, conj);
   out.final_degree = folded_poly_degree;
   return TVM_OK;
 }
 
 int stark_derive(const StarkParams &sp, size_t padded_height, StarkDerived &d) {
-  if (sp.log2_expansion == 0 || sp.log2_expansion > 8 || sp.security_level == 0 || sp.ldt_choice > 2) return TVM_ERR_LDT_PARAMS;
+  if (sp.log2_expansion == 0 || sp.log2_expansion > 8 || sp.security_level == 0 || sp.ldt_choice > 2 || sp.soundness > 1) return TVM_ERR_LDT_PARAMS;
+  const bool conj = sp.soundness == 1;
   padded_height = next_pow2(padded_height ? padded_height : 1);
   if (padded_height > ((size_t)1 << 31)) return TVM_ERR_DOMAIN;
   const int log2_ph = ilog2(padded_height);
   d = StarkDerived{};
-  d.ldt = sp.ldt_choice ? (int)sp.ldt_choice : (log2_ph < 16 ? 1 : 2);      // stark.rs:1942-1951 (proven regime)
-  // low_degree_test/mod.rs:250-300 (ProximityRegime::Proven) and fri.rs:832-836
-  const double rate = 1.0 / (double)(1u << sp.log2_expansion);
-  const double margin = std::sqrt(rate);
-  const double proximity_parameter = 1.0 - margin - margin / 20.0;
+  d.ldt = sp.ldt_choice ? (int)sp.ldt_choice : (log2_ph < (conj ? 17 : 16) ? 1 : 2);      // stark.rs:1942-1951
+  // low_degree_test/mod.rs:243-256 and fri.rs:832-836
+  const double proximity_parameter = rs_proximity_parameter(sp.log2_expansion, conj);
   const size_t checks = (size_t)std::ceil(-(double)sp.security_level / std::log2(1.0 - proximity_parameter));
   const size_t expansion = (size_t)1 << sp.log2_expansion;
   size_t h = 0, nqr = 0, rtl = 0, ldt_len = 0;
@@ -117,7 +127,7 @@ int stark_derive(const StarkParams &sp, size_t padded_height, StarkDerived &d) {
     ldt_len = (size_t)1 << (hdb + sp.log2_expansion);
     size_t first_round = checks;
     if (d.ldt == 2) {
-      int rc = stir_derive(sp.security_level, STIR_LOG2_FOLDING_FACTOR, sp.log2_expansion, (unsigned)hdb, d.stir);
+      int rc = stir_derive(sp.security_level, STIR_LOG2_FOLDING_FACTOR, sp.log2_expansion, (unsigned)hdb, conj, d.stir);
       if (rc) return rc;
       first_round = d.stir.num_rounds ? d.stir.in_domain[0] : d.stir.final_num_in_domain_queries;   // stir.rs:878-883
     }

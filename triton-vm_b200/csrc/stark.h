@@ -13,6 +13,7 @@ struct StarkParams {          // stark.rs:113-145 (proven regime)
   unsigned security_level;
   unsigned log2_expansion;
   unsigned ldt_choice;        // 0 = heuristic (stark.rs:1942-1957), 1 = FRI, 2 = STIR
+  unsigned soundness;         // 0 = ProximityRegime::Proven (default), 1 = ::Conjectured
 };
 static constexpr int STIR_MAX_ROUNDS = 16;
 static constexpr unsigned STIR_LOG2_FOLDING_FACTOR = 2;      // stark.rs:2023
@@ -31,7 +32,7 @@ struct StarkDerived {
   StirDerived stir;
 };
 int stir_derive(unsigned security_level, unsigned log2_folding_factor, unsigned log2_initial_expansion, unsigned log2_high_degree_bound,
-                StirDerived &out);
+                bool conjectured, StirDerived &out);
 int stark_derive(const StarkParams &sp, size_t padded_height, StarkDerived &d);
 
 struct ClaimView {            // proof.rs:68-88, canonical words

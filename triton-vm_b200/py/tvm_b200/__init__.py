@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
 
 
 class Params(ctypes.Structure):
-    _fields_ = [("security_level", ctypes.c_uint32), ("log2_ldt_expansion_factor", ctypes.c_uint32), ("ldt_choice", ctypes.c_uint32)]
+    _fields_ = [("security_level", ctypes.c_uint32), ("log2_ldt_expansion_factor", ctypes.c_uint32), ("ldt_choice", ctypes.c_uint32),
+                ("soundness", ctypes.c_uint32)]
 
 
 class Domains(ctypes.Structure):
@@ -151,9 +152,9 @@ def hash_varlen(words):
     return [int(v) for v in d]
 
 
-def derive_domains(security_level=160, log2_expansion=2, padded_height=1 << 10, ldt_choice=LDT_FRI):
-    """Stark::{fri, max_degree, ...} + ProverDomains::derive; pure host function."""
-    p = Params(security_level, log2_expansion, ldt_choice)
+def derive_domains(security_level=160, log2_expansion=2, padded_height=1 << 10, ldt_choice=LDT_FRI, conjectured=False):
+    """Stark::{fri, stir, max_degree, ...} + ProverDomains::derive; pure host function."""
+    p = Params(security_level, log2_expansion, ldt_choice, int(conjectured))
     d = Domains()
     rc = lib().tvm_derive_domains(ctypes.byref(p), padded_height, ctypes.byref(d))
     if rc:
@@ -240,7 +241,7 @@ class Backend:
         return (root, nodes) if want_nodes else root
 
     def prove(self, claim, main_trace, main_rand, aux_provider, quot_rand, security_level=160, log2_expansion=2,
-              padded_height=None, ldt_choice=LDT_FRI):
+              padded_height=None, ldt_choice=LDT_FRI, conjectured=False):
         """Stark::prove; `ldt_choice` LDT_FRI / LDT_STIR / LDT_AUTO (the reference's heuristic).  claim = (program_digest[5], input, output[, version]);
         main_trace [379, n], main_rand [379, h] canonical uint64; aux_provider(challenges [63,3]) ->
         (aux_trace [91, n, 3], aux_rand [91, h, 3]); quot_rand [(h+1)*5, 3].  Returns the proof words.
@@ -251,7 +252,7 @@ class Backend:
         qr, qrp = _np_u64(quot_rand)
         n = mt_shape[1]
         ph = padded_height or n
-        dom = derive_domains(security_level, log2_expansion, ph, ldt_choice)
+        dom = derive_domains(security_level, log2_expansion, ph, ldt_choice, conjectured)
         h = dom["num_trace_randomizers"]
         assert mt_shape == (379, dom["trace_len"]) and mr_shape == (379, h), (mt_shape, mr_shape, dom)
         assert qr.size == 3 * dom["num_quotient_randomizer_coefficients"]
@@ -279,7 +280,7 @@ class Backend:
                 err.append(e)
                 return 1
 
-        p = Params(security_level, log2_expansion, ldt_choice)
+        p = Params(security_level, log2_expansion, ldt_choice, int(conjectured))
         cap = ctypes.c_size_t(0)
         nfq = dom["num_first_round_queries"]
         est = 64 + nfq * (379 + 273 + 15 + 3 * 40 * (dom["fri_num_rounds"] + 4)) + \
