@@ -44,6 +44,16 @@ def measured_peaks():
         return None
 
 
+def measured_lde_traffic(alg_bytes):
+    """DRAM bytes (read + write) of the LDE kernels from the committed ncu capture, scaled to this workload:
+    profiles/r01d_ntt_traffic.json holds dram bytes per algorithmic byte of one 16-column LDE batch at 2^20."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01d_ntt_traffic.json")))
+        return float(t["dram_bytes_per_algorithmic_byte"]) * alg_bytes, t.get("source")
+    except Exception:
+        return None, None
+
+
 def algorithmic_lde_bytes(n, ncols):
     # SURVEY.md §8(d): column LDE reads 8 B per trace element and writes 64 B (8x blow-up): 72 B per trace element
     return 72 * n * ncols
@@ -239,6 +249,7 @@ def run_gpu(args):
     peak = (peaks["hbm_gbs"] if peaks else 6650.0) * world   # aggregate over the GPUs sharing the proof
     alg = algorithmic_lde_bytes(n, NM + 3 * NA)
     achieved = alg / (lde_ms * 1e-3) / 1e9 if lde_ms else 0.0
+    traffic, traffic_src = measured_lde_traffic(alg)
     out = {
         "metric": "prove() ms @ padded height 2^%d; NTT GF(p) elems/s vs HBM roofline" % args.log2_height,
         "value": device_ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -264,7 +275,7 @@ def run_gpu(args):
         "e2e_stages_ms": {k: round(v, 3) for k, v in e2e_stages.items()},
         "roofline": {"bound": "hbm", "kernel": "coset LDE (ntt_pass_a/ntt_pass_b) of the 652 table columns",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                     "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                      "algorithmic_bytes": alg,
                      "ntt_gelems_per_s": (NM + 3 * NA) * 8 * n / (lde_ms * 1e-3) / 1e9 if lde_ms else None},
         "clocks": clocks,

@@ -230,6 +230,57 @@ __device__ __forceinline__ void quad_mds_rc(u64 (&s)[4], int l, int group_base, 
     s[i] = fadd(reduce96(lsum, h), rc_smem[16 * rnd + l + 4 * i]);
   }
 }
+// Same MDS step with the 16 inputs exchanged through shared memory instead of 32 shuffles + 32 selects (cost model:
+// SHFL 4 clocks, SEL 2; LDS.64 ~2): the quad writes its state to a 20-word-strided slot (bank-conflict free: word index
+// 20*s + e covers all 16 residues mod 16 for 4 consecutive quads, two wavefronts per 64-bit warp access) and every
+// lane reads x_{(k+l) mod 16}.
+static constexpr int XCH_STRIDE = 20;
+__device__ __forceinline__ void quad_mds_rc_smem(u64 (&s)[4], int l, u64 *slot, const u64 *rc_smem, int rnd) {
+  constexpr unsigned short MDS[16] = TVM_MDS_COL;
+  __syncwarp();                                   // previous readers of this slot are done
+#pragma unroll
+  for (int i = 0; i < 4; i++) slot[l + 4 * i] = s[i];
+  __syncwarp();
+  u64 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const u64 X = slot[(k + l) & 15];
+    const u64 xl = X & 0xFFFFFFFFULL, xh = X >> 32;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const u64 m = MDS[(4 * i - k) & 15];
+      lo[i] += m * xl;
+      hi[i] += m * xh;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    u64 lsum = lo[i] + (hi[i] << 32);
+    u64 carry = lsum < lo[i];
+    u64 h = (hi[i] >> 32) + carry;
+    s[i] = fadd(reduce96(lsum, h), rc_smem[16 * rnd + l + 4 * i]);
+  }
+}
+template <bool SMEM>
+__device__ __forceinline__ void quad_mds_sel(u64 (&s)[4], int l, int group_base, u64 *slot, const u64 *rc_smem, int rnd) {
+  if (SMEM) quad_mds_rc_smem(s, l, slot, rc_smem, rnd);
+  else quad_mds_rc(s, l, group_base, rc_smem, rnd);
+}
+template <bool SMEM>
+__device__ __forceinline__ void tip5_perm_quad2x(u64 (&a)[4], u64 (&b)[4], int l, int group_base, const unsigned char *lut,
+                                                 const u64 *rc_smem, u64 *slot_a, u64 *slot_b) {
+  quad_sbox(a, lut);
+#pragma unroll 1
+  for (int rnd = 0; rnd < TIP5_ROUNDS - 1; rnd++) {
+    quad_mds_sel<SMEM>(a, l, group_base, slot_a, rc_smem, rnd);
+    quad_sbox(b, lut);
+    quad_mds_sel<SMEM>(b, l, group_base, slot_b, rc_smem, rnd);
+    quad_sbox(a, lut);
+  }
+  quad_mds_sel<SMEM>(a, l, group_base, slot_a, rc_smem, TIP5_ROUNDS - 1);
+  quad_sbox(b, lut);
+  quad_mds_sel<SMEM>(b, l, group_base, slot_b, rc_smem, TIP5_ROUNDS - 1);
+}
 __device__ __forceinline__ void tip5_perm_quad2(u64 (&a)[4], u64 (&b)[4], int l, int group_base, const unsigned char *lut,
                                                 const u64 *rc_smem) {
   quad_sbox(a, lut);
@@ -246,9 +297,13 @@ __device__ __forceinline__ void tip5_perm_quad2(u64 (&a)[4], u64 (&b)[4], int l,
 }
 
 static constexpr int HASHQ2_THREADS = 128;   // 32 quads, 64 rows per CTA
+template <bool SMEM>
 __global__ void __launch_bounds__(HASHQ2_THREADS) tip5_hash_rows_quad2_kernel(HashRowsParams p) {
   __shared__ unsigned char lut[256];
   __shared__ u64 rc[80];
+  __shared__ u64 xch[SMEM ? 2 * (HASHQ2_THREADS / 4) * XCH_STRIDE : 1];
+  u64 *slot_a = xch + (SMEM ? (threadIdx.x >> 2) * XCH_STRIDE : 0);
+  u64 *slot_b = xch + (SMEM ? ((HASHQ2_THREADS / 4) + (threadIdx.x >> 2)) * XCH_STRIDE : 0);
   for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
   for (int i = threadIdx.x; i < 80; i += blockDim.x) rc[i] = c_tip5_rc[i];
   __syncthreads();
@@ -276,7 +331,7 @@ __global__ void __launch_bounds__(HASHQ2_THREADS) tip5_hash_rows_quad2_kernel(Ha
       a[2] = base[0][(size_t)(c + l + 8) * p.col_stride];
       b[2] = base[1][(size_t)(c + l + 8) * p.col_stride];
     }
-    tip5_perm_quad2(a, b, l, group_base, lut, rc);
+    tip5_perm_quad2x<SMEM>(a, b, l, group_base, lut, rc, slot_a, slot_b);
   }
   unsigned rem = p.ncols - c;
 #pragma unroll
@@ -289,7 +344,7 @@ __global__ void __launch_bounds__(HASHQ2_THREADS) tip5_hash_rows_quad2_kernel(Ha
       a[i] = va; b[i] = vb;
     }
   }
-  tip5_perm_quad2(a, b, l, group_base, lut, rc);
+  tip5_perm_quad2x<SMEM>(a, b, l, group_base, lut, rc, slot_a, slot_b);
   const size_t per = p.nrows >> p.log_r;
 #pragma unroll
   for (int t = 0; t < 2; t++) {
@@ -465,7 +520,8 @@ void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, un
   } else {
     const size_t rows_per_cta = HASHQ2_THREADS / 2;
     unsigned grid = (unsigned)((nrows + rows_per_cta - 1) / rows_per_cta);
-    tip5_hash_rows_quad2_kernel<<<grid, HASHQ2_THREADS, 0, c.stream>>>(p);
+    if (getenv("TVM_TIP5_SHUFFLE")) tip5_hash_rows_quad2_kernel<false><<<grid, HASHQ2_THREADS, 0, c.stream>>>(p);
+    else tip5_hash_rows_quad2_kernel<true><<<grid, HASHQ2_THREADS, 0, c.stream>>>(p);
   }
   c.launches++;
   TVM_CUDA(cudaGetLastError());
