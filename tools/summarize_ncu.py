@@ -138,5 +138,43 @@ def table(src, dst):
                     f"{a['issue']/t:.0f} | {a['alu']/t:.0f} | {a['fma']/t:.0f} | {a['occ']/t:.0f} | {a['regs']} |\n")
 
 
+def table_long(src, dst):
+    """like `table`, from the long-format CSV that `ncu --metrics ... --csv --log-file` writes (one row per launch and metric)"""
+    with open(src, newline="") as f:
+        lines = [l for l in f if l.startswith('"')]
+    per = OrderedDict()
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        d = per.setdefault(r["ID"], {"name": short(r["Kernel Name"])})
+        try:
+            v = float(r["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        unit = r["Metric Unit"]
+        v *= {"us": 1e3, "ms": 1e6, "s": 1e9, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        d[r["Metric Name"]] = v
+    agg = OrderedDict()
+    for d in per.values():
+        name = "air_chunk_* (generated AIR kernels)" if d["name"].startswith("air_chunk_") else d["name"]
+        a = agg.setdefault(name, dict(n=0, ns=0.0, by=0.0, issue=0.0, alu=0.0, fma=0.0, occ=0.0, regs=0))
+        t = d.get("gpu__time_duration.sum", 0.0)
+        a["n"] += 1; a["ns"] += t
+        a["by"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+        a["issue"] += t * d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0.0)
+        a["alu"] += t * d.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", 0.0)
+        a["fma"] += t * d.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", 0.0)
+        a["occ"] += t * d.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0.0)
+        a["regs"] = max(a["regs"], int(d.get("launch__registers_per_thread", 0)))
+    total = sum(a["ns"] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# every kernel of one prove()\n\nsource: `{src}` ({len(per)} launches; ncu's serialised cold-cache per-launch durations; "
+                "pipe / issue figures are time-weighted means over the launches of a kernel)\n\n")
+        f.write("| kernel | launches | ms | share | DRAM GB/s (rd+wr) | issue % | ALU pipe % | FMA pipe % | warps active % | regs |\n"
+                "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ns"]):
+            t = a["ns"] or 1.0
+            f.write(f"| `{k}` | {a['n']} | {a['ns']/1e6:.3f} | {100*a['ns']/total:.1f}% | {a['by']/t:.0f} | "
+                    f"{a['issue']/t:.0f} | {a['alu']/t:.0f} | {a['fma']/t:.0f} | {a['occ']/t:.0f} | {a['regs']} |\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report, "table": table}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "report": report, "table": table, "table_long": table_long}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -35,6 +35,11 @@ CHUNK_COST_BUDGET = float(os.environ.get("TVM_AIR_BUDGET", "100"))
 SYNC_EVERY = int(os.environ.get("TVM_AIR_SYNC_EVERY", "0"))
 NUM_TUS = int(os.environ.get("TVM_AIR_TUS", "8"))
 MIN_BLOCKS = int(os.environ.get("TVM_AIR_MIN_BLOCKS", "1"))
+# measured at 2^20: splitting the few oversized constraints (up to 1079 operations in one kernel) raises the emitted
+# operations by 8-29 % (shared sub-expressions are recomputed per piece) and does not pay: 168.6 ms unsplit,
+# 171.6 ms with 400-cost pieces, 240.7 ms with 250-cost pieces.  Off by default.
+SPLIT_BIG = os.environ.get("TVM_AIR_SPLIT", "0") != "0"
+SPLIT_BUDGET = float(os.environ.get("TVM_AIR_SPLIT_BUDGET", "250"))   # pieces of an oversized constraint may be this large
 WTAB_WORDS = 7   # per weight: b0, b1, b2, -b1, -b2, b0+b2, b1-b2
 
 
@@ -53,27 +58,90 @@ def node_cost(b, n):
     return 1.0 if (lx and rx) else 0.35
 
 
+# ---- splitting a constraint that is larger than a chunk ------------------------------------------------
+# The weighted sum  sum_j w_j c_j  is linear in every c_j, so a constraint may be evaluated as a sum of pieces in
+# different kernels (same weight): a top-level sum is cut into groups of terms, and a product `big * small` is
+# distributed over the pieces of `big` (small is re-evaluated per piece).  Exact field arithmetic: same value.
+# A piece is ("node", n) | ("sum", [pieces]) | ("mul", piece, n).
+def subtree_cost(b, n, memo):
+    k = id(n)
+    if k not in memo:
+        memo[k] = sum(node_cost(b, x) for x in reachable_postorder([n]) if x.kind in "+*")
+    return memo[k]
+
+
+def flatten_sum(n):
+    out, st = [], [n]
+    while st:
+        x = st.pop()
+        if x.kind == "+":
+            st.append(x.rhs); st.append(x.lhs)
+        else:
+            out.append(x)
+    return out
+
+
+def piece_leaves(piece):
+    if piece[0] == "node": return [piece[1]]
+    if piece[0] == "sum": return [n for p in piece[1] for n in piece_leaves(p)]
+    return piece_leaves(piece[1]) + [piece[2]]
+
+
+def piece_cost(b, piece):
+    return sum(node_cost(b, x) for x in reachable_postorder(piece_leaves(piece)) if x.kind in "+*")
+
+
+def split_piece(b, n, budget, memo):
+    """-> list of pieces whose sum equals node n, each (roughly) within the budget where the shape allows"""
+    if subtree_cost(b, n, memo) <= budget or n.kind not in "+*":
+        return [("node", n)]
+    if n.kind == "+":
+        parts = []
+        for t in flatten_sum(n):
+            parts += split_piece(b, t, budget, memo)
+        groups, cur, cur_cost = [], [], 0.0
+        for p in parts:
+            pc = piece_cost(b, p)
+            if cur and cur_cost + pc > budget:
+                groups.append(cur); cur, cur_cost = [], 0.0
+            cur.append(p); cur_cost += pc
+        if cur: groups.append(cur)
+        return [g[0] if len(g) == 1 else ("sum", g) for g in groups]
+    # product: distribute over the pieces of the expensive factor when the other one is cheap
+    cl, cr = subtree_cost(b, n.lhs, memo), subtree_cost(b, n.rhs, memo)
+    big, small, cs_ = (n.lhs, n.rhs, cr) if cl >= cr else (n.rhs, n.lhs, cl)
+    if cs_ <= budget / 4:
+        sub = split_piece(b, big, budget - cs_, memo)
+        if len(sub) > 1:
+            return [("mul", p, small) for p in sub]
+    return [("node", n)]
+
+
 def chunk_constraints(air, budget=None):
-    """-> list of (category, [(global_weight_index, node)]).  Chunks are contiguous ranges of the
-    evaluator-order constraint list; the budget is in units of B-field multiplications because
-    ptxas time grows super-linearly with the size of the basic block."""
+    """-> list of (category, [(global_weight_index, piece)]).  Chunks are runs of the evaluator-order constraint
+    list; the budget is in units of B-field multiplications (~18 SASS instructions each): a chunk should stay
+    resident in the 32 KB L1.5 instruction cache.  A constraint above the budget is split into pieces."""
     budget = budget or CHUNK_COST_BUDGET
     chunks, offset = [], 0
     for cat in CATEGORIES:
         b = air.builders[cat]
         cs = air.constraints[cat]
+        memo = {}
         cur, seen, cost = [], set(), 0.0
         for j, c in enumerate(cs):
-            new = [x for x in reachable_postorder([c]) if id(x) not in seen and x.kind in "+*"]
-            new_cost = sum(node_cost(b, x) for x in new) + 6.0
-            if cur and cost + new_cost > budget:
-                chunks.append((cat, cur))
-                cur, seen, cost = [], set(), 0.0
-                new = [x for x in reachable_postorder([c]) if x.kind in "+*"]
+            pieces = split_piece(b, c, max(budget, SPLIT_BUDGET), memo) if SPLIT_BIG else [("node", c)]
+            for piece in pieces:
+                leaves = piece_leaves(piece)
+                new = [x for x in reachable_postorder(leaves) if id(x) not in seen and x.kind in "+*"]
                 new_cost = sum(node_cost(b, x) for x in new) + 6.0
-            cur.append((offset + j, c))
-            seen.update(id(x) for x in new)
-            cost += new_cost
+                if cur and cost + new_cost > budget:
+                    chunks.append((cat, cur))
+                    cur, seen, cost = [], set(), 0.0
+                    new = [x for x in reachable_postorder(leaves) if x.kind in "+*"]
+                    new_cost = sum(node_cost(b, x) for x in new) + 6.0
+                cur.append((offset + j, piece))
+                seen.update(id(x) for x in new)
+                cost += new_cost
         if cur:
             chunks.append((cat, cur))
         offset += len(cs)
@@ -94,6 +162,37 @@ class Emitter:
 
     def is_neg_one(self, n):
         return n.kind == "B" and n.val == P - 1
+
+    def binop(self, kind, l, r):
+        """emit `l kind r` for already emitted operands (name, is_x, is_neg_one) -> (name, is_x)"""
+        (ln, lx), (rn, rx) = l, r
+        v = self.tmp()
+        if kind == "*":
+            if lx and rx: expr, resx = f"xmul({ln}, {rn})", True
+            elif lx: expr, resx = f"xmulb({ln}, {rn})", True
+            elif rx: expr, resx = f"xmulb({rn}, {ln})", True
+            else: expr, resx = f"fmul({ln}, {rn})", False
+        else:
+            if lx and rx: expr, resx = f"xadd({ln}, {rn})", True
+            elif lx: expr, resx = f"xaddb({ln}, {rn})", True
+            elif rx: expr, resx = f"xaddb({rn}, {ln})", True
+            else: expr, resx = f"fadd({ln}, {rn})", False
+        self.lines.append(f"const {'xfe' if resx else 'u64'} {v} = {expr};")
+        return v, resx
+
+    def emit_piece(self, piece):
+        """pieces of a split constraint (see split_piece); leaves are already emitted"""
+        if piece[0] == "node":
+            n = piece[1]
+            return self.name[id(n)], self.isx[id(n)]
+        if piece[0] == "sum":
+            acc = self.emit_piece(piece[1][0])
+            for p in piece[1][1:]:
+                acc = self.binop("+", acc, self.emit_piece(p))
+            return acc
+        inner = self.emit_piece(piece[1])
+        n = piece[2]
+        return self.binop("*", inner, (self.name[id(n)], self.isx[id(n)]))
 
     def emit_node(self, n):
         k = n.kind
@@ -185,9 +284,10 @@ void %(tuname)s_launch(const AirArgs &a, const u64 *d_wtab, const u64 *d_challen
 def emit_chunk(air, idx, cat, items):
     b = air.builders[cat]
     em = Emitter(b)
-    roots = [c for _, c in items]
+    roots = [n for _, piece in items for n in piece_leaves(piece)]
     for n in reachable_postorder(roots):
         em.emit_node(n)
+    results = [em.emit_piece(piece) for _, piece in items]
     kname = f"air_chunk_{idx:03d}_{cat}"
     if SYNC_EVERY:
         guard = "  const bool active = m < a.nrows;\n  if (!active) m = 0;   // keep every thread alive for the block-wide barriers below"
@@ -201,9 +301,8 @@ def emit_chunk(air, idx, cat, items):
             body.append("__syncthreads();   // instruction-fetch locality: the CTA's warps share one I-cache window")
     src.append("  " + "\n  ".join(body))
     src.append("  AirAcc acc; air_acc_zero(acc);")
-    for j, c in items:
-        nm = em.name[id(c)]
-        if em.isx[id(c)]:
+    for (j, _), (nm, isx) in zip(items, results):
+        if isx:
             src.append(f"  air_acc_x(acc, c_w + {WTAB_WORDS * j}, {nm});")
         else:
             src.append(f"  air_acc_b(acc, c_w + {WTAB_WORDS * j}, {nm});")
