@@ -67,6 +67,15 @@ def cpu_baseline(log2_height, budget_note=True):
     rng = np.random.default_rng(7)
     n = 1 << log2_height
     N = 8 * n
+    # one OpenMP thread per physical core: on the hyper-threaded hosts of this pool 2 threads per core made the
+    # memory-bound NTT sample 5x slower (988 s vs 189 s extrapolated), which would flatter the GPU arm
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or 0
+    except Exception:
+        phys = 0
+    if phys and phys < corc.num_threads():
+        corc.set_num_threads(phys)
     cores = corc.num_threads()
     stages = {}
     # LDE: K full-size columns (iNTT n + NTT 8n each), OpenMP over columns like rayon

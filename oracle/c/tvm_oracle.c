@@ -28,6 +28,13 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 /* Montgomery reduction x*R^-1 mod p, x < p*2^64 (Pornin's formulation for this prime). */
 static inline u64 montyred(u128 x) {

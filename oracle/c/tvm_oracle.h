@@ -55,6 +55,7 @@ void orc_hash_rows_colmajor(const u64 *table, size_t nrows, size_t ncols, size_t
 void orc_merkle_build(const u64 *leaves, size_t nleaves, u64 *nodes);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* OpenMP team size of the parallel loops (no-op without OpenMP) */
 #ifdef __cplusplus
 }
 #endif

@@ -124,6 +124,10 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
+
+
 def _xarr(xs):
     """list of X-field tuples / [k,3] array -> Montgomery uint64 [k,3]"""
     return to_mont(np.array(xs, dtype=np.uint64).reshape(-1, 3)).reshape(-1, 3)

@@ -108,3 +108,44 @@ def test_low_memory_mode_produces_the_same_proof(backend, ldt):
     finally:
         backend.set_low_memory(0)
     assert np.array_equal(cached, jit)
+
+
+@pytest.mark.parametrize("ldt,padded_height", [("fri", 4), ("stir", 256)])
+def test_default_security_on_small_instances(backend, ldt, padded_height):
+    """Stark::default() parameters (security 160) on tiny padded heights: the trace domain is bumped by the number of
+    trace randomizers (stark.rs:1885-1890); with STIR there is no full round at this size (final round only, 284
+    queries).  Empty public input / output."""
+    import tvm_b200
+    st = S.Stark(160, 2, ldt)
+    d = st.derive(padded_height)
+    rng = np.random.default_rng(77 + padded_height)
+    n, h = d["trace_len"], d["num_trace_randomizers"]
+    assert n >= 512
+    main, mrand = rand_bfes(rng, (379, n)), rand_bfes(rng, (379, h))
+    qrand = rand_bfes(rng, (d["num_quotient_randomizer_coefficients"], 3))
+    aux_t, aux_r = rand_bfes(rng, (91, n, 3)), rand_bfes(rng, (91, h, 3))
+    claim = S.Claim([5, 4, 3, 2, 1], [], [])
+    want, _ = S.prove(st, claim, main, mrand, lambda ch: (aux_t, aux_r), qrand, padded_height=padded_height)
+    got = backend.prove((claim.program_digest, claim.input, claim.output), main, mrand, lambda ch: (aux_t, aux_r), qrand,
+                        security_level=160, log2_expansion=2, padded_height=padded_height,
+                        ldt_choice=tvm_b200.LDT_STIR if ldt == "stir" else tvm_b200.LDT_FRI)
+    assert [int(v) for v in got] == want
+    assert S.verify(st, claim, want, check_air=False)
+
+
+def test_prove_reports_errors_instead_of_falling_back(backend):
+    import tvm_b200
+    st, d, claim, main, mrand, aux_provider, qrand = synthetic_instance(4, 2, 16, 9)
+    args = ((claim.program_digest, claim.input, claim.output), main, mrand)
+    with pytest.raises(RuntimeError, match="boom"):          # an exception inside the aux callback surfaces to the caller
+        backend.prove(*args, lambda ch: (_ for _ in ()).throw(RuntimeError("boom")), qrand, security_level=4, log2_expansion=2,
+                      padded_height=16)
+    # unsupported expansion factor (LDT domain != 8 x trace domain): explicit error, no fallback
+    d3 = S.Stark(4, 3).derive(16)
+    n3, h3 = d3["trace_len"], d3["num_trace_randomizers"]
+    rng = np.random.default_rng(3)
+    with pytest.raises(tvm_b200.TvmError) as e:
+        backend.prove((claim.program_digest, claim.input, claim.output), rand_bfes(rng, (379, n3)), rand_bfes(rng, (379, h3)),
+                      lambda ch: (rand_bfes(rng, (91, n3, 3)), rand_bfes(rng, (91, h3, 3))),
+                      rand_bfes(rng, (d3["num_quotient_randomizer_coefficients"], 3)), security_level=4, log2_expansion=3, padded_height=16)
+    assert e.value.code == -8
