@@ -378,7 +378,9 @@ def prove(stark, claim, main_trace, main_rand, aux_provider, quot_rand, padded_h
     n = main_trace.shape[1]
     d = stark.derive(padded_height or n)
     assert d["trace_len"] == n, (d["trace_len"], n)
-    assert d["quotient_len"] == d["ldt_len"], "this oracle covers quotient domain == LDT domain (the default parameters)"
+    # the tables are extended over max(quotient, LDT) domain (master_table.rs:258-322); this oracle covers LDT >= quotient,
+    # i.e. expansion factors >= 4; the AIR then sees every (N/Q)-th row (quotient_domain_table, master_table.rs:769-779)
+    assert d["ldt_len"] % d["quotient_len"] == 0, "expansion factor 2 (quotient domain larger than LDT domain) is not covered"
     h, N, off = d["num_trace_randomizers"], d["ldt_len"], d["ldt_offset"]
     log2N = N.bit_length() - 1
     art = {"derived": d}
@@ -408,7 +410,9 @@ def prove(stark, claim, main_trace, main_rand, aux_provider, quot_rand, padded_h
     w0 = ps.sample_scalars(1)[0]
     num_constraints = sum(len(v) for v in constraint_degrees().values())
     quot_weights = xpows(w0, num_constraints)
-    quotient_codeword = corc.air_quotient(main_lde, aux_lde[:270], n.bit_length() - 1, off, challenges, quot_weights)  # [N,3]
+    qs = N // d["quotient_len"]
+    quotient_codeword = corc.air_quotient(np.ascontiguousarray(main_lde[:, ::qs]), np.ascontiguousarray(aux_lde[:270, ::qs]),
+                                          n.bit_length() - 1, off, challenges, quot_weights)                 # [Q,3]
     quotient_poly = xcoset_interpolate(quotient_codeword, off)                       # stark.rs:1224-1231
     seg_polys = [quotient_poly[s::NUM_QUOTIENT_SEGMENTS] for s in range(NUM_QUOTIENT_SEGMENTS)]   # 1252-1263
     quot_rand = np.ascontiguousarray(quot_rand, dtype=np.uint64).reshape(-1, 3)

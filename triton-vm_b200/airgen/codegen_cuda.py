@@ -263,9 +263,10 @@ __global__ void __launch_bounds__(AIR_THREADS, %(minb)d) %(kname)s(AirArgs a) {
 %(guard)s
   const size_t n = (size_t)1 << a.log_n;
   const size_t coset = m >> a.log_n, k = m & (n - 1);
-  const size_t m_next = (coset << a.log_n) | ((k + 1) & (n - 1));
-  const u64 *mc = a.main + m, *mn = a.main + m_next;
-  const u64 *ac = a.aux + m, *an = a.aux + m_next;
+  const size_t mem_base = (coset * a.coset_mem_stride) << a.log_n;
+  const size_t m_cur = mem_base | k, m_next = mem_base | ((k + 1) & (n - 1));
+  const u64 *mc = a.main + m_cur, *mn = a.main + m_next;
+  const u64 *ac = a.aux + m_cur, *an = a.aux + m_next;
   (void)mn; (void)an; (void)ac; (void)mc; (void)coset;
 """
 

@@ -24,8 +24,10 @@ struct AirArgs {
   size_t aux_stride;
   u64 *out;             // quotient codeword, planar: coordinate d at out + d*out_stride, memory order
   size_t out_stride;
-  size_t nrows;         // r * n
+  size_t nrows;         // (#cosets evaluated) * n
   int log_n;            // trace length n = 2^log_n
+  unsigned coset_mem_stride;   // evaluated coset y sits at table coset y * coset_mem_stride (quotient domain = every
+                               // (N/Q)-th coset of the LDT-domain tables when the expansion factor exceeds 4)
   // per-row zerofier inverses in memory order (air_zerofier_kernel):
   const u64 *zi_init;   // 1 / (x - 1)                         (master_table.rs:1194-1202)
   const u64 *zi_tran;   // (x - w_n^-1) / (x^n - 1)            (1216-1237)

@@ -371,7 +371,7 @@ int tvm_air_quotient_dev(tvm_ctx *ctx, const uint64_t *d_main, size_t main_strid
   u64 *d = (u64 *)c__->scratch_get(3, (nc + nw) * 8);
   TVM_CUDA(cudaMemcpyAsync(d, h.data(), (nc + nw) * 8, cudaMemcpyHostToDevice, c__->stream));
   TVM_CUDA(cudaStreamSynchronize(c__->stream));  // h is a stack-owned staging buffer
-  air_quotient_run(*c__, (const u64 *)d_main, main_stride, (const u64 *)d_aux, aux_stride, d, d + nc, log2_trace, log2_cosets, 0, 1, 1u << log2_cosets,
+  air_quotient_run(*c__, (const u64 *)d_main, main_stride, (const u64 *)d_aux, aux_stride, d, d + nc, log2_trace, log2_cosets, 0, 1, 1u << log2_cosets, 1,
                    to_mont(offset_canon), (u64 *)d_out, out_stride);
   TVM_API_END
 }

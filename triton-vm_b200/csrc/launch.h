@@ -46,11 +46,11 @@ void merkle_run_sharded(Ctx &c, u64 *nodes, size_t nleaves, unsigned rank, unsig
 void xfe_leaves_run(Ctx &c, const u64 *cw, size_t stride, size_t n, u64 *leaves);
 void to_mont_run(Ctx &c, u64 *d, size_t n);
 void from_mont_run(Ctx &c, u64 *d, size_t n);
-// evaluates on `num_cosets` of the 2^log_r cosets (domain coset coset_first + coset_step*y); tables and
-// output hold only those cosets ([col][y][k])
+// evaluates on `num_cosets` of the 2^log_r cosets (domain coset coset_first + coset_step*y); the output holds only those
+// cosets ([y][k]); the tables hold coset y at memory coset y*coset_mem_stride ([col][..][k])
 void air_quotient_run(Ctx &c, const u64 *d_main, size_t main_stride, const u64 *d_aux, size_t aux_stride,
                       const u64 *d_challenges, const u64 *d_weights, unsigned log_n, unsigned log_r,
-                      unsigned coset_first, unsigned coset_step, unsigned num_cosets,
+                      unsigned coset_first, unsigned coset_step, unsigned num_cosets, unsigned coset_mem_stride,
                       u64 offset_mont, u64 *d_out, size_t out_stride);
 int translate_exception(Ctx *c);
 

@@ -198,10 +198,15 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   StarkDerived d{};
   int rc = stark_derive(sp, padded_height, d);
   if (rc) throw ApiError{rc, "parameter derivation failed"};
-  if (d.quotient_len != d.ldt_len) throw ApiError{TVM_ERR_UNSUPPORTED, "quotient domain != LDT domain is not supported yet"};
-  const size_t n = d.trace_len, N = d.ldt_len, h = d.num_trace_randomizers;
-  const unsigned log_n = (unsigned)ilog2(n), log_N = (unsigned)ilog2(N), log_r = log_N - log_n;
-  if (N != 8 * n) throw ApiError{TVM_ERR_UNSUPPORTED, "only LDT domain = 8 x trace domain (expansion factor 4) is supported yet"};
+  const size_t n = d.trace_len, N = d.ldt_len, Q = d.quotient_len, h = d.num_trace_randomizers;
+  const unsigned log_n = (unsigned)ilog2(n), log_N = (unsigned)ilog2(N), log_r = log_N - log_n, log_Q = (unsigned)ilog2(Q);
+  // The tables live on the LDT domain (r = 2 * expansion cosets of the trace domain); the quotient domain (always 8
+  // cosets: AIR degree 4 on the randomized trace) is every (N/Q)-th coset of it (master_table.rs:769-779).
+  if (Q != 8 * n) throw ApiError{TVM_ERR_UNSUPPORTED, "quotient domain != 8 x trace domain"};
+  if (N < Q) throw ApiError{TVM_ERR_UNSUPPORTED, "expansion factor 2 (quotient domain larger than the LDT domain) is not supported"};
+  if (log_r > 6) throw ApiError{TVM_ERR_UNSUPPORTED, "expansion factors above 32 are not supported"};
+  const unsigned qs = (unsigned)(N / Q);                // LDT cosets per quotient coset
+  if (qs != 1 && c.comm.world > 1) throw ApiError{TVM_ERR_UNSUPPORTED, "multi-GPU sharding needs expansion factor 4"};
   const u64 off = to_mont(d.ldt_offset);
   const size_t NM = TVM_NUM_MAIN_COLUMNS, NA = TVM_NUM_AUX_COLUMNS, NA3 = 3 * NA;
   const size_t tmp_cols = 16;
@@ -385,34 +390,37 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   u64 *d_consts = mem.words(consts.size());
   TVM_CUDA(cudaMemcpyAsync(d_consts, consts.data(), consts.size() * 8, cudaMemcpyHostToDevice, c.stream));
   TVM_CUDA(cudaStreamSynchronize(c.stream));
-  u64 *d_quot = mem.words(3 * N);   // gather buffer [rank][3][NL]; this rank's rows go to its own block
+  const size_t QL = Q / W;          // quotient-domain rows of this rank
+  u64 *d_quot = mem.words(3 * Q);   // gather buffer [rank][3][QL]; this rank's rows go to its own block
   if (jit) {
     u64 *d_mc = mem.words(NM * n), *d_ac = mem.words(NA3 * n);
     for (unsigned y = 0; y < sh.count; y++) {
+      const unsigned coset = sh.first + sh.step * y;
+      if (coset % qs) continue;                          // not a quotient-domain coset
       evaluate_coset(d_main_coef, (unsigned)NM, y, d_mc);
       evaluate_coset(d_aux_coef, (unsigned)NA3, y, d_ac);
-      air_quotient_run(c, d_mc, n, d_ac, n, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, sh.first + sh.step * y, sh.step, 1,
-                       off, d_quot + (size_t)rank * 3 * NL + (size_t)y * n, NL);
+      air_quotient_run(c, d_mc, n, d_ac, n, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, coset, sh.step, 1, 1,
+                       off, d_quot + (size_t)rank * 3 * QL + (size_t)(y / qs) * n, QL);
     }
     mem.release(d_mc); mem.release(d_ac);
   } else {
-    air_quotient_run(c, d_main_lde, NL, d_aux_lde, NL, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, sh.first, sh.step,
-                     sh.count, off, d_quot + (size_t)rank * 3 * NL, NL);
+    air_quotient_run(c, d_main_lde, NL, d_aux_lde, NL, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, sh.first, sh.step * qs,
+                     sh.count / qs, qs, off, d_quot + (size_t)rank * 3 * QL, QL);
   }
   mark();  // 6: AIR quotient
 
   // interpolate (stark.rs:1224-1231): natural order, iNTT, (coset offset undone inside the segment kernel)
-  c.all_gather(d_quot, 3 * NL * 8);
-  u64 *d_qnat = mem.words(3 * N);
-  shards_to_natural_run(c, d_quot, d_qnat, 3 * NL, NL, N, (int)log_n, (int)log_r, sh.log_w, 3);
+  c.all_gather(d_quot, 3 * QL * 8);
+  u64 *d_qnat = mem.words(3 * Q);
+  shards_to_natural_run(c, d_quot, d_qnat, 3 * QL, QL, Q, (int)log_n, (int)(log_Q - log_n), sh.log_w, 3);
   {
     NttJob inv{};
-    inv.in = d_qnat; inv.in_cstride = N; inv.out = d_quot; inv.out_cstride = N; inv.tmp = d_tmp;
-    inv.log_n = (int)log_N; inv.ncols = 3; inv.inverse = true;
+    inv.in = d_qnat; inv.in_cstride = Q; inv.out = d_quot; inv.out_cstride = Q; inv.tmp = d_tmp;
+    inv.log_n = (int)log_Q; inv.ncols = 3; inv.inverse = true;
     ntt_run(c, inv);   // d_quot[d][j] = a_j * offset^j
   }
   // split into 4 segments + randomizer segment, randomize (stark.rs:1252-1263, 1302-1356)
-  const size_t seg_len = N / NUM_QUOTIENT_SEGMENTS;     // == 2n
+  const size_t seg_len = Q / NUM_QUOTIENT_SEGMENTS;     // == 2n
   const size_t nqr = d.num_quotient_randomizer_coefficients;
   u64 *d_qr_in = mem.words(3 * nqr);
   u64 *d_qr = mem.words(3 * nqr);
@@ -422,9 +430,9 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   u64 *d_seg_coef = mem.words(15 * seg_len);
   {
     // undo the coset offset: a_j = (a_j offset^j) * offset^-j
-    scale_by_powers_run(c, d_quot, N, 3, N, c.get_pow_tab(finv(off), (int)log_N));
+    scale_by_powers_run(c, d_quot, Q, 3, Q, c.get_pow_tab(finv(off), (int)log_Q));
     SegmentArgs sa{};
-    sa.quot = d_quot; sa.quot_stride = N;
+    sa.quot = d_quot; sa.quot_stride = Q;
     sa.rnd = d_qr; sa.rnd_stride = nqr; sa.rnd_len = (unsigned)nqr;
     sa.out = d_seg_coef; sa.out_stride = seg_len; sa.seg_len = seg_len;
     u64 zeta = to_mont(3);

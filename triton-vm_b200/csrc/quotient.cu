@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) air_zerofier_kernel(ZerofierArgs a) {
 // d_out: 3 planes of r*n words (memory order = coset-major), overwritten.
 void air_quotient_run(Ctx &c, const u64 *d_main, size_t main_stride, const u64 *d_aux, size_t aux_stride,
                       const u64 *d_challenges, const u64 *d_weights, unsigned log_n, unsigned log_r,
-                      unsigned coset_first, unsigned coset_step, unsigned num_cosets,
+                      unsigned coset_first, unsigned coset_step, unsigned num_cosets, unsigned coset_mem_stride,
                       u64 offset_mont, u64 *d_out, size_t out_stride) {
   if (num_cosets > (unsigned)AIR_MAX_COSETS) throw ApiError{TVM_ERR_UNSUPPORTED, "too many cosets"};
   const unsigned num_weights = AIR_NUM_INIT + AIR_NUM_CONS + AIR_NUM_TRAN + AIR_NUM_TERM;
@@ -80,6 +80,7 @@ void air_quotient_run(Ctx &c, const u64 *d_main, size_t main_stride, const u64 *
   a.out = d_out; a.out_stride = out_stride;
   a.nrows = (size_t)num_cosets << log_n;
   a.log_n = (int)log_n;
+  a.coset_mem_stride = coset_mem_stride;
   ZerofierArgs z{};
   z.nrows = a.nrows; z.log_n = a.log_n;
   u64 wn = root_of_unity_mont(log_n);
