@@ -378,11 +378,14 @@ def prove(stark, claim, main_trace, main_rand, aux_provider, quot_rand, padded_h
     n = main_trace.shape[1]
     d = stark.derive(padded_height or n)
     assert d["trace_len"] == n, (d["trace_len"], n)
-    # the tables are extended over max(quotient, LDT) domain (master_table.rs:258-322); this oracle covers LDT >= quotient,
-    # i.e. expansion factors >= 4; the AIR then sees every (N/Q)-th row (quotient_domain_table, master_table.rs:769-779)
-    assert d["ldt_len"] % d["quotient_len"] == 0, "expansion factor 2 (quotient domain larger than LDT domain) is not covered"
+    # the tables are extended over the larger of the quotient and the LDT domain (evaluation domain, master_table.rs:
+    # 258-322); the AIR sees every qs-th row of it (quotient_domain_table, 769-779), commitments and openings every
+    # es-th row (ldt_domain_table)
     h, N, off = d["num_trace_randomizers"], d["ldt_len"], d["ldt_offset"]
+    E = max(N, d["quotient_len"])
+    es, qs = E // N, E // d["quotient_len"]
     log2N = N.bit_length() - 1
+    log2E = E.bit_length() - 1
     art = {"derived": d}
 
     ps = codec.ProofStream()
@@ -391,8 +394,8 @@ def prove(stark, claim, main_trace, main_rand, aux_provider, quot_rand, padded_h
 
     # main table: LDE, row hashes, Merkle tree
     main_rand = np.ascontiguousarray(main_rand, dtype=np.uint64).reshape(NUM_MAIN_COLUMNS, h)
-    main_lde = corc.lde_table(main_trace, main_rand, off, log2N)                     # [379, N]
-    main_nodes = corc.merkle_build(corc.hash_rows_colmajor(main_lde))
+    main_lde = corc.lde_table(main_trace, main_rand, off, log2E)                     # [379, E]
+    main_nodes = corc.merkle_build(corc.hash_rows_colmajor(np.ascontiguousarray(main_lde[:, ::es])))
     ps.enqueue("MerkleRoot", [int(v) for v in main_nodes[1]])
     challenges = derive_challenges(ps.sample_scalars(NUM_SAMPLED_CHALLENGES), claim)
 
@@ -402,15 +405,14 @@ def prove(stark, claim, main_trace, main_rand, aux_provider, quot_rand, padded_h
     aux_rand = np.ascontiguousarray(aux_rand, dtype=np.uint64).reshape(NUM_AUX_COLUMNS, h, 3)
     aux_planar = np.ascontiguousarray(aux_trace.transpose(0, 2, 1)).reshape(3 * NUM_AUX_COLUMNS, n)   # column 3q+d
     aux_rand_planar = np.ascontiguousarray(aux_rand.transpose(0, 2, 1)).reshape(3 * NUM_AUX_COLUMNS, h)
-    aux_lde = corc.lde_table(aux_planar, aux_rand_planar, off, log2N)                # [273, N]
-    aux_nodes = corc.merkle_build(corc.hash_rows_colmajor(aux_lde))
+    aux_lde = corc.lde_table(aux_planar, aux_rand_planar, off, log2E)                # [273, E]
+    aux_nodes = corc.merkle_build(corc.hash_rows_colmajor(np.ascontiguousarray(aux_lde[:, ::es])))
     ps.enqueue("MerkleRoot", [int(v) for v in aux_nodes[1]])
 
     # quotient
     w0 = ps.sample_scalars(1)[0]
     num_constraints = sum(len(v) for v in constraint_degrees().values())
     quot_weights = xpows(w0, num_constraints)
-    qs = N // d["quotient_len"]
     quotient_codeword = corc.air_quotient(np.ascontiguousarray(main_lde[:, ::qs]), np.ascontiguousarray(aux_lde[:270, ::qs]),
                                           n.bit_length() - 1, off, challenges, quot_weights)                 # [Q,3]
     quotient_poly = xcoset_interpolate(quotient_codeword, off)                       # stark.rs:1224-1231
@@ -534,9 +536,9 @@ def prove(stark, claim, main_trace, main_rand, aux_provider, quot_rand, padded_h
     def auth(nodes):
         return [[int(v) for v in nodes[k]] for k in merkle.auth_structure_node_indices(N, revealed)]
 
-    ps.enqueue("MasterMainTableRows", [[int(v) for v in main_lde[:, i]] for i in revealed])
+    ps.enqueue("MasterMainTableRows", [[int(v) for v in main_lde[:, i * es]] for i in revealed])
     ps.enqueue("AuthenticationStructure", auth(main_nodes))
-    ps.enqueue("MasterAuxTableRows", [[tuple(int(v) for v in aux_lde[3 * q:3 * q + 3, i]) for q in range(NUM_AUX_COLUMNS)]
+    ps.enqueue("MasterAuxTableRows", [[tuple(int(v) for v in aux_lde[3 * q:3 * q + 3, i * es]) for q in range(NUM_AUX_COLUMNS)]
                                       for i in revealed])
     ps.enqueue("AuthenticationStructure", auth(aux_nodes))
     ps.enqueue("QuotientSegmentsElements", [[tuple(int(v) for v in seg_codewords[s][i]) for s in range(5)] for i in revealed])

@@ -30,7 +30,8 @@ def synthetic_instance(security, log2_exp, padded_height, seed):
 
 
 @pytest.mark.parametrize("security,log2_exp,padded_height,seed", [(4, 2, 16, 1), (8, 2, 64, 2), (32, 2, 256, 3),
-                                                                  (4, 3, 16, 31), (8, 5, 32, 32)])   # expansion 8, 32
+                                                                  (4, 3, 16, 31), (8, 5, 32, 32),    # expansion 8, 32
+                                                                  (4, 1, 16, 33)])                   # expansion 2
 def test_proof_is_bit_exact_vs_oracle(backend, security, log2_exp, padded_height, seed):
     st, d, claim, main, mrand, aux_provider, qrand = synthetic_instance(security, log2_exp, padded_height, seed)
     want, _ = S.prove(st, claim, main, mrand, aux_provider, qrand, padded_height=padded_height)
@@ -88,9 +89,12 @@ def test_stir_proof_is_bit_exact_vs_oracle(backend, security, padded_height, see
     assert S.verify(st, claim, got, check_air=False)
 
 
-def test_stir_with_expansion_factor_16(backend):
+@pytest.mark.parametrize("log2_exp", [4, 1])
+def test_stir_with_other_expansion_factors(backend, log2_exp):
+    """expansion 16: the quotient domain is a sub-domain of the LDT-domain tables; expansion 2: the tables live on the
+    (larger) quotient domain and the LDT domain is every second coset of it.  Cached and just-in-time tables."""
     import tvm_b200
-    st = S.Stark(6, 4, "stir")
+    st = S.Stark(6, log2_exp, "stir")
     d = st.derive(64)
     rng = np.random.default_rng(41)
     n, h = d["trace_len"], d["num_trace_randomizers"]
@@ -103,7 +107,7 @@ def test_stir_with_expansion_factor_16(backend):
         backend.set_low_memory(mode)
         try:
             got = backend.prove((claim.program_digest, claim.input, claim.output), main, mrand, lambda ch: (aux_t, aux_r), qrand,
-                                security_level=6, log2_expansion=4, padded_height=64, ldt_choice=tvm_b200.LDT_STIR)
+                                security_level=6, log2_expansion=log2_exp, padded_height=64, ldt_choice=tvm_b200.LDT_STIR)
         finally:
             backend.set_low_memory(0)
         assert [int(v) for v in got] == want, mode
@@ -162,12 +166,12 @@ def test_prove_reports_errors_instead_of_falling_back(backend):
     with pytest.raises(RuntimeError, match="boom"):          # an exception inside the aux callback surfaces to the caller
         backend.prove(*args, lambda ch: (_ for _ in ()).throw(RuntimeError("boom")), qrand, security_level=4, log2_expansion=2,
                       padded_height=16)
-    # unsupported expansion factor 2 (quotient domain larger than the LDT domain): explicit error, no fallback
-    d1 = S.Stark(4, 1).derive(16)
+    # unsupported expansion factor 64: explicit error, no fallback
+    d1 = S.Stark(4, 6).derive(16)
     n1, h1 = d1["trace_len"], d1["num_trace_randomizers"]
     rng = np.random.default_rng(3)
     with pytest.raises(tvm_b200.TvmError) as e:
         backend.prove((claim.program_digest, claim.input, claim.output), rand_bfes(rng, (379, n1)), rand_bfes(rng, (379, h1)),
                       lambda ch: (rand_bfes(rng, (91, n1, 3)), rand_bfes(rng, (91, h1, 3))),
-                      rand_bfes(rng, (d1["num_quotient_randomizer_coefficients"], 3)), security_level=4, log2_expansion=1, padded_height=16)
+                      rand_bfes(rng, (d1["num_quotient_randomizer_coefficients"], 3)), security_level=4, log2_expansion=6, padded_height=16)
     assert e.value.code == -8

@@ -45,6 +45,7 @@ struct HashRowsParams {
   unsigned ncols;
   int log_r;
   u64 *digests;         // [nrows][5], natural row order
+  unsigned coset_mem_stride;   // rows of coset c are read from table coset c * coset_mem_stride
 };
 
 __global__ void __launch_bounds__(HASH_THREADS) tip5_hash_rows_kernel(HashRowsParams p) {
@@ -318,7 +319,8 @@ __global__ void __launch_bounds__(HASHQ2_THREADS) tip5_hash_rows_quad2_kernel(Ha
     active[t] = m < p.nrows;
     if (!active[t]) m = p.nrows - 1;                              // keep the quad alive for the shuffles
     mrow[t] = m;
-    base[t] = p.table + m;
+    const size_t per_ = p.nrows >> p.log_r, cs_ = m / per_;
+    base[t] = p.table + m + cs_ * (p.coset_mem_stride - 1) * per_;
   }
   u64 a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
   unsigned c = 0;
@@ -504,10 +506,15 @@ __global__ void __launch_bounds__(HASHQ_THREADS) tip5_hash_rows_quad_kernel(Hash
   }
 }
 
-void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, unsigned ncols, int log_r, u64 *digests) {
-  HashRowsParams p{table, col_stride, nrows, ncols, log_r, digests};
+void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, unsigned ncols, int log_r, u64 *digests,
+                   unsigned coset_mem_stride) {
+  HashRowsParams p{table, col_stride, nrows, ncols, log_r, digests, coset_mem_stride};
   static const bool use_thread_per_row = getenv("TVM_TIP5_THREAD_PER_ROW") != nullptr;
-  if (use_thread_per_row) {
+  if (coset_mem_stride != 1) {   // only the default kernel knows about strided cosets
+    const size_t rows_per_cta = HASHQ2_THREADS / 2;
+    unsigned grid = (unsigned)((nrows + rows_per_cta - 1) / rows_per_cta);
+    tip5_hash_rows_quad2_kernel<false><<<grid, HASHQ2_THREADS, 0, c.stream>>>(p);
+  } else if (use_thread_per_row) {
     unsigned grid = (unsigned)((nrows + HASH_THREADS - 1) / HASH_THREADS);
     tip5_hash_rows_kernel<<<grid, HASH_THREADS, 0, c.stream>>>(p);
   } else if (getenv("TVM_TIP5_ONE_ROW_PER_QUAD")) {

@@ -40,7 +40,9 @@ void lde_interpolate_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned
                          u64 offset_mont, size_t ncols, u64 *d_coef, size_t coef_stride, u64 *d_tmp);
 void lde_evaluate_run(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_count, unsigned log2_trace, unsigned log2_cosets,
                       unsigned coset_first, unsigned coset_step, unsigned num_cosets, size_t ncols, u64 *d_out, u64 *d_tmp);
-void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, unsigned ncols, int log_r, u64 *digests);
+// row i = coset + (k << log_r) of the nrows rows is read from table coset `coset * coset_mem_stride` ([col][coset][k])
+void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, unsigned ncols, int log_r, u64 *digests,
+                   unsigned coset_mem_stride = 1);
 void merkle_run(Ctx &c, u64 *nodes, size_t nleaves);
 void merkle_run_sharded(Ctx &c, u64 *nodes, size_t nleaves, unsigned rank, unsigned world);
 void xfe_leaves_run(Ctx &c, const u64 *cw, size_t stride, size_t n, u64 *leaves);

@@ -203,10 +203,12 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   // The tables live on the LDT domain (r = 2 * expansion cosets of the trace domain); the quotient domain (always 8
   // cosets: AIR degree 4 on the randomized trace) is every (N/Q)-th coset of it (master_table.rs:769-779).
   if (Q != 8 * n) throw ApiError{TVM_ERR_UNSUPPORTED, "quotient domain != 8 x trace domain"};
-  if (N < Q) throw ApiError{TVM_ERR_UNSUPPORTED, "expansion factor 2 (quotient domain larger than the LDT domain) is not supported"};
-  if (log_r > 6) throw ApiError{TVM_ERR_UNSUPPORTED, "expansion factors above 32 are not supported"};
-  const unsigned qs = (unsigned)(N / Q);                // LDT cosets per quotient coset
-  if (qs != 1 && c.comm.world > 1) throw ApiError{TVM_ERR_UNSUPPORTED, "multi-GPU sharding needs expansion factor 4"};
+  if (log_r > 6 || log_r < 2) throw ApiError{TVM_ERR_UNSUPPORTED, "expansion factors outside 2..32 are not supported"};
+  // Evaluation domain of the tables = the larger of the two (master_table.rs:258-322): `re` cosets.  Commitments and
+  // openings use every es-th coset (LDT domain), the AIR every qs-th (quotient domain); es = qs = 1 at expansion 4.
+  const unsigned log_re = std::max(log_r, 3u);
+  const unsigned es = (1u << log_re) >> log_r, qs = (1u << log_re) / 8;
+  if ((qs != 1 || es != 1) && c.comm.world > 1) throw ApiError{TVM_ERR_UNSUPPORTED, "multi-GPU sharding needs expansion factor 4"};
   const u64 off = to_mont(d.ldt_offset);
   const size_t NM = TVM_NUM_MAIN_COLUMNS, NA = TVM_NUM_AUX_COLUMNS, NA3 = 3 * NA;
   const size_t tmp_cols = 16;
@@ -214,8 +216,10 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   // for the column-sharded interpolation
   const unsigned W = (unsigned)c.comm.world, rank = (unsigned)c.comm.rank;
   if (W > (1u << log_r)) throw ApiError{TVM_ERR_INVALID_ARG, "more ranks than cosets"};
-  const Shard sh{rank, W, (1u << log_r) / W, ilog2(W)};
+  const Shard sh{rank, W, (1u << log_r) / W, ilog2(W)};      // LDT-domain cosets of this rank
+  const Shard she{rank, W, (1u << log_re) / W, ilog2(W)};   // evaluation-domain cosets of this rank (tables)
   const size_t NL = n * sh.count;                       // rows of the LDT domain held by this rank
+  const size_t NLe = n * she.count;                     // rows of the evaluation domain held by this rank
   const size_t hpad = std::min(n, (h + 63) & ~(size_t)63);
   const size_t cs = n + hpad;                           // stride of a table column's interpolant coefficients
   // Low-memory mode (the reference's just-in-time LDE, stark.rs:805-1006, master_table.rs:470-503, 557-606): the
@@ -227,7 +231,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     TVM_CUDA(cudaMemGetInfo(&free_b, &total_b));
     size_t pooled = 0;
     for (auto &kv : c.pool_free) pooled += kv.first;
-    const double need = 8.0 * ((double)(NM + NA3) * (NL + cs) + 40.0 * N) * 1.15;
+    const double need = 8.0 * ((double)(NM + NA3) * (NLe + cs) + 40.0 * N) * 1.15;
     jit = need > (double)(free_b + pooled);
   }
   if (timings) timings->low_memory = jit;
@@ -248,7 +252,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   mark();  // 0
 
   // ---- main table: upload, LDE, row hashes, Merkle tree (stark.rs:359-374) -------------------------
-  u64 *d_tmp = mem.words(std::max(tmp_cols * NL, 3 * N));
+  u64 *d_tmp = mem.words(std::max(tmp_cols * NLe, 3 * std::max(N, Q)));
   mark();  // (kept for the stage table: uploads are issued asynchronously below)
   cudaStream_t cs_copy = c.get_copy_stream();
   size_t nevt = 0;
@@ -263,7 +267,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     const size_t own0 = std::min(ncols, rank * cpr), own1 = std::min(ncols, own0 + cpr), nown = own1 - own0;
     const size_t bcols = ncols * xf;                    // B-field columns
     d_coef = mem.words(cpr * W * xf * cs);
-    d_lde = jit ? nullptr : mem.words(bcols * NL);
+    d_lde = jit ? nullptr : mem.words(bcols * NLe);
     u64 *d_in = mem.words(std::max<size_t>(1, nown) * xf * n + ncols * xf * h);
     u64 *d_rand_in = d_in + std::max<size_t>(1, nown) * xf * n;
     u64 *d_planar = xf == 3 ? mem.words(std::max<size_t>(1, nown) * 3 * n + ncols * 3 * h) : d_in;
@@ -295,37 +299,42 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
       const size_t q0 = (own0 + c0) * xf;               // first B-field column of the batch
       lde_interpolate_run(c, d_planar + c0 * xf * n, d_rand + q0 * h, (unsigned)h, (unsigned)hpad, log_n, off, b * xf,
                           d_coef + q0 * cs, cs, d_tmp);
-      if (W == 1 && !jit) lde_evaluate_run(c, d_coef + q0 * cs, cs, (unsigned)h, log_n, log_r, sh.first, sh.step, sh.count, b * xf,
-                                           d_lde + q0 * NL, d_tmp);
+      if (W == 1 && !jit) lde_evaluate_run(c, d_coef + q0 * cs, cs, (unsigned)h, log_n, log_re, she.first, she.step, she.count, b * xf,
+                                           d_lde + q0 * NLe, d_tmp);
     }
     if (W > 1) {
       c.all_gather(d_coef, cpr * xf * cs * 8);
-      if (!jit) evaluate_cols(c, d_coef, cs, (unsigned)h, bcols, log_n, log_r, sh, d_lde, d_tmp, tmp_cols);
+      if (!jit) evaluate_cols(c, d_coef, cs, (unsigned)h, bcols, log_n, log_re, she, d_lde, d_tmp, tmp_cols);
     }
     if (xf == 3) mem.release(d_planar);
     mem.release(d_in);
   };
   // Row digests of this rank's rows -> leaves of the full tree (all-gathered across ranks), then the tree.
-  // one local coset y of a table, evaluated from its coefficients (low-memory mode): [ncols][n]
+  // one local evaluation-domain coset y of a table, evaluated from its coefficients (low-memory mode): [ncols][n]
   auto evaluate_coset = [&](const u64 *d_coef, unsigned ncols, unsigned y, u64 *d_out) {
-    const Shard one{sh.first + sh.step * y, sh.step, 1, sh.log_w};
-    evaluate_cols(c, d_coef, cs, (unsigned)h, ncols, log_n, log_r, one, d_out, d_tmp, tmp_cols);
+    const Shard one{she.first + she.step * y, she.step, 1, she.log_w};
+    evaluate_cols(c, d_coef, cs, (unsigned)h, ncols, log_n, log_re, one, d_out, d_tmp, tmp_cols);
   };
+  // d_lde: a table on the evaluation domain (main/aux, `d_coef` given: LDT rows are every es-th coset) or on the LDT
+  // domain (quotient segments, d_coef == nullptr)
   auto commit_rows = [&](const u64 *d_lde, const u64 *d_coef, unsigned ncols, u64 *d_nodes) {
+    const unsigned stride = d_coef ? es : 1;
+    const size_t col_stride = d_coef ? NLe : NL;
     TVM_CUDA(cudaMemsetAsync(d_nodes, 0, 40, c.stream));
     if (!d_lde) {                                       // low-memory mode: hash coset by coset
-      u64 *d_dig = mem.words(5 * N);                    // [rank][y][k][5]
+      u64 *d_dig = mem.words(5 * N);                    // [rank][y][k][5], y = local LDT coset
       u64 *d_coset = mem.words((size_t)ncols * n);
-      for (unsigned y = 0; y < sh.count; y++) {
+      for (unsigned y = 0; y < she.count; y++) {
+        if (y % stride) continue;                       // W == 1 whenever stride != 1: y is the evaluation coset itself
         evaluate_coset(d_coef, ncols, y, d_coset);
-        hash_rows_run(c, d_coset, n, n, ncols, 0, d_dig + ((size_t)rank * NL + (size_t)y * n) * 5);
+        hash_rows_run(c, d_coset, n, n, ncols, 0, d_dig + ((size_t)rank * NL + (size_t)(y / stride) * n) * 5);
       }
       mem.release(d_coset);
       c.all_gather(d_dig, NL * 40);
       shard_digests_to_natural_run(c, d_dig, d_nodes + 5 * N, (int)log_n, (int)log_r, sh.log_w);
       mem.release(d_dig);
     } else if (W == 1) {
-      hash_rows_run(c, d_lde, N, N, ncols, (int)log_r, d_nodes + 5 * N);
+      hash_rows_run(c, d_lde, col_stride, N, ncols, (int)log_r, d_nodes + 5 * N, stride);
     } else {
       u64 *d_dig = mem.words(5 * N);                    // [rank][y][k][5]
       hash_rows_run(c, d_lde, NL, NL, ncols, 0, d_dig + (size_t)rank * NL * 5);
@@ -394,18 +403,18 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   u64 *d_quot = mem.words(3 * Q);   // gather buffer [rank][3][QL]; this rank's rows go to its own block
   if (jit) {
     u64 *d_mc = mem.words(NM * n), *d_ac = mem.words(NA3 * n);
-    for (unsigned y = 0; y < sh.count; y++) {
-      const unsigned coset = sh.first + sh.step * y;
+    for (unsigned y = 0; y < she.count; y++) {
+      const unsigned coset = she.first + she.step * y;
       if (coset % qs) continue;                          // not a quotient-domain coset
       evaluate_coset(d_main_coef, (unsigned)NM, y, d_mc);
       evaluate_coset(d_aux_coef, (unsigned)NA3, y, d_ac);
-      air_quotient_run(c, d_mc, n, d_ac, n, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, coset, sh.step, 1, 1,
+      air_quotient_run(c, d_mc, n, d_ac, n, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_re, coset, she.step, 1, 1,
                        off, d_quot + (size_t)rank * 3 * QL + (size_t)(y / qs) * n, QL);
     }
     mem.release(d_mc); mem.release(d_ac);
   } else {
-    air_quotient_run(c, d_main_lde, NL, d_aux_lde, NL, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_r, sh.first, sh.step * qs,
-                     sh.count / qs, qs, off, d_quot + (size_t)rank * 3 * QL, QL);
+    air_quotient_run(c, d_main_lde, NLe, d_aux_lde, NLe, d_consts, d_consts + 3 * TVM_NUM_CHALLENGES, log_n, log_re, she.first, she.step * qs,
+                     she.count / qs, qs, off, d_quot + (size_t)rank * 3 * QL, QL);
   }
   mark();  // 6: AIR quotient
 
@@ -655,15 +664,18 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
 
   // ---- open rows (stark.rs:665-716) ---------------------------------------------------------------------------------------------
   auto open_table = [&](const u64 *table, const u64 *d_coef, unsigned ncols, ItemKind kind, const u64 *nodes) {
+    const unsigned stride = d_coef ? es : 1;            // main/aux tables live on the evaluation domain
     if (table) {
       TVM_CUDA(cudaMemcpyAsync(d_idx, a_indices.data(), nq * 4, cudaMemcpyHostToDevice, c.stream));
-      gather_rows_run(c, table, NL, ncols, d_idx, nq, (int)log_n, (int)log_r, d_gather, sh.log_w, rank);
+      gather_rows_run(c, table, d_coef ? NLe : NL, ncols, d_idx, nq, (int)log_n, (int)log_r, d_gather, sh.log_w, rank, stride);
     } else {
       // low-memory mode: re-evaluate the cosets that contain opened rows (master_table.rs:557-606)
       TVM_CUDA(cudaMemsetAsync(d_gather, 0, (size_t)nq * ncols * 8, c.stream));
       u64 *d_coset = mem.words((size_t)ncols * n);
-      for (unsigned y = 0; y < sh.count; y++) {
-        const unsigned coset = sh.first + sh.step * y;
+      for (unsigned y = 0; y < she.count; y++) {
+        const unsigned ecoset = she.first + she.step * y;
+        if (ecoset % stride) continue;
+        const unsigned coset = ecoset / stride;         // LDT-domain coset
         std::vector<unsigned> kt;                       // (k, t) pairs of the queries that fall into this coset
         for (unsigned t = 0; t < nq; t++)
           if ((a_indices[t] & ((1u << log_r) - 1)) == coset) { kt.push_back(a_indices[t] >> log_r); kt.push_back(t); }

@@ -317,7 +317,7 @@ void fri_fold_run(Ctx &c, const u64 *in, size_t in_stride, size_t n, u64 offset_
 // Sharded tables (log_w > 0): a row this rank does not own is written as zeros, so that the
 // wrapping sum over ranks (all_reduce_sum_u64) reassembles the rows exactly.
 __global__ void gather_rows_kernel(const u64 *table, size_t col_stride, unsigned ncols, const unsigned *idx, unsigned nidx, int log_n,
-                                   int log_r, int log_w, unsigned rank, u64 *out) {
+                                   int log_r, int log_w, unsigned rank, unsigned coset_mem_stride, u64 *out) {
   size_t t = blockIdx.x;
   if (t >= nidx) return;
   size_t i = idx[t];
@@ -326,15 +326,15 @@ __global__ void gather_rows_kernel(const u64 *table, size_t col_stride, unsigned
   if (log_r >= 0) {
     size_t c = i & (((size_t)1 << log_r) - 1), k = i >> log_r;
     mine = (c & (((size_t)1 << log_w) - 1)) == rank;
-    m = ((c >> log_w) << log_n) + k;
+    m = (((c >> log_w) * coset_mem_stride) << log_n) + k;
   }
   for (unsigned q = threadIdx.x; q < ncols; q += blockDim.x)
     out[t * ncols + q] = mine ? from_mont(table[(size_t)q * col_stride + m]) : 0;
 }
 void gather_rows_run(Ctx &c, const u64 *table, size_t col_stride, unsigned ncols, const unsigned *d_idx, unsigned nidx, int log_n, int log_r,
-                     u64 *d_out, int log_w, unsigned rank) {
+                     u64 *d_out, int log_w, unsigned rank, unsigned coset_mem_stride) {
   if (!nidx) return;
-  gather_rows_kernel<<<nidx, 128, 0, c.stream>>>(table, col_stride, ncols, d_idx, nidx, log_n, log_r, log_w, rank, d_out);
+  gather_rows_kernel<<<nidx, 128, 0, c.stream>>>(table, col_stride, ncols, d_idx, nidx, log_n, log_r, log_w, rank, coset_mem_stride, d_out);
   c.launches++;
   TVM_CUDA(cudaGetLastError());
 }
