@@ -165,8 +165,8 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"         # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / warnings go to a file instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/tvm_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     ldt_choice = {"auto": tvm_b200.LDT_AUTO, "fri": tvm_b200.LDT_FRI, "stir": tvm_b200.LDT_STIR}[args.ldt]
