@@ -74,8 +74,8 @@ def cpu_baseline(log2_height, budget_note=True):
         phys = psutil.cpu_count(logical=False) or 0
     except Exception:
         phys = 0
-    if phys and phys < corc.num_threads():
-        corc.set_num_threads(phys)
+    if phys and phys != corc.num_threads():
+        corc.set_num_threads(phys)       # also undoes torchrun's OMP_NUM_THREADS=1 for the reference arm at N > 1
     cores = corc.num_threads()
     stages = {}
     # LDE: K full-size columns (iNTT n + NTT 8n each), OpenMP over columns like rayon
@@ -165,8 +165,11 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         import torch.distributed as dist
-        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / warnings go to a file instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/tvm_b200_nccl.%h.%p.log")
+        # rank 0 prints ONE JSON line on stdout: anything libraries print meanwhile (NCCL's version banner) is sent to
+        # stderr by pointing fd 1 at fd 2 until the result is ready
+        sys.stdout.flush()
+        saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     ldt_choice = {"auto": tvm_b200.LDT_AUTO, "fri": tvm_b200.LDT_FRI, "stir": tvm_b200.LDT_STIR}[args.ldt]
@@ -251,6 +254,11 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        import ctypes
+        ctypes.CDLL(None).fflush(None)          # NCCL prints through C stdio: drain its buffer while fd 1 still is stderr
+        os.dup2(saved_stdout_fd, 1)
+        os.close(saved_stdout_fd)
     if rank != 0:
         return
     lde_ms = stages.get("upload+LDE(main)", 0.0) + stages.get("upload+LDE(aux)", 0.0)
