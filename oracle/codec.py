@@ -18,7 +18,7 @@ in-tree known-answer test pins them except the two whole-proof digests, so this 
 
 TEST INFRASTRUCTURE ONLY."""
 from . import tip5
-from .field import P
+
 
 STRUCT_FIELDS_REVERSED = True
 

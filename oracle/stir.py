@@ -16,7 +16,7 @@ import math
 
 import numpy as np
 
-from . import codec, corc, field as F, merkle, tip5
+from . import corc, field as F, merkle, tip5
 from .field import P
 
 LOG2_FIELD_SIZE_U32 = 8 * 8 * 3          # StirParameters::LOG2_FIELD_SIZE (stir.rs:412-413)

@@ -24,7 +24,6 @@ few translation units so `make -j` compiles them in parallel.
 Run:  python -m airgen.codegen_cuda   (writes csrc/air_gen/*)
 """
 import os
-import sys
 
 from .build import CATEGORIES, build_air
 from .circuit import P, reachable_postorder
