@@ -59,7 +59,7 @@ def test_oracle_proof_of_halt_verifies_with_air_check(halt, ldt):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("security,ldt", [(8, "fri"), (160, "stir")])
+@pytest.mark.parametrize("security,ldt", [(160, "fri"), (8, "stir")])
 def test_gpu_proof_of_halt_verifies_with_air_check(backend, halt, security, ldt):
     import tvm_b200
     st, claim, main, mrand, aux_provider, qrand = _instance(halt, security, ldt)
