@@ -64,16 +64,131 @@ def lookup8(v): return tip5.LOOKUP_TABLE[v]
 def lookup16(v): return (lookup8(v >> 8) << 8) + lookup8(v & 0xFF)       # cascade.rs:29-35
 
 
+# ---- a small VM (vm.rs:361-1000) ---------------------------------------------------------------------------
+# Instruction subset: halt nop push pop dup swap add mul eq skiz call return recurse assert read_io write_io.
+# No RAM, u32, hash or sponge instructions (their tables stay in the all-padding form).
+from .isa_words import OPCODES, HAS_ARG, assemble   # noqa: E402
+
+_NAME = {v: k for k, v in OPCODES.items()}
+SUPPORTED = {"halt", "nop", "push", "pop", "dup", "swap", "add", "mul", "eq", "skiz", "call", "return", "recurse", "assert",
+             "read_io", "write_io"}
+
+
+def run(words, public_input=()):
+    """-> (processor rows [dict], op-stack table entries [(clk, shrink, pointer, payload)], instruction multiplicities,
+    public output, program digest)"""
+    digest = [int(v) for v in tip5.hash_varlen(words)]
+    stack = list(reversed(digest)) + [0] * 11                 # OpStack::new: vec index 0 = deepest element
+    jump_stack, inp, out = [], list(public_input), []
+    mult = [0] * len(words)
+    rows, os_entries = [], []
+    ip = clk = 0
+    while True:
+        if not 0 <= ip < len(words):
+            raise ValueError("instruction pointer out of bounds")
+        name = _NAME[words[ip]]
+        if name not in SUPPORTED:
+            raise ValueError(f"instruction {name} is not restated")
+        arg = words[ip + 1] if name in HAS_ARG else None
+        size = 2 if name in HAS_ARG else 1
+        nxt_ip = ip + size
+        nia = arg if arg is not None else (words[nxt_ip] if nxt_ip < len(words) else 1)      # vm.rs:1178-1189
+        hv = [0] * 6                                                                        # vm.rs:270-345
+        st = lambda i: stack[len(stack) - 1 - i]                                           # noqa: E731
+        if name in ("pop", "dup", "swap", "read_io", "write_io"):
+            hv[:4] = [(arg >> k) & 1 for k in range(4)]
+        elif name == "skiz":
+            hv[0] = inv_or_zero(st(0))
+            hv[1:6] = [nia % 2, (nia >> 1) % 4, (nia >> 3) % 4, (nia >> 5) % 4, nia >> 7]
+        elif name == "eq":
+            hv[0] = inv_or_zero(st(1) - st(0))
+        rows.append(dict(clk=clk, ip=ip, ci=words[ip], nia=nia, jsp=len(jump_stack),
+                         jso=jump_stack[-1][0] if jump_stack else 0, jsd=jump_stack[-1][1] if jump_stack else 0,
+                         st=[st(i) for i in range(16)], osp=len(stack), hv=hv))
+        mult[ip] += 1
+        io = []                                                   # underflow IO of this instruction (op_stack.rs:77-103)
+
+        def push(e):
+            stack.append(e % P)
+            io.append(("w", stack[len(stack) - 1 - 16]))
+
+        def pop():
+            io.append(("r", stack[len(stack) - 1 - 16] if len(stack) > 16 else 0))
+            if len(stack) <= 16:
+                raise ValueError("op stack too shallow")
+            return stack.pop()
+        halting = False
+        if name == "halt": halting = True; ip = nxt_ip
+        elif name == "nop": ip = nxt_ip
+        elif name == "push": push(arg); ip = nxt_ip
+        elif name == "pop":
+            for _ in range(arg): pop()
+            ip = nxt_ip
+        elif name == "dup": push(st(arg)); ip = nxt_ip
+        elif name == "swap":
+            i0, i1 = len(stack) - 1, len(stack) - 1 - arg
+            stack[i0], stack[i1] = stack[i1], stack[i0]
+            ip = nxt_ip
+        elif name == "add": x = pop(); y = pop(); push(x + y); ip = nxt_ip
+        elif name == "mul": x = pop(); y = pop(); push(x * y); ip = nxt_ip
+        elif name == "eq": x = pop(); y = pop(); push(1 if x == y else 0); ip = nxt_ip
+        elif name == "assert":
+            if pop() != 1: raise ValueError("assertion failed")
+            ip = nxt_ip
+        elif name == "skiz":
+            top = pop()
+            if top == 0:
+                nn = _NAME[words[nxt_ip]]
+                ip = nxt_ip + (2 if nn in HAS_ARG else 1)
+            else:
+                ip = nxt_ip
+        elif name == "call": jump_stack.append((ip + 2, arg)); ip = arg
+        elif name == "return": ip = jump_stack.pop()[0]
+        elif name == "recurse": ip = jump_stack[-1][1]
+        elif name == "read_io":
+            for _ in range(arg): push(inp.pop(0))
+            ip = nxt_ip
+        elif name == "write_io":
+            for _ in range(arg): out.append(pop())
+            ip = nxt_ip
+        # canonicalise the underflow IO sequence and turn it into table entries (op_stack.rs:61-87, 234-255)
+        changed = True
+        while changed:
+            changed = False
+            for k in range(len(io) - 1):
+                if io[k][0] != io[k + 1][0] and io[k][1] == io[k + 1][1]:
+                    del io[k:k + 2]; changed = True
+                    break
+        assert len({t for t, _ in io}) <= 1
+        if io:
+            ptr = len(stack) - len(io) if io[0][0] == "w" else len(stack) + len(io)
+            for t, payload in io:
+                if t == "r":
+                    ptr -= 1
+                os_entries.append((clk, 1 if t == "r" else 0, ptr, payload))
+                if t == "w":
+                    ptr += 1
+        clk += 1
+        if halting:
+            break
+    return rows, os_entries, mult, out, digest
+
+
 # ---- main table -------------------------------------------------------------------------------------
-def halt_main_table(n):
-    """[379][n] canonical uint64: MasterMainTable::new + pad for the program `halt` (master_table.rs:881-1004)."""
+def main_table(words, public_input, n):
+    """[379][n] canonical ints: MasterMainTable::new + pad (master_table.rs:881-1004) for a program of the supported
+    instruction subset.  -> (table, program digest, public output)"""
     assert n >= 256 and n & (n - 1) == 0
     T = np.zeros((NUM_MAIN, n), dtype=object)
-    program = [OP_HALT]
+    program = list(words)
+    rows, os_entries, mult, public_output, program_digest = run(program, public_input)
+    plen = len(rows)
+    assert plen <= n and len(os_entries) <= n
 
     # -- AET: program hashing (aet.rs:150-190) and the cascade / lookup multiplicities (305-344)
     padded_len = -(-(len(program) + 1) // 10) * 10
     padded_program = (program + [1] + [0] * 10)[:padded_len]
+    assert padded_len <= n
     cascade_mult, lookup_mult = {}, [0] * 256
     hash_rows = []
     sponge = [0] * 16
@@ -91,8 +206,9 @@ def halt_main_table(n):
                         lookup_mult[limb >> 8] += 1
         for rnd, row in enumerate(trace):
             hash_rows.append((rnd, row))
-        sponge = trace[-1]
-    program_digest = sponge[:5]
+        sponge = list(trace[-1])
+    assert sponge[:5] == program_digest
+    assert len(hash_rows) <= n and len(cascade_mult) <= n
 
     # -- program table (program.rs:33-113)
     c = MAIN["program"]
@@ -102,45 +218,72 @@ def halt_main_table(n):
         T[c.MaxMinusIndexInChunkInv, i] = inv_or_zero(9 - i % 10)
         if i < padded_len:
             T[c.Instruction, i] = padded_program[i]
-            T[c.LookupMultiplicity, i] = 1 if i < len(program) else 0     # `halt` is executed once
+            T[c.LookupMultiplicity, i] = mult[i] if i < len(program) else 0
             T[c.IsHashInputPadding, i] = 0 if i < len(program) else 1
         else:
             T[c.IsHashInputPadding, i] = 1
             T[c.IsTablePadding, i] = 1
 
-    # -- processor table (vm.rs:1113-1190, processor.rs:45-95): one executed row, then padding
-    c = MAIN["processor"]
-    row = {c.CLK: 0, c.IP: 0, c.CI: OP_HALT, c.NIA: 1, c.OpStackPointer: 16}
-    for b in range(7):
-        row[c.IB0 + b] = (OP_HALT >> b) & 1
-    # OpStack::new (op_stack.rs:58-68): the reversed digest occupies the 5 DEEPEST of the 16 stack registers, i.e.
-    # st11..st15 = digest[0..5]; st0..st10 = 0
-    for i in range(16):
-        row[c.ST0 + i] = program_digest[i - 11] if i >= 11 else 0
-    for k, v in row.items():
-        T[k, 0] = v
-    for i in range(1, n):
-        for k, v in row.items():
-            T[k, i] = v
-        T[c.IsPadding, i] = 1
-        T[c.CLK, i] = i
-    T[c.ClockJumpDifferenceLookupMultiplicity, 1] = (T[c.ClockJumpDifferenceLookupMultiplicity, 1] + (n - 1)) % P
-
-    # -- op stack table: empty -> padding rows only (op_stack.rs:197-211)
+    # -- op stack table (op_stack.rs:179-211): sorted by (stack pointer, clk); padding copies the last row
     c = MAIN["op_stack"]
-    T[c.IB1ShrinkStack, :] = 2
-    T[c.StackPointer, :] = 16
+    os_sorted = sorted(os_entries, key=lambda e: (e[2], e[0]))
+    clk_jump_diffs = []
+    for i, (clk, shrink, ptr, payload) in enumerate(os_sorted):
+        T[c.CLK, i], T[c.IB1ShrinkStack, i], T[c.StackPointer, i], T[c.FirstUnderflowElement, i] = clk, shrink, ptr, payload
+        if i and os_sorted[i - 1][2] == ptr:
+            clk_jump_diffs.append(clk - os_sorted[i - 1][0])
+    if os_sorted:
+        last = len(os_sorted) - 1
+        for i in range(len(os_sorted), n):
+            T[c.CLK, i], T[c.StackPointer, i] = T[c.CLK, last], T[c.StackPointer, last]
+            T[c.FirstUnderflowElement, i] = T[c.FirstUnderflowElement, last]
+            T[c.IB1ShrinkStack, i] = 2
+    else:
+        T[c.IB1ShrinkStack, :] = 2
+        T[c.StackPointer, :] = 16
 
     # -- RAM table: empty (ram.rs:89-103)
     c = MAIN["ram"]
     T[c.InstructionType, :] = 2
     T[c.BezoutCoefficientPolynomialCoefficient1, :] = 1
 
-    # -- jump stack table (jump_stack.rs:90-205)
+    # -- jump stack table (jump_stack.rs:90-205): grouped by jsp, execution order inside a group; the padding rows
+    #    follow the row with the largest clock cycle, the rows after it move to the end
     c = MAIN["jump_stack"]
-    for i in range(n):
-        T[c.CLK, i] = i
-        T[c.CI, i] = OP_HALT
+    groups = {}
+    for r in rows:
+        groups.setdefault(r["jsp"], []).append((r["clk"], r["ci"], r["jsp"], r["jso"], r["jsd"]))
+    js = [e for jsp in sorted(groups) for e in groups[jsp]]
+    for i in range(len(js) - 1):
+        if js[i][2] == js[i + 1][2]:
+            clk_jump_diffs.append(js[i + 1][0] - js[i][0])
+    k_max = next(i for i, e in enumerate(js) if e[0] == plen - 1)
+    padded_js = js[:k_max + 1] + [(clk, js[k_max][1], js[k_max][2], js[k_max][3], js[k_max][4]) for clk in range(plen, n)] + js[k_max + 1:]
+    for i, (clk, ci, jsp, jso, jsd) in enumerate(padded_js):
+        T[c.CLK, i], T[c.CI, i], T[c.JSP, i], T[c.JSO, i], T[c.JSD, i] = clk, ci, jsp, jso, jsd
+
+    # -- processor table (vm.rs:1113-1190, processor.rs:45-95)
+    c = MAIN["processor"]
+
+    def put(i, r, padding):
+        T[c.CLK, i], T[c.IP, i], T[c.CI, i], T[c.NIA, i] = r["clk"], r["ip"], r["ci"], r["nia"]
+        for b in range(7):
+            T[c.IB0 + b, i] = (r["ci"] >> b) & 1
+        T[c.JSP, i], T[c.JSO, i], T[c.JSD, i] = r["jsp"], r["jso"], r["jsd"]
+        for k in range(16):
+            T[c.ST0 + k, i] = r["st"][k]
+        T[c.OpStackPointer, i] = r["osp"]
+        for k in range(6):
+            T[c.HV0 + k, i] = r["hv"][k]
+        T[c.IsPadding, i] = 1 if padding else 0
+    for i, r in enumerate(rows):
+        put(i, r, False)
+    for d in clk_jump_diffs:
+        T[c.ClockJumpDifferenceLookupMultiplicity, d] += 1
+    for i in range(plen, n):
+        put(i, dict(rows[-1], clk=i), True)
+    if n > plen:
+        T[c.ClockJumpDifferenceLookupMultiplicity, 1] = (T[c.ClockJumpDifferenceLookupMultiplicity, 1] + (n - plen)) % P
 
     # -- hash table (hash.rs:36-302)
     c = MAIN["hash"]
@@ -173,12 +316,12 @@ def halt_main_table(n):
 
     # -- cascade table (cascade.rs:41-66): insertion order of the multiplicity map
     c = MAIN["cascade"]
-    for i, (limb, mult) in enumerate(cascade_mult.items()):
+    for i, (limb, m) in enumerate(cascade_mult.items()):
         T[c.LookInLo, i] = limb & 0xFF
         T[c.LookInHi, i] = limb >> 8
         T[c.LookOutLo, i] = lookup8(limb & 0xFF)
         T[c.LookOutHi, i] = lookup8(limb >> 8)
-        T[c.LookupMultiplicity, i] = mult
+        T[c.LookupMultiplicity, i] = m
     for i in range(len(cascade_mult), n):
         T[c.IsPadding, i] = 1
 
@@ -197,7 +340,33 @@ def halt_main_table(n):
     T[c.BitsMinus33Inv, :] = F.inv((-33) % P)
 
     fill_derived_main_columns(T)
-    return T, program_digest
+    return T, program_digest, public_output
+
+
+def padded_height(words, public_input=()):
+    """AlgebraicExecutionTrace::padded_height (aet.rs:99-135) for the supported subset"""
+    rows, os_entries, _, _, _ = run(list(words), public_input)
+    padded_len = -(-(len(words) + 1) // 10) * 10
+    hash_len = 6 * (padded_len // 10)
+    cascade = set()
+    sponge = [0] * 16
+    pp = (list(words) + [1] + [0] * 10)[:padded_len]
+    for c0 in range(0, padded_len, 10):
+        sponge[:10] = pp[c0:c0 + 10]
+        tr = tip5_trace(sponge)
+        for row in tr[:-1]:
+            for e in row[:4]:
+                cascade.update(limbs16(e))
+        sponge = list(tr[-1])
+    h = max(padded_len, len(rows), len(os_entries), hash_len, len(cascade), 256)
+    p2 = 1
+    while p2 < h: p2 <<= 1
+    return p2
+
+
+def halt_main_table(n):
+    T, digest, _ = main_table([OP_HALT], (), n)
+    return T, digest
 
 
 def _derive(constraints, start, T_cur_row, T_next_row, aux_cur, aux_next, challenges, is_main):
@@ -389,7 +558,8 @@ def extend_by_solving(T, challenges, randomizer_seed=1):
                 A[0][q] = (0, 0, 0)
     unsolved0 = [q for q in base_aux if q not in solved]
     # rows 1.. from the transition constraints
-    by_col = {q: [ev for ev in tran_evs if (1, False, q) in ev.inputs] for q in base_aux}
+    by_col = {q: [(ev, {col for (r, is_main, col) in ev.inputs if not is_main and r == 1})
+                  for ev in tran_evs if (1, False, q) in ev.inputs] for q in base_aux}
     unconstrained = set(unsolved0)
     for i in range(n - 1):
         solved = set()
@@ -399,10 +569,17 @@ def extend_by_solving(T, challenges, randomizer_seed=1):
             progress = False
             for q in base_aux:
                 if q in solved: continue
-                for ev in by_col[q]:
-                    next_refs = {col for (r, is_main, col) in ev.inputs if not is_main and r == 1}
-                    if not (next_refs - {q}) <= solved: continue
+                for ev, next_refs in by_col[q]:
+                    others = next_refs - {q} - solved
                     u = _solve_affine(ev, rows_m[i], A[i], rows_m[i + 1], nxt, challenges, 1, q)
+                    if u is not None and others:
+                        # the combined per-instruction constraints mention other, still unknown, columns of the next
+                        # row in the branches of the instructions that are NOT executing; accept the root only if it
+                        # does not move when those unknowns do
+                        for o in others: nxt[o] = (0x1234567 + o, 1, 2)
+                        u2 = _solve_affine(ev, rows_m[i], A[i], rows_m[i + 1], nxt, challenges, 1, q)
+                        for o in others: nxt[o] = (0, 0, 0)
+                        if u2 != u: u = None
                     if u is not None:
                         nxt[q] = u; solved.add(q); progress = True
                         break
