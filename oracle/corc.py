@@ -12,7 +12,7 @@ _U64P = ctypes.POINTER(ctypes.c_uint64)
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "c", f) for f in os.listdir(os.path.join(_HERE, "c"))]
+    srcs = [os.path.join(_HERE, "c", f) for f in os.listdir(os.path.join(_HERE, "c"))]   # .c, .h and generated .inc
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "_build/libtvm_oracle.so"] + (["-B"] if force else []))
     return _LIB
@@ -164,3 +164,19 @@ def fri_fold(cw, domain_offset, challenge):
     out = np.empty((n // 2, 3), dtype=np.uint64)
     lib().orc_fri_fold(_p(c), ctypes.c_size_t(n), ctypes.c_uint64(mont1(domain_offset)), _p(ch), _p(out))
     return from_mont(out).reshape(-1, 3)
+
+
+def aux_extend(main_table, challenges, randomizer_column=None):
+    """MasterMainTable::extend (master_table.rs:1006-1075) through the rules generated from the AIR
+    (triton-vm_b200/airgen/extend_gen.py -> c/aux_extend_gen.inc), run as a sequential loop.
+    main_table: [379][n] canonical; challenges: 63 X-field triples; randomizer_column: [n][3] canonical (column 90).
+    -> [91][n][3] canonical"""
+    T = to_mont(np.ascontiguousarray(main_table, dtype=np.uint64))
+    ncols, n = T.shape
+    assert ncols == 379
+    ch = to_mont(np.array(challenges, dtype=np.uint64).reshape(63, 3))
+    aux = np.zeros((91 * 3, n), dtype=np.uint64)
+    if randomizer_column is not None:
+        aux[270:273] = to_mont(np.ascontiguousarray(np.asarray(randomizer_column, dtype=np.uint64).reshape(n, 3).T))
+    lib().orc_aux_extend(_p(T), ctypes.c_size_t(n), _p(ch), _p(aux))
+    return np.ascontiguousarray(from_mont(aux).reshape(91, 3, n).transpose(0, 2, 1))

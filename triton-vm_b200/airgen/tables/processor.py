@@ -899,11 +899,15 @@ def combine_instruction_constraints_with_deselectors(e, deselectors, all_tc):
     return [msum(d * tc for d, tc in zip(deselectors, row)) for row in transposed]
 
 
+def padding_row_constraints(e):
+    return ([e.next_main(C.IP) - e.cur_main(C.IP), e.next_main(C.CI) - e.cur_main(C.CI),
+             e.next_main(C.NIA) - e.cur_main(C.NIA)]
+            + instruction_group_keep_jump_stack(e) + instruction_group_keep_op_stack(e)
+            + instruction_group_no_ram(e) + instruction_group_no_io(e))
+
+
 def combine_transition_constraints_with_padding_constraints(e, instruction_transition_constraints):
-    padding = ([e.next_main(C.IP) - e.cur_main(C.IP), e.next_main(C.CI) - e.cur_main(C.CI),
-                e.next_main(C.NIA) - e.cur_main(C.NIA)]
-               + instruction_group_keep_jump_stack(e) + instruction_group_keep_op_stack(e)
-               + instruction_group_no_ram(e) + instruction_group_no_io(e))
+    padding = padding_row_constraints(e)
     padding_row_deselector = e.constant(1) - e.next_main(C.IsPadding)
     padding_row_selector = e.next_main(C.IsPadding)
     n = max(len(instruction_transition_constraints), len(padding))
