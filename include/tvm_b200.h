@@ -182,6 +182,18 @@ typedef struct tvm_claim {
 int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height,
               const uint64_t *main_trace, const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user,
               const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len);
+/* ---- auxiliary table: MasterMainTable::extend (master_table.rs:1006-1075) = the nine tables' `extend`
+ *      (TraceTable::extend, table.rs:29-48; e.g. processor.rs:97-137, hash.rs:304-460, ram.rs:105-255) followed by
+ *      DegreeLoweringTable::fill_derived_aux_columns (substitutions.rs:163-205).  SURVEY.md 8(f).1: the stage a host
+ *      otherwise runs inside tvm_aux_callback.
+ *      main_trace         [379][n]  canonical, column-major (the tvm_prove layout), host or device memory
+ *      challenges         [63][3]   canonical, host memory (what tvm_aux_callback receives)
+ *      randomizer_column  [n][3]    canonical, host or device: the batch-randomizer column 90 (master_table.rs:1019-1025;
+ *                                   the reference draws it from its own seeded RNG); NULL = zeros
+ *      aux_trace_out      [91][n][3] canonical, host or device memory — directly usable as tvm_aux_callback's *aux_trace
+ *      n = 2^log2_n rows.  May be called from inside tvm_aux_callback on the same or on another context. --- */
+int tvm_aux_extend(tvm_ctx *ctx, const uint64_t *main_trace, unsigned log2_n, const uint64_t *challenges,
+                   const uint64_t *randomizer_column, uint64_t *aux_trace_out);
 /* device time per stage of the last tvm_prove on this ctx, reference profiler labels; returns #stages */
 int tvm_last_prove_timings(const tvm_ctx *ctx, const char **names /*[20]*/, float *ms /*[20]*/);
 

@@ -342,6 +342,8 @@ def generate():
             expr = xf.copy(rule, {own: nb.b_constant(0)})
             later = {col for (row, is_main, col) in inputs_of(expr.n) if not is_main and col >= start + k and row == 0}
             assert not later, "derived column depends on a later derived column of its own row"
+            nxt_derived = {col for (row, is_main, col) in inputs_of(expr.n) if not is_main and col >= NUM_BASE_AUX and row == 1}
+            assert not nxt_derived, "derived column reads a derived column of the next row"      # substitutions.rs:360-361
             em = Emitter("      ")
             em.emit([expr.n])
             L.append("    {")

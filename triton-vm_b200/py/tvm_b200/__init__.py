@@ -78,6 +78,7 @@ class CommStruct(ctypes.Structure):   # tvm_comm
 LDT_AUTO, LDT_FRI, LDT_STIR = 0, 1, 2      # tvm_params.ldt_choice
 
 _lib = None
+NUM_MAIN_COLUMNS, NUM_AUX_COLUMNS, NUM_CHALLENGES = 379, 91, 63      # include/tvm_b200.h
 
 # name -> (restype, argtypes); every symbol declared in include/tvm_b200.h
 _SIGNATURES = {
@@ -108,6 +109,7 @@ _SIGNATURES = {
     "tvm_derive_domains": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_uint64, ctypes.POINTER(Domains)]),
     "tvm_prove": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, _u64p, _u64p,
                                  AUX_CALLBACK, _vp, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
+    "tvm_aux_extend": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint, _u64p, _u64p, _u64p]),
     "tvm_last_prove_timings": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]),
     "tvm_air_quotient_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _u64p, _u64p, ctypes.c_uint,
                                             ctypes.c_uint, ctypes.c_uint64, _vp, ctypes.c_size_t]),
@@ -239,6 +241,26 @@ class Backend:
         self._chk(self._l.tvm_merkle_build(self._h, lp, n, nodes.ctypes.data_as(_u64p) if want_nodes else None,
                                            root.ctypes.data_as(_u64p)))
         return (root, nodes) if want_nodes else root
+
+    def aux_extend(self, main_trace, challenges, randomizer_column=None, out=None):
+        """MasterMainTable::extend on the device: main_trace [379, n] canonical (numpy, or a contiguous torch tensor on
+        the host or on this GPU), challenges [63, 3], randomizer_column [n, 3] (column 90) or None -> aux trace [91, n, 3]
+        canonical.  `out`: optional preallocated destination (numpy or torch, host or device); a numpy array otherwise."""
+        keep, mp, shape = _u64_arg(main_trace)
+        assert len(shape) == 2 and shape[0] == NUM_MAIN_COLUMNS and shape[1] & (shape[1] - 1) == 0
+        n = shape[1]
+        ch = np.ascontiguousarray(np.asarray(challenges, dtype=np.uint64).reshape(63, 3))
+        rp, rkeep = None, None
+        if randomizer_column is not None:
+            rkeep, rp, rshape = _u64_arg(randomizer_column)
+            assert tuple(rshape) == (n, 3)
+        if out is None:
+            out = np.empty((NUM_AUX_COLUMNS, n, 3), dtype=np.uint64)
+        okeep, op, oshape = _u64_arg(out)
+        assert tuple(oshape) == (NUM_AUX_COLUMNS, n, 3)
+        self._chk(self._l.tvm_aux_extend(self._h, mp, n.bit_length() - 1, ch.ctypes.data_as(_u64p), rp, op))
+        del keep, rkeep, okeep
+        return out
 
     def prove(self, claim, main_trace, main_rand, aux_provider, quot_rand, security_level=160, log2_expansion=2,
               padded_height=None, ldt_choice=LDT_FRI, conjectured=False):
