@@ -1,14 +1,14 @@
-"""Trace generation for the smallest Triton VM program (`halt`): master main table (fill + pad + derived columns) and
-master auxiliary table (`extend`), restated from the reference so that an AIR-SATISFYING instance exists in this
-repository — with it the oracle verifier runs with `check_air=True` (the out-of-domain AIR / quotient identity,
-stark.rs:1469-1540), which synthetic tables can never pass.
+"""Trace generation: a restatement of the VM (41 of the 46 instructions), of the master main table (fill + pad + derived
+columns) and of the master auxiliary table (`extend`), so that AIR-SATISFYING instances exist in this repository — with
+them the oracle verifier runs with `check_air=True` (the out-of-domain AIR / quotient identity, stark.rs:1469-1540), which
+synthetic tables can never pass.
 
 TEST INFRASTRUCTURE ONLY.  Follows, table by table:
   aet.rs:95-215 (program hashing trace, lookup multiplicities), vm.rs:246-268, 1113-1190 (initial state, processor row),
   table/master_table.rs:881-1004 (fill order, pad, derived columns), table/{program,processor,op_stack,ram,jump_stack,
   hash,cascade,lookup,u32}.rs (fill / pad / extend), triton-constraint-builder/src/substitutions.rs:128-330
-  (derived-column fill).  Only what the one-instruction program exercises is restated: no op-stack underflow, RAM,
-  u32, sponge or hash-instruction rows.
+  (derived-column fill), vm.rs:270-1100 (instruction semantics, helper variables), triton-isa/src/op_stack.rs:61-255
+  (underflow I/O), table/u32.rs:100-290, table/ram.rs:64-262 (sections, Bezout coefficients).
 """
 import os
 import sys
@@ -64,24 +64,37 @@ def lookup8(v): return tip5.LOOKUP_TABLE[v]
 def lookup16(v): return (lookup8(v >> 8) << 8) + lookup8(v & 0xFF)       # cascade.rs:29-35
 
 
-# ---- a small VM (vm.rs:361-1000) ---------------------------------------------------------------------------
-# Instruction subset: halt nop push pop dup swap add mul eq skiz call return recurse assert read_io write_io.
-# No RAM, u32, hash or sponge instructions (their tables stay in the all-padding form).
+# ---- a VM (vm.rs:361-1100) -----------------------------------------------------------------------------------------
+# Everything except merkle_step, merkle_step_mem, sponge_absorb_mem, b_horner_step, x_horner_step.
 from .isa_words import OPCODES, HAS_ARG, assemble   # noqa: E402
 
 _NAME = {v: k for k, v in OPCODES.items()}
-SUPPORTED = {"halt", "nop", "push", "pop", "dup", "swap", "add", "mul", "eq", "skiz", "call", "return", "recurse", "assert",
-             "read_io", "write_io"}
+UNSUPPORTED = {"merkle_step", "merkle_step_mem", "sponge_absorb_mem", "b_horner_step", "x_horner_step"}
+SUPPORTED = set(OPCODES) - UNSUPPORTED
+U32_MAX = (1 << 32) - 1
 
 
-def run(words, public_input=()):
-    """-> (processor rows [dict], op-stack table entries [(clk, shrink, pointer, payload)], instruction multiplicities,
-    public output, program digest)"""
-    digest = [int(v) for v in tip5.hash_varlen(words)]
-    stack = list(reversed(digest)) + [0] * 11                 # OpStack::new: vec index 0 = deepest element
-    jump_stack, inp, out = [], list(public_input), []
-    mult = [0] * len(words)
-    rows, os_entries = [], []
+class Execution:
+    """what AlgebraicExecutionTrace (aet.rs:41-91) records"""
+
+    def __init__(self):
+        self.rows, self.op_stack_entries, self.output = [], [], []
+        self.sponge_rows = []            # (CI, round number, state)                         aet.rs:276-297
+        self.hash_traces = []            # permutation traces of `hash`                      aet.rs:264-274
+        self.lookup_traces = []          # every trace whose S-box look-ups are counted, in execution order
+        self.u32_entries = {}            # (instruction name, lhs, rhs) -> multiplicity       aet.rs:346-348 (IndexMap)
+        self.ram_calls = []              # (clk, is_write, pointer, value)                    ram.rs:38-60
+
+
+def execute(words, public_input=(), secret_input=(), initial_ram=None):
+    """VM::run with full tracing (vm.rs:361-1000) -> Execution"""
+    ex = Execution()
+    ex.digest = [int(v) for v in tip5.hash_varlen(words)]
+    stack = list(reversed(ex.digest)) + [0] * 11                # OpStack::new: list index 0 = deepest element
+    jump_stack, inp, sec = [], list(public_input), list(secret_input)
+    ram = dict(initial_ram or {})
+    sponge = None
+    ex.multiplicities = [0] * len(words)
     ip = clk = 0
     while True:
         if not 0 <= ip < len(words):
@@ -90,67 +103,192 @@ def run(words, public_input=()):
         if name not in SUPPORTED:
             raise ValueError(f"instruction {name} is not restated")
         arg = words[ip + 1] if name in HAS_ARG else None
-        size = 2 if name in HAS_ARG else 1
-        nxt_ip = ip + size
+        nxt_ip = ip + (2 if name in HAS_ARG else 1)
         nia = arg if arg is not None else (words[nxt_ip] if nxt_ip < len(words) else 1)      # vm.rs:1178-1189
-        hv = [0] * 6                                                                        # vm.rs:270-345
         st = lambda i: stack[len(stack) - 1 - i]                                           # noqa: E731
-        if name in ("pop", "dup", "swap", "read_io", "write_io"):
+        hv = [0] * 6                                                                        # vm.rs:270-345
+        if name in ("pop", "divine", "pick", "place", "dup", "swap", "read_mem", "write_mem", "read_io", "write_io"):
             hv[:4] = [(arg >> k) & 1 for k in range(4)]
         elif name == "skiz":
             hv[0] = inv_or_zero(st(0))
             hv[1:6] = [nia % 2, (nia >> 1) % 4, (nia >> 3) % 4, (nia >> 5) % 4, nia >> 7]
+        elif name == "recurse_or_return":
+            hv[0] = inv_or_zero(st(6) - st(5))
+        elif name == "split":
+            if st(0) & U32_MAX:
+                hv[0] = inv_or_zero((st(0) >> 32) - U32_MAX)
         elif name == "eq":
             hv[0] = inv_or_zero(st(1) - st(0))
-        rows.append(dict(clk=clk, ip=ip, ci=words[ip], nia=nia, jsp=len(jump_stack),
-                         jso=jump_stack[-1][0] if jump_stack else 0, jsd=jump_stack[-1][1] if jump_stack else 0,
-                         st=[st(i) for i in range(16)], osp=len(stack), hv=hv))
-        mult[ip] += 1
-        io = []                                                   # underflow IO of this instruction (op_stack.rs:77-103)
+        ex.rows.append(dict(clk=clk, ip=ip, ci=words[ip], nia=nia, jsp=len(jump_stack),
+                            jso=jump_stack[-1][0] if jump_stack else 0, jsd=jump_stack[-1][1] if jump_stack else 0,
+                            st=[st(i) for i in range(16)], osp=len(stack), hv=hv))
+        ex.multiplicities[ip] += 1
+        io = []                                                   # underflow IO of this instruction (op_stack.rs:61-103)
+
+        def underflow():
+            return stack[len(stack) - 17] if len(stack) > 16 else 0
 
         def push(e):
             stack.append(e % P)
-            io.append(("w", stack[len(stack) - 1 - 16]))
+            io.append(("w", underflow()))
 
         def pop():
-            io.append(("r", stack[len(stack) - 1 - 16] if len(stack) > 16 else 0))
+            io.append(("r", underflow()))
             if len(stack) <= 16:
                 raise ValueError("op stack too shallow")
             return stack.pop()
+
+        def pop_u32():
+            v = pop()
+            if v > U32_MAX: raise ValueError("not a u32")
+            return v
+
+        def need_u32(i):
+            if st(i) > U32_MAX: raise ValueError("not a u32")
+
+        def u32_call(instr, lhs, rhs):
+            key = (instr, lhs % P, rhs % P)
+            ex.u32_entries[key] = ex.u32_entries.get(key, 0) + 1
+
+        def permutation(state, sponge_ci=None):
+            trace = tip5_trace(state)
+            ex.lookup_traces.append(trace)
+            if sponge_ci is None:
+                ex.hash_traces.append(trace)
+            else:
+                ex.sponge_rows.extend((sponge_ci, rnd, row) for rnd, row in enumerate(trace))
+            return trace
+
+        def pop_x(): return (pop(), pop(), pop())
+
+        def push_x(x):
+            for c in reversed(x): push(c)
+
         halting = False
-        if name == "halt": halting = True; ip = nxt_ip
-        elif name == "nop": ip = nxt_ip
-        elif name == "push": push(arg); ip = nxt_ip
+        ip_after = nxt_ip
+        if name == "halt": halting = True
+        elif name == "nop": pass
+        elif name == "push": push(arg)
         elif name == "pop":
             for _ in range(arg): pop()
-            ip = nxt_ip
-        elif name == "dup": push(st(arg)); ip = nxt_ip
+        elif name == "divine":
+            if len(sec) < arg: raise IndexError("secret input exhausted")
+            for _ in range(arg): push(sec.pop(0))
+        elif name == "pick":
+            io.append(("r", underflow()))
+            push(stack.pop(len(stack) - 1 - arg))
+        elif name == "place":
+            e = pop()
+            stack.insert(len(stack) - arg, e)
+            io.append(("w", underflow()))
+        elif name == "dup": push(st(arg))
         elif name == "swap":
             i0, i1 = len(stack) - 1, len(stack) - 1 - arg
             stack[i0], stack[i1] = stack[i1], stack[i0]
-            ip = nxt_ip
-        elif name == "add": x = pop(); y = pop(); push(x + y); ip = nxt_ip
-        elif name == "mul": x = pop(); y = pop(); push(x * y); ip = nxt_ip
-        elif name == "eq": x = pop(); y = pop(); push(1 if x == y else 0); ip = nxt_ip
-        elif name == "assert":
-            if pop() != 1: raise ValueError("assertion failed")
-            ip = nxt_ip
         elif name == "skiz":
+            if pop() == 0:
+                ip_after = nxt_ip + (2 if _NAME[words[nxt_ip]] in HAS_ARG else 1)
+        elif name == "call": jump_stack.append((ip + 2, arg)); ip_after = arg
+        elif name == "return": ip_after = jump_stack.pop()[0]
+        elif name == "recurse": ip_after = jump_stack[-1][1]
+        elif name == "recurse_or_return":
+            ip_after = jump_stack.pop()[0] if st(5) == st(6) else jump_stack[-1][1]
+        elif name == "assert":
+            if st(0) != 1: raise ValueError("assertion failed")
+            pop()
+        elif name == "read_mem":
+            ptr = pop()
+            for _ in range(arg):
+                v = ram.get(ptr, 0)
+                ex.ram_calls.append((clk, 0, ptr, v))
+                push(v)
+                ptr = (ptr - 1) % P
+            push(ptr)
+        elif name == "write_mem":
+            ptr = pop()
+            for _ in range(arg):
+                v = pop()
+                ex.ram_calls.append((clk, 1, ptr, v))
+                ram[ptr] = v
+                ptr = (ptr + 1) % P
+            push(ptr)
+        elif name == "hash":
+            to_hash = [pop() for _ in range(10)]
+            out = permutation(to_hash + [1] * 6)[-1][:5]            # Domain::FixedLength: capacity of ones
+            for e in reversed(out): push(e)
+        elif name == "assert_vector":
+            if any(st(i) != st(i + 5) for i in range(5)): raise ValueError("vector assertion failed")
+            for _ in range(5): pop()
+        elif name == "sponge_init":
+            sponge = [0] * 16
+            ex.sponge_rows.append((OPCODES["sponge_init"], 0, list(sponge)))
+        elif name == "sponge_absorb":
+            if sponge is None: raise ValueError("sponge not initialized")
+            sponge[:10] = [pop() for _ in range(10)]
+            sponge = list(permutation(sponge, OPCODES["sponge_absorb"])[-1])
+        elif name == "sponge_squeeze":
+            if sponge is None: raise ValueError("sponge not initialized")
+            for i in reversed(range(10)): push(sponge[i])
+            sponge = list(permutation(sponge, OPCODES["sponge_squeeze"])[-1])
+        elif name == "add": x = pop(); y = pop(); push(x + y)
+        elif name == "addi": stack[-1] = (stack[-1] + arg) % P
+        elif name == "mul": x = pop(); y = pop(); push(x * y)
+        elif name == "invert":
+            if st(0) == 0: raise ValueError("inverse of zero")
+            push(F.inv(pop()))
+        elif name == "eq": x = pop(); y = pop(); push(1 if x == y else 0)
+        elif name == "split":
             top = pop()
-            if top == 0:
-                nn = _NAME[words[nxt_ip]]
-                ip = nxt_ip + (2 if nn in HAS_ARG else 1)
-            else:
-                ip = nxt_ip
-        elif name == "call": jump_stack.append((ip + 2, arg)); ip = arg
-        elif name == "return": ip = jump_stack.pop()[0]
-        elif name == "recurse": ip = jump_stack[-1][1]
+            lo, hi = top & U32_MAX, top >> 32
+            push(hi); push(lo)
+            u32_call("split", lo, hi)
+        elif name == "lt":
+            need_u32(0); need_u32(1)
+            lhs = pop_u32(); rhs = pop_u32(); push(1 if lhs < rhs else 0)
+            u32_call("lt", lhs, rhs)
+        elif name == "and":
+            need_u32(0); need_u32(1)
+            lhs = pop_u32(); rhs = pop_u32(); push(lhs & rhs)
+            u32_call("and", lhs, rhs)
+        elif name == "xor":
+            need_u32(0); need_u32(1)
+            lhs = pop_u32(); rhs = pop_u32(); push(lhs ^ rhs)
+            u32_call("and", lhs, rhs)                              # a ^ b = a + b - 2 (a & b), vm.rs:860-865
+        elif name == "log_2_floor":
+            need_u32(0)
+            if st(0) == 0: raise ValueError("logarithm of zero")
+            top = pop_u32(); push(top.bit_length() - 1)
+            u32_call("log_2_floor", top, 0)
+        elif name == "pow":
+            need_u32(1)
+            base = pop(); exponent = pop_u32(); push(pow(base, exponent, P))
+            u32_call("pow", base, exponent)
+        elif name == "div_mod":
+            need_u32(0); need_u32(1)
+            if st(1) == 0: raise ValueError("division by zero")
+            numerator = pop_u32(); denominator = pop_u32()
+            quotient, remainder = divmod(numerator, denominator)
+            push(quotient); push(remainder)
+            u32_call("lt", remainder, denominator)
+            u32_call("split", numerator, quotient)
+        elif name == "pop_count":
+            need_u32(0)
+            top = pop_u32(); push(bin(top).count("1"))
+            u32_call("pop_count", top, 0)
+        elif name == "xx_add": x = pop_x(); y = pop_x(); push_x(F.xadd(x, y))
+        elif name == "xx_mul": x = pop_x(); y = pop_x(); push_x(F.xmul(x, y))
+        elif name == "x_invert":
+            if (st(0), st(1), st(2)) == (0, 0, 0): raise ValueError("inverse of zero")
+            push_x(F.xinv(pop_x()))
+        elif name == "xb_mul": x = pop(); y = pop_x(); push_x(F.xmul((x, 0, 0), y))
         elif name == "read_io":
+            if len(inp) < arg: raise IndexError("public input exhausted")
             for _ in range(arg): push(inp.pop(0))
-            ip = nxt_ip
         elif name == "write_io":
-            for _ in range(arg): out.append(pop())
-            ip = nxt_ip
+            for _ in range(arg): ex.output.append(pop())
+        else:
+            raise AssertionError(name)
+        ip = ip_after
         # canonicalise the underflow IO sequence and turn it into table entries (op_stack.rs:61-87, 234-255)
         changed = True
         while changed:
@@ -165,36 +303,41 @@ def run(words, public_input=()):
             for t, payload in io:
                 if t == "r":
                     ptr -= 1
-                os_entries.append((clk, 1 if t == "r" else 0, ptr, payload))
+                ex.op_stack_entries.append((clk, 1 if t == "r" else 0, ptr, payload))
                 if t == "w":
                     ptr += 1
         clk += 1
         if halting:
             break
-    return rows, os_entries, mult, out, digest
+    return ex
 
 
-# ---- main table -------------------------------------------------------------------------------------
-def main_table(words, public_input, n):
-    """[379][n] canonical ints: MasterMainTable::new + pad (master_table.rs:881-1004) for a program of the supported
-    instruction subset.  -> (table, program digest, public output)"""
-    assert n >= 256 and n & (n - 1) == 0
-    T = np.zeros((NUM_MAIN, n), dtype=object)
-    program = list(words)
-    rows, os_entries, mult, public_output, program_digest = run(program, public_input)
-    plen = len(rows)
-    assert plen <= n and len(os_entries) <= n
+def run(words, public_input=(), secret_input=()):
+    """-> (processor rows, op-stack table entries, instruction multiplicities, public output, program digest)"""
+    ex = execute(words, public_input, secret_input)
+    return ex.rows, ex.op_stack_entries, ex.multiplicities, ex.output, ex.digest
 
-    # -- AET: program hashing (aet.rs:150-190) and the cascade / lookup multiplicities (305-344)
+
+# ---- co-processor tables -------------------------------------------------------------------------------------------
+def _program_hash(program):
+    """aet.rs:150-190 -> (padded program, hash-table rows [(round, state)], permutation traces)"""
     padded_len = -(-(len(program) + 1) // 10) * 10
-    padded_program = (program + [1] + [0] * 10)[:padded_len]
-    assert padded_len <= n
-    cascade_mult, lookup_mult = {}, [0] * 256
-    hash_rows = []
+    padded_program = (list(program) + [1] + [0] * 10)[:padded_len]
+    rows, traces = [], []
     sponge = [0] * 16
     for c0 in range(0, padded_len, 10):
         sponge[:10] = padded_program[c0:c0 + 10]
         trace = tip5_trace(sponge)
+        traces.append(trace)
+        rows += list(enumerate(trace))
+        sponge = list(trace[-1])
+    return padded_program, rows, traces, sponge[:5]
+
+
+def _lookup_multiplicities(traces):
+    """aet.rs:305-344: cascade multiplicities in first-use order (IndexMap), lookup-table multiplicities"""
+    cascade_mult, lookup_mult = {}, [0] * 256
+    for trace in traces:
         for row in trace[:-1]:
             for e in row[:4]:
                 for limb in limbs16(e):
@@ -204,11 +347,116 @@ def main_table(words, public_input, n):
                         cascade_mult[limb] = 1
                         lookup_mult[limb & 0xFF] += 1
                         lookup_mult[limb >> 8] += 1
-        for rnd, row in enumerate(trace):
-            hash_rows.append((rnd, row))
-        sponge = list(trace[-1])
-    assert sponge[:5] == program_digest
-    assert len(hash_rows) <= n and len(cascade_mult) <= n
+    return cascade_mult, lookup_mult
+
+
+def _u32_section(instr, lhs, rhs, multiplicity):
+    """u32.rs:193-290: rows (CopyFlag, Bits, CI, LHS, RHS, Result, LookupMultiplicity) of one table section"""
+    rows = []
+    bits, flag, m = 0, 1, multiplicity
+    while True:
+        rows.append(dict(flag=flag, bits=bits, lhs=lhs, rhs=rhs, mult=m))
+        if (lhs == 0 or instr == "pow") and rhs == 0:
+            break
+        lhs = lhs if instr == "pow" else lhs >> 1
+        rhs >>= 1
+        bits, flag, m = bits + 1, 0, 0
+    last = rows[-1]
+    last["result"] = {"split": 0, "lt": 2, "and": 0, "log_2_floor": P - 1, "pow": 1, "pop_count": 0}[instr]
+    if instr == "lt" and last["bits"] == 0:
+        last["result"] = 0
+    for k in range(len(rows) - 2, -1, -1):
+        row, nxt = rows[k], rows[k + 1]
+        lsb_l, lsb_r, nr = row["lhs"] & 1, row["rhs"] & 1, nxt["result"]
+        if instr == "split": r = nr
+        elif instr == "lt":
+            if nr in (0, 1): r = nr
+            elif (lsb_l, lsb_r) == (0, 1): r = 1
+            elif (lsb_l, lsb_r) == (1, 0): r = 0
+            else: r = 0 if row["flag"] == 1 else 2
+        elif instr == "and": r = (2 * nr + lsb_l * lsb_r) % P
+        elif instr == "log_2_floor":
+            r = P - 1 if row["lhs"] == 0 else (nr if nxt["lhs"] != 0 else row["bits"])
+        elif instr == "pow": r = nr * nr % P if lsb_r == 0 else nr * nr % P * row["lhs"] % P
+        else: r = (nr + lsb_l) % P
+        row["result"] = r
+    return rows
+
+
+def _poly_mul(a, b):
+    out = [0] * (len(a) + len(b) - 1)
+    for i, x in enumerate(a):
+        if x:
+            for j, y in enumerate(b):
+                out[i + j] = (out[i + j] + x * y) % P
+    return out
+
+
+def bezout_coefficients(roots):
+    """ram.rs:162-214: a, b with a*rp + b*fd = 1 for rp = prod (x - r), fd = rp' ; coefficient lists of length len(roots)"""
+    n = len(roots)
+    if n == 0:
+        return [], []
+    rp = [1]
+    for r in roots:
+        rp = _poly_mul(rp, [(-r) % P, 1])
+    fd = [(k * rp[k]) % P for k in range(1, n + 1)]
+    ev = lambda poly, x: sum(c * pow(x, k, P) for k, c in enumerate(poly)) % P        # noqa: E731
+    b = [0] * n                                                    # Lagrange interpolation of 1 / fd(r) in the roots
+    for r in roots:
+        num, den = [1], 1
+        for r2 in roots:
+            if r2 != r:
+                num = _poly_mul(num, [(-r2) % P, 1])
+                den = den * (r - r2) % P
+        scale = F.inv(ev(fd, r)) * F.inv(den) % P
+        for k, c in enumerate(num):
+            b[k] = (b[k] + c * scale) % P
+    rem = _poly_mul(fd, b)                                         # a = (1 - fd b) / rp, an exact division
+    rem = [(-c) % P for c in rem]
+    rem[0] = (rem[0] + 1) % P
+    a = [0] * max(1, len(rem) - n)
+    for k in range(len(rem) - 1, n - 1, -1):                        # rp is monic of degree n
+        q = rem[k]
+        a[k - n] = q
+        if q:
+            for j in range(n + 1):
+                rem[k - n + j] = (rem[k - n + j] - q * rp[j]) % P
+    assert not any(rem), "division of 1 - fd*b by rp left a remainder"
+    return (a + [0] * n)[:n], (b + [0] * n)[:n]
+
+
+def table_heights(words, ex):
+    """AlgebraicExecutionTrace::height_of_table (aet.rs:137-168)"""
+    padded_len = -(-(len(words) + 1) // 10) * 10
+    traces = _program_hash(words)[2] + ex.lookup_traces
+    u32 = sum(1 if max(l if i != "pow" else 0, r) == 0 else 1 + max(l if i != "pow" else 0, r).bit_length()
+              for (i, l, r) in ex.u32_entries)
+    return dict(program=padded_len, processor=len(ex.rows), op_stack=len(ex.op_stack_entries), ram=len(ex.ram_calls),
+                jump_stack=len(ex.rows), hash=6 * (padded_len // 10) + len(ex.sponge_rows) + 6 * len(ex.hash_traces),
+                cascade=len(_lookup_multiplicities(traces)[0]), lookup=256, u32=u32)
+
+
+# ---- main table -------------------------------------------------------------------------------------
+def main_table(words, public_input, n, secret_input=(), initial_ram=None):
+    """[379][n] canonical ints: MasterMainTable::new + pad (master_table.rs:881-1004).
+    -> (table, program digest, public output)"""
+    assert n >= 256 and n & (n - 1) == 0
+    T = np.zeros((NUM_MAIN, n), dtype=object)
+    program = list(words)
+    ex = execute(program, public_input, secret_input, initial_ram)
+    rows, plen = ex.rows, len(ex.rows)
+    heights = table_heights(program, ex)
+    assert max(heights.values()) <= n, f"table heights {heights} exceed {n}"
+
+    padded_program, program_hash_rows, program_traces, digest = _program_hash(program)
+    assert digest == ex.digest
+    padded_len = len(padded_program)
+    cascade_mult, lookup_mult = _lookup_multiplicities(program_traces + ex.lookup_traces)
+    h_op = OPCODES["hash"]
+    hash_rows = ([(1, h_op, rnd, st) for rnd, st in program_hash_rows]                       # hash.rs:241-268
+                 + [(2, ci, rnd, st) for ci, rnd, st in ex.sponge_rows]
+                 + [(3, h_op, rnd, st) for trace in ex.hash_traces for rnd, st in enumerate(trace)])
 
     # -- program table (program.rs:33-113)
     c = MAIN["program"]
@@ -218,7 +466,7 @@ def main_table(words, public_input, n):
         T[c.MaxMinusIndexInChunkInv, i] = inv_or_zero(9 - i % 10)
         if i < padded_len:
             T[c.Instruction, i] = padded_program[i]
-            T[c.LookupMultiplicity, i] = mult[i] if i < len(program) else 0
+            T[c.LookupMultiplicity, i] = ex.multiplicities[i] if i < len(program) else 0
             T[c.IsHashInputPadding, i] = 0 if i < len(program) else 1
         else:
             T[c.IsHashInputPadding, i] = 1
@@ -226,7 +474,7 @@ def main_table(words, public_input, n):
 
     # -- op stack table (op_stack.rs:179-211): sorted by (stack pointer, clk); padding copies the last row
     c = MAIN["op_stack"]
-    os_sorted = sorted(os_entries, key=lambda e: (e[2], e[0]))
+    os_sorted = sorted(ex.op_stack_entries, key=lambda e: (e[2], e[0]))
     clk_jump_diffs = []
     for i, (clk, shrink, ptr, payload) in enumerate(os_sorted):
         T[c.CLK, i], T[c.IB1ShrinkStack, i], T[c.StackPointer, i], T[c.FirstUnderflowElement, i] = clk, shrink, ptr, payload
@@ -242,10 +490,32 @@ def main_table(words, public_input, n):
         T[c.IB1ShrinkStack, :] = 2
         T[c.StackPointer, :] = 16
 
-    # -- RAM table: empty (ram.rs:89-103)
+    # -- RAM table (ram.rs:64-141, 216-262): sorted by (pointer, clk); Bezout coefficients change with the pointer
     c = MAIN["ram"]
-    T[c.InstructionType, :] = 2
-    T[c.BezoutCoefficientPolynomialCoefficient1, :] = 1
+    ram_sorted = sorted(ex.ram_calls, key=lambda e: (e[2], e[0]))
+    if ram_sorted:
+        unique = list(dict.fromkeys(e[2] for e in ram_sorted))
+        bez0, bez1 = bezout_coefficients(unique)
+        cur0, cur1 = bez0.pop(), bez1.pop()
+        for i, (clk, is_write, ptr, val) in enumerate(ram_sorted):
+            if i:
+                prev = ram_sorted[i - 1]
+                if prev[2] == ptr:
+                    clk_jump_diffs.append(clk - prev[0])
+                else:
+                    cur0, cur1 = bez0.pop(), bez1.pop()
+                T[c.InverseOfRampDifference, i - 1] = inv_or_zero(ptr - prev[2])
+            T[c.CLK, i], T[c.InstructionType, i], T[c.RamPointer, i], T[c.RamValue, i] = clk, 0 if is_write else 1, ptr, val
+            T[c.BezoutCoefficientPolynomialCoefficient0, i], T[c.BezoutCoefficientPolynomialCoefficient1, i] = cur0, cur1
+        assert not bez0 and not bez1
+        last = len(ram_sorted) - 1
+        for i in range(len(ram_sorted), n):
+            for col in range(c.start, c.start + c.COUNT):
+                T[col, i] = T[col, last]
+            T[c.InstructionType, i] = 2
+    else:
+        T[c.InstructionType, :] = 2
+        T[c.BezoutCoefficientPolynomialCoefficient1, :] = 1
 
     # -- jump stack table (jump_stack.rs:90-205): grouped by jsp, execution order inside a group; the padding rows
     #    follow the row with the largest clock cycle, the rows after it move to the end
@@ -291,9 +561,9 @@ def main_table(words, public_input, n):
 
     def col(name): return c.start + names.index(name)
     parts = ("Lowest", "MidLow", "MidHigh", "Highest")
-    for i, (rnd, st) in enumerate(hash_rows):
-        T[c.Mode, i] = 1
-        T[c.CI, i] = OP_HASH
+    for i, (mode, ci, rnd, st) in enumerate(hash_rows):
+        T[c.Mode, i] = mode
+        T[c.CI, i] = ci
         T[c.RoundNumber, i] = rnd
         for e in range(4):
             lb = limbs16(st[e])
@@ -312,9 +582,9 @@ def main_table(words, public_input, n):
         for k in range(16):
             T[col(f"Constant{k}"), i] = tip5.ROUND_CONSTANTS[k]
         T[c.Mode, i] = 0
-        T[c.CI, i] = OP_HASH
+        T[c.CI, i] = h_op
 
-    # -- cascade table (cascade.rs:41-66): insertion order of the multiplicity map
+    # -- cascade table (cascade.rs:41-66): first-use order of the multiplicity map
     c = MAIN["cascade"]
     for i, (limb, m) in enumerate(cascade_mult.items()):
         T[c.LookInLo, i] = limb & 0xFF
@@ -334,31 +604,33 @@ def main_table(words, public_input, n):
     for i in range(256, n):
         T[c.IsPadding, i] = 1
 
-    # -- u32 table: empty (u32.rs:126-154)
+    # -- u32 table (u32.rs:100-154, 193-290): one section per distinct (instruction, operands), first-use order
     c = MAIN["u32"]
-    T[c.CI, :] = OP_SPLIT
-    T[c.BitsMinus33Inv, :] = F.inv((-33) % P)
+    i = 0
+    for (instr, lhs, rhs), mult in ex.u32_entries.items():
+        for r in _u32_section(instr, lhs, rhs, mult):
+            T[c.CopyFlag, i], T[c.Bits, i], T[c.CI, i] = r["flag"], r["bits"], OPCODES[instr]
+            T[c.BitsMinus33Inv, i] = F.inv((r["bits"] - 33) % P)
+            T[c.LHS, i], T[c.RHS, i] = r["lhs"], r["rhs"]
+            T[c.LhsInv, i], T[c.RhsInv, i] = inv_or_zero(r["lhs"]), inv_or_zero(r["rhs"])
+            T[c.Result, i], T[c.LookupMultiplicity, i] = r["result"], r["mult"]
+            i += 1
+    pad_ci, pad_lhs, pad_lhs_inv, pad_result = OP_SPLIT, 0, 0, 0
+    if i:
+        pad_ci, pad_lhs, pad_lhs_inv, pad_result = T[c.CI, i - 1], T[c.LHS, i - 1], T[c.LhsInv, i - 1], T[c.Result, i - 1]
+        if pad_ci == OPCODES["lt"]:
+            pad_result = 2
+    for k in range(i, n):
+        T[c.CI, k], T[c.LHS, k], T[c.LhsInv, k], T[c.Result, k] = pad_ci, pad_lhs, pad_lhs_inv, pad_result
+        T[c.BitsMinus33Inv, k] = F.inv((-33) % P)
 
     fill_derived_main_columns(T)
-    return T, program_digest, public_output
+    return T, ex.digest, ex.output
 
 
-def padded_height(words, public_input=()):
-    """AlgebraicExecutionTrace::padded_height (aet.rs:99-135) for the supported subset"""
-    rows, os_entries, _, _, _ = run(list(words), public_input)
-    padded_len = -(-(len(words) + 1) // 10) * 10
-    hash_len = 6 * (padded_len // 10)
-    cascade = set()
-    sponge = [0] * 16
-    pp = (list(words) + [1] + [0] * 10)[:padded_len]
-    for c0 in range(0, padded_len, 10):
-        sponge[:10] = pp[c0:c0 + 10]
-        tr = tip5_trace(sponge)
-        for row in tr[:-1]:
-            for e in row[:4]:
-                cascade.update(limbs16(e))
-        sponge = list(tr[-1])
-    h = max(padded_len, len(rows), len(os_entries), hash_len, len(cascade), 256)
+def padded_height(words, public_input=(), secret_input=(), initial_ram=None):
+    """AlgebraicExecutionTrace::padded_height (aet.rs:99-135)"""
+    h = max(table_heights(list(words), execute(list(words), public_input, secret_input, initial_ram)).values())
     p2 = 1
     while p2 < h: p2 <<= 1
     return p2

@@ -32,12 +32,12 @@ BRANCHY = """
 _CACHE = {}
 
 
-def tables(program, public_input, n=None):
-    key = (program, tuple(public_input), n)
+def tables(program, public_input, n=None, secret_input=()):
+    key = (program, tuple(public_input), n, tuple(secret_input))
     if key not in _CACHE:
         words = tg.assemble(program)
-        ph = tg.padded_height(words, public_input)
-        T, digest, out = tg.main_table(words, public_input, n or ph)
+        ph = tg.padded_height(words, public_input, secret_input)
+        T, digest, out = tg.main_table(words, public_input, n or ph, secret_input)
         _CACHE[key] = (T, digest, out, ph, np.array(T.tolist(), dtype=np.uint64))
     return _CACHE[key]
 

@@ -1,0 +1,162 @@
+"""The oracle's VM restatement (oracle/tracegen.execute: 41 of the 46 instructions) and the fill of ALL nine tables from an
+execution — u32 sections, RAM table with its Bezout coefficients, hash table in all three modes, op-stack underflow, jump
+stack, cascade / lookup multiplicities — checked against the one authority available without the Rust toolchain: the AIR.
+A kitchen-sink program touching every restated instruction yields tables on which all 604 constraints vanish, whose
+cross-table arguments close, and whose proof verifies including the out-of-domain AIR identity."""
+import numpy as np
+import pytest
+
+from conftest import rand_bfes
+from oracle import corc, field as F, stark as S, tracegen as tg
+from test_fibonacci_program import tables
+
+P = F.P
+KITCHEN_SINK = """
+    push 1234567 push 89 lt pop 1
+    push 61680 push 65280 and pop 1
+    push 12345 push 54321 xor pop 1
+    push 1000 log_2_floor pop 1
+    push 10 push 3 pow pop 1
+    push 7 push 100 div_mod pop 2
+    push 255 pop_count pop 1
+    push 18446744069414584320 split pop 2
+    push 4294967299 split pop 2
+    push 0 push 0 lt pop 1
+    push 5 invert addi 7 pop 1
+    push 1 push 2 push 3 push 4 push 5 push 6 xx_add
+    push 7 push 8 push 9 xx_mul x_invert push 11 xb_mul pop 3
+    divine 2 add
+    push 2 swap 1 push 0 push 0 push 0 push 0 push 0
+    call count_up
+    pop 5 pop 2
+    push 11 push 22 push 33 push 100 write_mem 3 pop 1
+    push 102 read_mem 2 pop 3
+    push 555 read_mem 1 pop 2
+    push 44 push 101 write_mem 1 read_mem 1 pop 2
+    push 1 push 2 push 3 push 4 push 5 push 6 push 7 push 8 push 9 push 10 hash
+    dup 4 dup 4 dup 4 dup 4 dup 4 assert_vector
+    sponge_init
+    push 0 push 0 push 0 push 0 push 0 sponge_absorb
+    sponge_squeeze pop 5 pop 5
+    read_io 1 write_io 1
+    nop halt
+  count_up:
+    pick 5 addi 1 place 5 recurse_or_return
+"""
+SINK_INPUT, SINK_SECRET = [42], [0, 0]
+
+
+def _run(src, inp=(), sec=()):
+    ex = tg.execute(tg.assemble(src), inp, sec)
+    return ex
+
+
+def test_instruction_semantics():
+    assert _run("push 89 push 1234567 lt write_io 1 halt").output == [0]          # st0 < st1 ?
+    assert _run("push 1234567 push 89 lt write_io 1 halt").output == [1]
+    assert _run("push 61680 push 65280 and push 12345 push 54321 xor write_io 2 halt").output == [12345 ^ 54321, 61680 & 65280]
+    assert _run("push 10 push 3 pow push 7 push 100 div_mod write_io 3 halt").output == [100 % 7, 100 // 7, 3 ** 10]
+    assert _run("push 1000 log_2_floor push 255 pop_count write_io 2 halt").output == [8, 9]
+    assert _run("push 18446744069414584320 split write_io 2 halt").output == [0, (1 << 32) - 1]      # lo, hi of p - 1
+    assert _run("push 5 invert push 5 mul write_io 1 halt").output == [1]
+    x, y = (4, 5, 6), (7, 8, 9)
+    got = _run("push 6 push 5 push 4 push 9 push 8 push 7 xx_mul write_io 3 halt").output
+    assert tuple(got) == F.xmul(x, y)
+    assert _run("push 33 push 22 push 11 push 100 write_mem 3 pop 1 push 102 read_mem 3 pop 1 write_io 3 halt").output == [11, 22, 33]
+    assert _run("push 77 read_mem 1 pop 1 write_io 1 halt").output == [0]                            # untouched RAM reads 0
+    h = _run("push 10 push 9 push 8 push 7 push 6 push 5 push 4 push 3 push 2 push 1 hash write_io 5 halt").output
+    from oracle import tip5
+    assert h == [int(v) for v in tip5.hash_10(list(range(1, 11)))]                                   # st0 is the first input word
+    assert _run("divine 2 add write_io 1 halt", sec=[3, 4]).output == [7]
+    assert _run(KITCHEN_SINK, SINK_INPUT, SINK_SECRET).output == [42]
+
+
+@pytest.mark.parametrize("src,exc", [("push 18446744069414584320 push 1 lt halt", "u32"), ("push 0 push 5 div_mod halt", "zero"),
+                                     ("push 0 invert halt", "zero"), ("push 0 assert halt", "assert"),
+                                     ("sponge_squeeze halt", "sponge"), ("pop 1 halt", "shallow"), ("merkle_step halt", "restated")])
+def test_instruction_errors(src, exc):
+    with pytest.raises(ValueError, match=exc):
+        _run(src)
+
+
+def test_u32_sections_and_bezout_coefficients():
+    sec = tg._u32_section("lt", 5, 9, 3)                          # u32.rs:193-290
+    assert [r["bits"] for r in sec] == [0, 1, 2, 3, 4] and sec[0]["result"] == 1 and sec[0]["mult"] == 3 and sec[-1]["result"] == 2
+    assert tg._u32_section("pow", 3, 10, 1)[0]["result"] == 3 ** 10
+    assert tg._u32_section("log_2_floor", 1000, 0, 1)[0]["result"] == 9
+    assert tg._u32_section("lt", 0, 0, 1)[0]["result"] == 0
+    roots = [3, 5, 11, 1 << 40]
+    a, b = tg.bezout_coefficients(roots)                          # a * rp + b * rp' == 1   (ram.rs:162-214)
+    rp = [1]
+    for r in roots:
+        rp = tg._poly_mul(rp, [(-r) % P, 1])
+    fd = [(k * rp[k]) % P for k in range(1, len(rp))]
+    lhs = [0] * 8
+    for k, c in enumerate(tg._poly_mul(a, rp)):
+        lhs[k] = (lhs[k] + c) % P
+    for k, c in enumerate(tg._poly_mul(b, fd)):
+        lhs[k] = (lhs[k] + c) % P
+    assert lhs == [1] + [0] * 7
+
+
+def _sink_challenges(digest, out, seed=5):
+    rng = np.random.default_rng(seed)
+    sampled = [tuple(int(v) for v in rng.integers(0, P, 3, dtype=np.uint64)) for _ in range(59)]
+    return S.derive_challenges(sampled, S.Claim(digest, list(SINK_INPUT), list(out)))
+
+
+def test_kitchen_sink_satisfies_every_constraint():
+    T, digest, out, ph, main = tables(KITCHEN_SINK, SINK_INPUT, None, SINK_SECRET)
+    words = tg.assemble(KITCHEN_SINK)
+    heights = tg.table_heights(words, tg.execute(words, SINK_INPUT, SINK_SECRET))
+    assert ph == 2048 and heights["u32"] > 100 and heights["ram"] == 8 and heights["hash"] > 6 * 22
+    ch = _sink_challenges(digest, out)
+    B = corc.aux_extend(main, ch)
+    n = main.shape[1]
+    A = [[tuple(int(v) for v in B[q][i]) for i in range(n)] for q in range(91)]
+    assert tg.failing_constraints(T, A, ch) == []
+    from airgen.columns import MAIN
+    for tab, col, row in (("u32", "Result", 3), ("ram", "RamValue", 2), ("hash", "State5", 140), ("processor", "HV0", 40),
+                          ("ram", "BezoutCoefficientPolynomialCoefficient0", 1), ("op_stack", "FirstUnderflowElement", 7)):
+        T2 = T.copy()
+        idx = getattr(MAIN[tab], col)
+        T2[idx, row] = (int(T2[idx, row]) + 1) % P
+        assert tg.failing_constraints(T2, A, ch) != [], (tab, col)
+
+
+def sink_instance(security, ldt, seed=31):
+    st = S.Stark(security, 2, ldt)
+    ph = tables(KITCHEN_SINK, SINK_INPUT, None, SINK_SECRET)[3]
+    d = st.derive(ph)
+    T, digest, out, _, main = tables(KITCHEN_SINK, SINK_INPUT, d["trace_len"], SINK_SECRET)
+    n, h = d["trace_len"], d["num_trace_randomizers"]
+    rng = np.random.default_rng(seed)
+    mrand, arand, rcol = rand_bfes(rng, (379, h)), rand_bfes(rng, (91, h, 3)), rand_bfes(rng, (n, 3))
+    qrand = rand_bfes(rng, (d["num_quotient_randomizer_coefficients"], 3))
+
+    def cpu_extend(ch):
+        return corc.aux_extend(main, np.asarray(ch, dtype=np.uint64).reshape(63, 3), rcol), arand
+    return st, S.Claim(digest, list(SINK_INPUT), list(out)), main, mrand, cpu_extend, qrand, ph, rcol, arand
+
+
+def test_oracle_proof_of_kitchen_sink_verifies_with_air_check():
+    st, claim, main, mrand, cpu_extend, qrand, ph, _, _ = sink_instance(4, "fri")
+    proof, _ = S.prove(st, claim, main, mrand, cpu_extend, qrand, padded_height=ph)
+    assert S.verify(st, claim, proof, check_air=True)
+
+
+@pytest.mark.gpu
+def test_gpu_kitchen_sink_device_extension_and_proof(backend):
+    import tvm_b200
+    st, claim, main, mrand, cpu_extend, qrand, ph, rcol, arand = sink_instance(4, "fri")
+    ch = np.array(_sink_challenges(claim.program_digest, claim.output), dtype=np.uint64)
+    assert np.array_equal(backend.aux_extend(main, ch, rcol), corc.aux_extend(main, ch, rcol))   # real RAM / u32 / hash rows
+
+    def device_extend(c):
+        return backend.aux_extend(main, np.asarray(c, dtype=np.uint64).reshape(63, 3), rcol), arand
+    got = backend.prove((claim.program_digest, claim.input, claim.output), main, mrand, device_extend, qrand,
+                        security_level=4, log2_expansion=2, padded_height=ph, ldt_choice=tvm_b200.LDT_FRI)
+    got = [int(v) for v in got]
+    assert S.verify(st, claim, got, check_air=True)
+    want, _ = S.prove(st, claim, main, mrand, cpu_extend, qrand, padded_height=ph)
+    assert got == want
