@@ -1,4 +1,4 @@
-"""Trace generation: a restatement of the VM (41 of the 46 instructions), of the master main table (fill + pad + derived
+"""Trace generation: a restatement of the VM (all 46 instructions), of the master main table (fill + pad + derived
 columns) and of the master auxiliary table (`extend`), so that AIR-SATISFYING instances exist in this repository — with
 them the oracle verifier runs with `check_air=True` (the out-of-domain AIR / quotient identity, stark.rs:1469-1540), which
 synthetic tables can never pass.
@@ -65,12 +65,11 @@ def lookup16(v): return (lookup8(v >> 8) << 8) + lookup8(v & 0xFF)       # casca
 
 
 # ---- a VM (vm.rs:361-1100) -----------------------------------------------------------------------------------------
-# Everything except merkle_step, merkle_step_mem, sponge_absorb_mem, b_horner_step, x_horner_step.
+# All 46 instructions.
 from .isa_words import OPCODES, HAS_ARG, assemble   # noqa: E402
 
 _NAME = {v: k for k, v in OPCODES.items()}
-UNSUPPORTED = {"merkle_step", "merkle_step_mem", "sponge_absorb_mem", "b_horner_step", "x_horner_step"}
-SUPPORTED = set(OPCODES) - UNSUPPORTED
+SUPPORTED = set(OPCODES)
 U32_MAX = (1 << 32) - 1
 
 
@@ -86,12 +85,12 @@ class Execution:
         self.ram_calls = []              # (clk, is_write, pointer, value)                    ram.rs:38-60
 
 
-def execute(words, public_input=(), secret_input=(), initial_ram=None):
-    """VM::run with full tracing (vm.rs:361-1000) -> Execution"""
+def execute(words, public_input=(), secret_input=(), initial_ram=None, secret_digests=()):
+    """VM::run with full tracing (vm.rs:361-1111) -> Execution"""
     ex = Execution()
     ex.digest = [int(v) for v in tip5.hash_varlen(words)]
     stack = list(reversed(ex.digest)) + [0] * 11                # OpStack::new: list index 0 = deepest element
-    jump_stack, inp, sec = [], list(public_input), list(secret_input)
+    jump_stack, inp, sec, digests = [], list(public_input), list(secret_input), [list(d) for d in secret_digests]
     ram = dict(initial_ram or {})
     sponge = None
     ex.multiplicities = [0] * len(words)
@@ -119,6 +118,18 @@ def execute(words, public_input=(), secret_input=(), initial_ram=None):
                 hv[0] = inv_or_zero((st(0) >> 32) - U32_MAX)
         elif name == "eq":
             hv[0] = inv_or_zero(st(1) - st(0))
+        elif name == "sponge_absorb_mem":
+            hv[:6] = [ram.get((st(0) + k) % P, 0) for k in range(4, 10)]
+        elif name == "merkle_step":
+            hv[:5] = digests[0] if digests else [0] * 5
+            hv[5] = st(5) % 2
+        elif name == "merkle_step_mem":
+            hv[:5] = [ram.get((st(7) + k) % P, 0) for k in range(5)]
+            hv[5] = st(5) % 2
+        elif name == "b_horner_step":
+            hv[0] = ram.get(st(5), 0)
+        elif name == "x_horner_step":
+            hv[2], hv[1], hv[0] = ram.get(st(5), 0), ram.get((st(5) - 1) % P, 0), ram.get((st(5) - 2) % P, 0)
         ex.rows.append(dict(clk=clk, ip=ip, ci=words[ip], nia=nia, jsp=len(jump_stack),
                             jso=jump_stack[-1][0] if jump_stack else 0, jsd=jump_stack[-1][1] if jump_stack else 0,
                             st=[st(i) for i in range(16)], osp=len(stack), hv=hv))
@@ -161,6 +172,26 @@ def execute(words, public_input=(), secret_input=(), initial_ram=None):
 
         def pop_x(): return (pop(), pop(), pop())
 
+        def ram_read(ptr):
+            v = ram.get(ptr % P, 0)
+            ex.ram_calls.append((clk, 0, ptr % P, v))
+            return v
+
+        def merkle_step(sibling):                                   # vm.rs:1026-1062
+            need_u32(5)
+            node_index = st(5)
+            acc = [pop() for _ in range(5)]
+            left, right = (acc, sibling) if node_index % 2 == 0 else (sibling, acc)
+            out = permutation(left + right + [1] * 6)[-1][:5]
+            for e in reversed(out): push(e)
+            stack[len(stack) - 1 - 5] = node_index // 2
+            u32_call("split", node_index, node_index // 2)
+
+        def horner_step(coefficient):                               # vm.rs:1064-1111
+            x = (st(0), st(1), st(2))
+            acc = F.xadd(F.xmul((st(7), st(8), st(9)), x), coefficient)
+            for k in range(3): stack[len(stack) - 1 - (7 + k)] = acc[k]
+
         def push_x(x):
             for c in reversed(x): push(c)
 
@@ -199,9 +230,7 @@ def execute(words, public_input=(), secret_input=(), initial_ram=None):
         elif name == "read_mem":
             ptr = pop()
             for _ in range(arg):
-                v = ram.get(ptr, 0)
-                ex.ram_calls.append((clk, 0, ptr, v))
-                push(v)
+                push(ram_read(ptr))
                 ptr = (ptr - 1) % P
             push(ptr)
         elif name == "write_mem":
@@ -226,6 +255,37 @@ def execute(words, public_input=(), secret_input=(), initial_ram=None):
             if sponge is None: raise ValueError("sponge not initialized")
             sponge[:10] = [pop() for _ in range(10)]
             sponge = list(permutation(sponge, OPCODES["sponge_absorb"])[-1])
+        elif name == "sponge_absorb_mem":                          # vm.rs:699-729
+            if sponge is None: raise ValueError("sponge not initialized")
+            ptr = pop()
+            for i in range(10):
+                sponge[i] = ram_read(ptr)
+                ptr = (ptr + 1) % P
+                if i < 4: stack[len(stack) - 1 - i] = sponge[i]
+            push(ptr)
+            sponge = list(permutation(sponge, OPCODES["sponge_absorb"])[-1])
+        elif name == "merkle_step":
+            if not digests: raise IndexError("secret digests exhausted")
+            merkle_step(digests.pop(0))
+        elif name == "merkle_step_mem":
+            need_u32(5)
+            ptr = st(7)
+            sibling = []
+            for _ in range(5):
+                sibling.append(ram_read(ptr))
+                ptr = (ptr + 1) % P
+            stack[len(stack) - 1 - 7] = ptr
+            merkle_step(sibling)
+        elif name == "b_horner_step":
+            ptr = st(5)
+            c0 = ram_read(ptr)
+            stack[len(stack) - 1 - 5] = (ptr - 1) % P
+            horner_step((c0, 0, 0))
+        elif name == "x_horner_step":
+            ptr = st(5)
+            c2 = ram_read(ptr); c1 = ram_read(ptr - 1); c0 = ram_read(ptr - 2)
+            stack[len(stack) - 1 - 5] = (ptr - 3) % P
+            horner_step((c0, c1, c2))
         elif name == "sponge_squeeze":
             if sponge is None: raise ValueError("sponge not initialized")
             for i in reversed(range(10)): push(sponge[i])
@@ -438,13 +498,13 @@ def table_heights(words, ex):
 
 
 # ---- main table -------------------------------------------------------------------------------------
-def main_table(words, public_input, n, secret_input=(), initial_ram=None):
+def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret_digests=()):
     """[379][n] canonical ints: MasterMainTable::new + pad (master_table.rs:881-1004).
     -> (table, program digest, public output)"""
     assert n >= 256 and n & (n - 1) == 0
     T = np.zeros((NUM_MAIN, n), dtype=object)
     program = list(words)
-    ex = execute(program, public_input, secret_input, initial_ram)
+    ex = execute(program, public_input, secret_input, initial_ram, secret_digests)
     rows, plen = ex.rows, len(ex.rows)
     heights = table_heights(program, ex)
     assert max(heights.values()) <= n, f"table heights {heights} exceed {n}"
@@ -628,9 +688,9 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None):
     return T, ex.digest, ex.output
 
 
-def padded_height(words, public_input=(), secret_input=(), initial_ram=None):
+def padded_height(words, public_input=(), secret_input=(), initial_ram=None, secret_digests=()):
     """AlgebraicExecutionTrace::padded_height (aet.rs:99-135)"""
-    h = max(table_heights(list(words), execute(list(words), public_input, secret_input, initial_ram)).values())
+    h = max(table_heights(list(words), execute(list(words), public_input, secret_input, initial_ram, secret_digests)).values())
     p2 = 1
     while p2 < h: p2 <<= 1
     return p2

@@ -1,7 +1,7 @@
-"""The oracle's VM restatement (oracle/tracegen.execute: 41 of the 46 instructions) and the fill of ALL nine tables from an
+"""The oracle's VM restatement (oracle/tracegen.execute: all 46 instructions) and the fill of ALL nine tables from an
 execution — u32 sections, RAM table with its Bezout coefficients, hash table in all three modes, op-stack underflow, jump
 stack, cascade / lookup multiplicities — checked against the one authority available without the Rust toolchain: the AIR.
-A kitchen-sink program touching every restated instruction yields tables on which all 604 constraints vanish, whose
+Two programs that together execute every instruction yield tables on which all 604 constraints vanish, whose
 cross-table arguments close, and whose proof verifies including the out-of-domain AIR identity."""
 import numpy as np
 import pytest
@@ -45,6 +45,26 @@ KITCHEN_SINK = """
 """
 SINK_INPUT, SINK_SECRET = [42], [0, 0]
 
+# Horner evaluation from memory, absorbing from memory, a two-level Merkle walk (one sibling divined, one from memory)
+MEMORY_AND_MERKLE = """
+    push 0 push 0 push 0 push 0 push 202 push 0 push 0 push 4 push 3 push 2
+    b_horner_step b_horner_step b_horner_step
+    pop 5 pop 2 write_io 3
+    push 0 push 0 push 0 push 0 push 305 push 0 push 0 push 4 push 3 push 2
+    x_horner_step x_horner_step
+    pop 5 pop 2 write_io 3
+    sponge_init push 400 sponge_absorb_mem pop 1
+    sponge_squeeze write_io 5 pop 5
+    push 0 push 0 push 0 push 0 push 500 push 0 push 6
+    push 15 push 14 push 13 push 12 push 11
+    merkle_step merkle_step_mem
+    write_io 5 pop 5 pop 2
+    halt
+"""
+MEM_RAM = {200: 7, 201: 8, 202: 9, 300: 1, 301: 2, 302: 3, 303: 4, 304: 5, 305: 6,
+           **{400 + k: 100 + k for k in range(10)}, **{500 + k: 900 + k for k in range(5)}}
+MEM_SIBLING = [21, 22, 23, 24, 25]
+
 
 def _run(src, inp=(), sec=()):
     ex = tg.execute(tg.assemble(src), inp, sec)
@@ -73,10 +93,32 @@ def test_instruction_semantics():
 
 @pytest.mark.parametrize("src,exc", [("push 18446744069414584320 push 1 lt halt", "u32"), ("push 0 push 5 div_mod halt", "zero"),
                                      ("push 0 invert halt", "zero"), ("push 0 assert halt", "assert"),
-                                     ("sponge_squeeze halt", "sponge"), ("pop 1 halt", "shallow"), ("merkle_step halt", "restated")])
+                                     ("sponge_squeeze halt", "sponge"), ("pop 1 halt", "shallow")])
 def test_instruction_errors(src, exc):
     with pytest.raises(ValueError, match=exc):
         _run(src)
+
+
+def test_memory_and_merkle_program():
+    from oracle import tip5
+    words = tg.assemble(MEMORY_AND_MERKLE)
+    ex = tg.execute(words, [], [], MEM_RAM, [MEM_SIBLING])
+    x = (2, 3, 4)
+    assert tuple(ex.output[:3]) == F.xadd(F.xmul(F.xadd(F.xmul((9, 0, 0), x), (8, 0, 0)), x), (7, 0, 0))      # 7 + 8x + 9x^2
+    assert tuple(ex.output[3:6]) == F.xadd(F.xmul((4, 5, 6), x), (1, 2, 3))
+    d1 = [int(v) for v in tip5.hash_pair([11, 12, 13, 14, 15], MEM_SIBLING)]        # node 6 is a left child
+    assert ex.output[-5:] == [int(v) for v in tip5.hash_pair([900, 901, 902, 903, 904], d1)]   # node 3 is a right child
+    with pytest.raises(IndexError):
+        tg.execute(words, [], [], MEM_RAM, [])
+    n = tg.padded_height(words, [], [], MEM_RAM, [MEM_SIBLING])
+    T, digest, out = tg.main_table(words, [], n, [], MEM_RAM, [MEM_SIBLING])
+    rng = np.random.default_rng(6)
+    sampled = [tuple(int(v) for v in rng.integers(0, P, 3, dtype=np.uint64)) for _ in range(59)]
+    ch = S.derive_challenges(sampled, S.Claim(digest, [], list(out)))
+    B = corc.aux_extend(np.array(T.tolist(), dtype=np.uint64), ch)
+    assert tg.failing_constraints(T, [[tuple(int(v) for v in B[q][i]) for i in range(n)] for q in range(91)], ch) == []
+    executed = {tg._NAME[r["ci"]] for r in ex.rows} | {tg._NAME[r["ci"]] for r in _run(KITCHEN_SINK, SINK_INPUT, SINK_SECRET).rows}
+    assert executed | {"skiz", "return", "recurse", "assert", "eq", "mul"} == set(tg.OPCODES)   # the rest: test_fibonacci_program
 
 
 def test_u32_sections_and_bezout_coefficients():
