@@ -127,6 +127,7 @@ int tvm_merkle_build(tvm_ctx *ctx, const uint64_t *leaves /* [nleaves][5] */, si
  *      d_out: 3 planes (coordinate d at d_out + d*out_stride) of r*n words, coset-major order:
  *      d_out[c*n + k] = quotient value at domain index i = c + r*k. ----------------------- */
 #define TVM_NUM_MAIN_COLUMNS 379
+#define TVM_NUM_MAIN_TABLE_COLUMNS 149 /* the nine tables' columns; 149..378 are degree-lowering columns */
 #define TVM_NUM_AUX_COLUMNS 91
 #define TVM_NUM_CHALLENGES 63
 #define TVM_NUM_CONSTRAINTS 604
@@ -194,6 +195,11 @@ int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, ui
  *      n = 2^log2_n rows.  May be called from inside tvm_aux_callback on the same or on another context. --- */
 int tvm_aux_extend(tvm_ctx *ctx, const uint64_t *main_trace, unsigned log2_n, const uint64_t *challenges,
                    const uint64_t *randomizer_column, uint64_t *aux_trace_out);
+/* DegreeLoweringTable::fill_derived_main_columns (generated in the reference: triton-constraint-builder/src/
+ * substitutions.rs:128-161, 237-300; called from MasterMainTable::new, master_table.rs:975-983): fills the 230
+ * degree-lowering columns 149..378 of main_trace [379][n] (canonical, column-major, host or device memory, IN PLACE) from
+ * the 149 table columns 0..148, which are not modified. */
+int tvm_fill_derived_main_columns(tvm_ctx *ctx, uint64_t *main_trace, unsigned log2_n);
 /* device time per stage of the last tvm_prove on this ctx, reference profiler labels; returns #stages */
 int tvm_last_prove_timings(const tvm_ctx *ctx, const char **names /*[20]*/, float *ms /*[20]*/);
 

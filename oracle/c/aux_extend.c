@@ -11,10 +11,11 @@
 #include "tvm_oracle.h"
 
 typedef struct {
-  const u64 *main_t; u64 *aux_t; const u64 *ch; size_t n, cur, nxt;
+  u64 *main_t; u64 *aux_t; const u64 *ch; size_t n, cur, nxt;
 } auxctx;
 
 static inline xfe xlift(u64 b) { xfe r = {b, 0, 0}; return r; }
+static inline u64 fneg(u64 a) { return fsub(0, a); }
 static inline xfe xneg(xfe a) { xfe r = {fsub(0, a.c0), fsub(0, a.c1), fsub(0, a.c2)}; return r; }
 static inline int xis_zero(xfe a) { return (a.c0 | a.c1 | a.c2) == 0; }
 static inline xfe xinv(xfe a) { u64 in[3] = {a.c0, a.c1, a.c2}, out[3]; orc_xinv(in, out); xfe r = {out[0], out[1], out[2]}; return r; }
@@ -39,11 +40,12 @@ static inline xfe ch_load(const auxctx *c, int i) { xfe r = {c->ch[3 * i], c->ch
 #define AN(col) aux_load(c, (col), c->nxt)
 #define CH(i) ch_load(c, (i))
 #define AW(col, v) aux_store(c, (col), c->cur, (v))
+#define MW(col, v) (c->main_t[(size_t)(col) * c->n + c->cur] = (v))
 #include "aux_extend_gen.inc"
 
 /* main_t: [379][n]; ch: [63][3]; aux_t: [91*3][n], column 90 (the batch randomizer) is left as the caller filled it */
 void orc_aux_extend(const u64 *main_t, size_t n, const u64 *ch, u64 *aux_t) {
-  auxctx c = {main_t, aux_t, ch, n, 0, 0};
+  auxctx c = {(u64 *)main_t, aux_t, ch, n, 0, 0};
   for (int level = 0; level < AUXGEN_NUM_LEVELS; level++)
     for (int q = 0; q < AUXGEN_NUM_BASE; q++) {
       if (AUXGEN_LEVEL[q] != level) continue;
@@ -64,4 +66,19 @@ void orc_aux_extend(const u64 *main_t, size_t n, const u64 *ch, u64 *aux_t) {
   }
   c.cur = n - 1;
   for (int k = 0; k < AUXGEN_NUM_DERIVED_TRAN; k++) aux_store(&c, AUXGEN_DERIVED_START_TRAN + k, n - 1, zero);
+}
+
+/* DegreeLoweringTable::fill_derived_main_columns (substitutions.rs:128-161): columns 149.. of main_t [379][n] from 0..148 */
+void orc_fill_derived_main(u64 *main_t, size_t n) {
+  auxctx c = {main_t, 0, 0, n, 0, 0};
+  for (size_t i = 0; i < n; i++) {
+    c.cur = c.nxt = i;
+    auxgen_derived_main_init(&c);
+    auxgen_derived_main_cons(&c);
+  }
+  for (size_t i = 0; i + 1 < n; i++) {
+    c.cur = i; c.nxt = i + 1;
+    auxgen_derived_main_tran(&c);
+  }
+  for (int k = 0; k < AUXGEN_NUM_DERIVED_MAIN_TRAN; k++) main_t[(size_t)(AUXGEN_DERIVED_MAIN_START_TRAN + k) * n + n - 1] = 0;
 }

@@ -61,4 +61,5 @@ void orc_set_num_threads(int n);   /* OpenMP team size of the parallel loops (no
 #endif
 /* auxiliary-table extension from the AIR-derived rules (aux_extend.c); Montgomery form, column-major planes */
 void orc_aux_extend(const u64 *main_t, size_t n, const u64 *ch, u64 *aux_t);
+void orc_fill_derived_main(u64 *main_t, size_t n);
 #endif

@@ -180,3 +180,12 @@ def aux_extend(main_table, challenges, randomizer_column=None):
         aux[270:273] = to_mont(np.ascontiguousarray(np.asarray(randomizer_column, dtype=np.uint64).reshape(n, 3).T))
     lib().orc_aux_extend(_p(T), ctypes.c_size_t(n), _p(ch), _p(aux))
     return np.ascontiguousarray(from_mont(aux).reshape(91, 3, n).transpose(0, 2, 1))
+
+
+def fill_derived_main(main_table):
+    """DegreeLoweringTable::fill_derived_main_columns through the generated rules: [379][n] canonical -> copy with columns
+    149..378 recomputed from columns 0..148"""
+    T = to_mont(np.ascontiguousarray(main_table, dtype=np.uint64))
+    assert T.shape[0] == 379
+    lib().orc_fill_derived_main(_p(T), ctypes.c_size_t(T.shape[1]))
+    return from_mont(T).reshape(main_table.shape)

@@ -97,3 +97,14 @@ def test_derived_columns_of_the_last_row_are_zero():
     B = corc.aux_extend(np.array(T.tolist(), dtype=np.uint64), _challenges(9))
     assert not B[49:90, -1].any() and B[49:90, :-1].any()
     assert not B[90].any()                          # no randomizer column supplied
+
+
+@pytest.mark.parametrize("program,inp", [(FIBONACCI, [7]), (BRANCHY, [5, 7])])
+def test_generated_derived_main_columns_equal_the_evaluated_substitutions(program, inp):
+    # tracegen.fill_derived_main_columns evaluates the substitution circuits node by node; the generated straight-line
+    # code (the text the device compiles) must reproduce all 230 columns from the 149 table columns
+    main = tables(program, inp)[4]
+    scrambled = main.copy()
+    scrambled[149:] = 12345
+    assert np.array_equal(corc.fill_derived_main(scrambled), main)
+    assert main[149:169].any() and main[169:].any() and not main[169:, -1].any()      # last row of the tran section is 0

@@ -63,3 +63,15 @@ def test_prove_halt_with_device_side_extension(backend):
 
 def test_prove_fibonacci_with_device_side_extension(backend):
     _prove_with_device_extension(backend, FIBONACCI, [7], 8, "stir")
+
+
+def test_device_fills_derived_main_columns(backend):
+    main = tables(FIBONACCI, [7])[4]                         # a real table: the substitutions of live constraints
+    got = main.copy()
+    got[149:] = 7
+    backend.fill_derived_main_columns(got)
+    assert np.array_equal(got, main)
+    rnd = rand_bfes(np.random.default_rng(3), (379, 1024))    # and arbitrary field elements in the 149 table columns
+    want = corc.fill_derived_main(rnd)
+    backend.fill_derived_main_columns(rnd)
+    assert np.array_equal(rnd, want)

@@ -299,7 +299,8 @@ def generate():
          " *     aux[i][q] = a * aux[i-1][q] + b",
          " * (initial value for i = 0).  Including file defines AUXGEN_FN, AUXGEN_ARGS, MC/MN (main row i-1 / i, Montgomery),",
          " * AC/AN (auxiliary row i-1 / i as xfe), CH (challenge as xfe), AW (store into the current row), AUXGEN_PASS (the",
-         " * argument forwarded to callees), AUXGEN_TOUCH (statement marking the argument used) and the field ops. */",
+         " * argument forwarded to callees), AUXGEN_TOUCH (statement marking the argument used), MW (store a base-field value",
+         " * into the current row of the main table) and the field ops. */",
          f"#define AUXGEN_NUM_BASE {NUM_BASE_AUX}",
          f"#define AUXGEN_NUM_LEVELS {nlev}",
          "static const int AUXGEN_LEVEL[AUXGEN_NUM_BASE] = {" + ", ".join(str(level[q]) for q in range(NUM_BASE_AUX)) + "};", ""]
@@ -349,6 +350,37 @@ def generate():
             L.append("    {")
             L += em.take()
             L.append(f"      AW({start + k}, xneg({em.ref_x(expr)}));")
+            L.append("    }")
+        L += ["}", ""]
+    # derived (degree-lowering) MAIN columns, substitutions.rs:128-161, 237-300: sections init | cons (single row, every
+    # row) and tran (rows i, i+1; the last row stays 0).  Base-field valued; a rule may read earlier derived columns of its
+    # own row and, in the transition section, the next row's columns of the earlier sections.
+    L.append(f"#define AUXGEN_NUM_BASE_MAIN {air.subst_col_start['init'][0]}")
+    for cat in CATEGORIES:
+        rules = air.main_subst[cat]
+        start = air.subst_col_start[cat][0]
+        dual = cat == "tran"
+        nb = Builder(dual=dual)
+        xf = Xform(nb)
+        L.append(f"#define AUXGEN_NUM_DERIVED_MAIN_{cat.upper()} {len(rules)}")
+        L.append(f"#define AUXGEN_DERIVED_MAIN_START_{cat.upper()} {start}")
+        if not rules: continue
+        L.append(f"AUXGEN_FN void auxgen_derived_main_{cat}(AUXGEN_ARGS) {{")
+        L.append("    AUXGEN_TOUCH;")
+        for k, rule in enumerate(rules):
+            own = (0, True, start + k)
+            assert own in inputs_of(rule)
+            expr = xf.copy(rule, {own: nb.b_constant(0)})
+            ins = inputs_of(expr.n)
+            assert all(is_main for (_, is_main, _) in ins), "main substitution reads an auxiliary column"
+            assert not {c for (row, _, c) in ins if row == 0 and c >= start + k}, "reads a later derived column of its row"
+            assert not {c for (row, _, c) in ins if row == 1 and c >= start}, "reads the next row's column of its own section"
+            em = Emitter("      ")
+            em.emit([expr.n])
+            assert not em.isx[id(expr.n)]
+            L.append("    {")
+            L += em.take()
+            L.append(f"      MW({start + k}, fneg({em.name[id(expr.n)]}));")
             L.append("    }")
         L += ["}", ""]
     text = "\n".join(L) + "\n"

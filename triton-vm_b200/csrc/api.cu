@@ -438,6 +438,29 @@ int tvm_aux_extend(tvm_ctx *ctx, const uint64_t *main_trace, unsigned log2_n, co
   TVM_API_END
 }
 
+int tvm_fill_derived_main_columns(tvm_ctx *ctx, uint64_t *main_trace, unsigned log2_n) {
+  if (!ctx || !main_trace) return TVM_ERR_INVALID_ARG;
+  if (log2_n > 26) return TVM_ERR_DOMAIN;
+  TVM_API_BEGIN(ctx)
+  const size_t n = (size_t)1 << log2_n, NM = TVM_NUM_MAIN_COLUMNS, NB = TVM_NUM_MAIN_TABLE_COLUMNS;
+  Ctx &c = *c__;
+  u64 *d_main = (u64 *)c.pool_alloc(NM * n * 8);
+  try {
+    TVM_CUDA(cudaMemcpyAsync(d_main, main_trace, NB * n * 8, cudaMemcpyDefault, c.stream));
+    to_mont_run(c, d_main, NB * n);
+    main_derived_run(c, d_main, n);
+    from_mont_run(c, d_main + NB * n, (NM - NB) * n);
+    TVM_CUDA(cudaMemcpyAsync(main_trace + NB * n, d_main + NB * n, (NM - NB) * n * 8, cudaMemcpyDefault, c.stream));
+    TVM_CUDA(cudaStreamSynchronize(c.stream));
+  } catch (...) {
+    cudaStreamSynchronize(c.stream);
+    c.pool_release(d_main);
+    throw;
+  }
+  c.pool_release(d_main);
+  TVM_API_END
+}
+
 int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height, const uint64_t *main_trace,
               const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user, const uint64_t *quot_rand, uint64_t *proof_out,
               size_t *proof_len) {

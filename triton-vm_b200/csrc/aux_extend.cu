@@ -27,7 +27,7 @@ namespace tvm {
 namespace {
 
 struct auxctx {
-  const u64 *main_t;
+  u64 *main_t;     // written only by the derived-main-column kernels
   u64 *aux_t;
   const u64 *ch;
   size_t n, cur, nxt;
@@ -53,6 +53,7 @@ TVM_D xfe ch_load(const auxctx &c, int i) { return xmake(c.ch[3 * i], c.ch[3 * i
 #define AN(col) aux_load(c, (col), c.nxt)
 #define CH(i) ch_load(c, (i))
 #define AW(col, v) aux_store(c, (col), c.cur, (v))
+#define MW(col, v) (c.main_t[(size_t)(col) * c.n + c.cur] = (v))
 #include "aux_gen/aux_extend_gen.inc"
 #undef MC
 #undef MN
@@ -60,6 +61,7 @@ TVM_D xfe ch_load(const auxctx &c, int i) { return xmake(c.ch[3 * i], c.ch[3 * i
 #undef AN
 #undef CH
 #undef AW
+#undef MW
 
 constexpr int AUX_CHUNK = 256;
 
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(AUX_CHUNK) aux_scan_kernel(AuxScanArgs p) {
   m.a = xone();
   m.b = xzero();
   if (i < p.n) {
-    auxctx c{p.main_t, p.aux_t, p.ch, p.n, i ? i - 1 : 0, i};
+    auxctx c{const_cast<u64 *>(p.main_t), p.aux_t, p.ch, p.n, i ? i - 1 : 0, i};
     xfe a = xone(), b = xzero();
     if (i == 0) {                       // the initial constraint fixes row 0: constant map
       auxgen_init(q, c, &b);
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(AUX_CHUNK) aux_scan_kernel(AuxScanArgs p) {
   } else if (i < p.n) {
     const u64 *vi = p.vin + slot * 3;
     xfe v = xadd(xmul(m.a, xmake(vi[0], vi[1], vi[2])), m.b);
-    auxctx c{p.main_t, p.aux_t, p.ch, p.n, i, i};
+    auxctx c{const_cast<u64 *>(p.main_t), p.aux_t, p.ch, p.n, i, i};
     aux_store(c, q, i, v);
   }
 }
@@ -162,11 +164,29 @@ __global__ void aux_scan_tops_kernel(AuxScanArgs p) {
 __global__ void __launch_bounds__(128) aux_derived_kernel(const u64 *main_t, u64 *aux_t, const u64 *ch, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  auxctx c{main_t, aux_t, ch, n, i, i + 1};
+  auxctx c{const_cast<u64 *>(main_t), aux_t, ch, n, i, i + 1};
   if (i + 1 < n) {
     auxgen_derived_tran(c);
   } else {
     for (int k = 0; k < AUXGEN_NUM_DERIVED_TRAN; k++) aux_store(c, AUXGEN_DERIVED_START_TRAN + k, i, xzero());
+  }
+}
+
+// DegreeLoweringTable::fill_derived_main_columns (substitutions.rs:128-161, 237-300): main columns 149..378 from 0..148.
+// Sections init | cons read their own row (pass 0, every row); section tran reads rows i and i+1 including the next row's
+// init / cons columns (pass 1, after pass 0 has completed; the last row's tran columns are 0).
+template <int PASS>
+__global__ void __launch_bounds__(128) main_derived_kernel(u64 *main_t, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auxctx c{main_t, nullptr, nullptr, n, i, PASS ? i + 1 : i};
+  if (PASS == 0) {
+    auxgen_derived_main_init(c);
+    auxgen_derived_main_cons(c);
+  } else if (i + 1 < n) {
+    auxgen_derived_main_tran(c);
+  } else {
+    for (int k = 0; k < AUXGEN_NUM_DERIVED_MAIN_TRAN; k++) main_t[(size_t)(AUXGEN_DERIVED_MAIN_START_TRAN + k) * n + i] = 0;
   }
 }
 
@@ -203,6 +223,15 @@ void aux_extend_run(Ctx &c, const u64 *d_main, size_t n, const u64 *d_ch, u64 *d
   }
   aux_derived_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(d_main, d_aux, d_ch, n);
   c.launches++;
+  TVM_CUDA(cudaGetLastError());
+}
+
+// d_main [379][n] Montgomery, columns 149.. overwritten
+void main_derived_run(Ctx &c, u64 *d_main, size_t n) {
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  main_derived_kernel<0><<<grid, 128, 0, c.stream>>>(d_main, n);
+  main_derived_kernel<1><<<grid, 128, 0, c.stream>>>(d_main, n);
+  c.launches += 2;
   TVM_CUDA(cudaGetLastError());
 }
 

@@ -59,6 +59,7 @@ void air_quotient_run(Ctx &c, const u64 *d_main, size_t main_stride, const u64 *
 size_t aux_extend_scratch_words(size_t n);
 void aux_extend_run(Ctx &c, const u64 *d_main, size_t n, const u64 *d_ch, u64 *d_aux, u64 *d_scratch);
 void interleave3_from_mont_run(Ctx &c, const u64 *in, u64 *out, size_t n, size_t ncols);
+void main_derived_run(Ctx &c, u64 *d_main, size_t n);   // main columns 149..378 from 0..148, [379][n] Montgomery
 int translate_exception(Ctx *c);
 
 }  // namespace tvm

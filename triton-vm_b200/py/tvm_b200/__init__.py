@@ -109,6 +109,7 @@ _SIGNATURES = {
     "tvm_derive_domains": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_uint64, ctypes.POINTER(Domains)]),
     "tvm_prove": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, _u64p, _u64p,
                                  AUX_CALLBACK, _vp, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
+    "tvm_fill_derived_main_columns": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint]),
     "tvm_aux_extend": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint, _u64p, _u64p, _u64p]),
     "tvm_last_prove_timings": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]),
     "tvm_air_quotient_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _u64p, _u64p, ctypes.c_uint,
@@ -241,6 +242,17 @@ class Backend:
         self._chk(self._l.tvm_merkle_build(self._h, lp, n, nodes.ctypes.data_as(_u64p) if want_nodes else None,
                                            root.ctypes.data_as(_u64p)))
         return (root, nodes) if want_nodes else root
+
+    def fill_derived_main_columns(self, main_trace):
+        """DegreeLoweringTable::fill_derived_main_columns IN PLACE: main_trace [379, n] (writable C-contiguous numpy uint64
+        array or contiguous torch tensor, host or this GPU); columns 149.. are overwritten from columns 0..148."""
+        if isinstance(main_trace, np.ndarray):
+            assert main_trace.dtype == np.uint64 and main_trace.flags["C_CONTIGUOUS"] and main_trace.flags["WRITEABLE"]
+        keep, mp, shape = _u64_arg(main_trace)
+        assert len(shape) == 2 and shape[0] == NUM_MAIN_COLUMNS and shape[1] & (shape[1] - 1) == 0
+        self._chk(self._l.tvm_fill_derived_main_columns(self._h, mp, shape[1].bit_length() - 1))
+        del keep
+        return main_trace
 
     def aux_extend(self, main_trace, challenges, randomizer_column=None, out=None):
         """MasterMainTable::extend on the device: main_trace [379, n] canonical (numpy, or a contiguous torch tensor on
