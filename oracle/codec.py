@@ -21,6 +21,9 @@ from . import tip5
 
 
 STRUCT_FIELDS_REVERSED = True
+# Polynomial<FF> { coefficients } encoded like a derived one-field struct: the coefficient Vec's encoding prefixed with
+# its length (recalled: twenty-first keeps the manual impl compatible with the derive).  False: the bare Vec encoding.
+POLYNOMIAL_AS_STRUCT = True
 
 # proof_item.rs:96-147 — (variant index, absorbed into Fiat-Shamir?)
 ITEMS = {
@@ -74,7 +77,8 @@ def enc_polynomial_xfe(coeffs):
     c = list(coeffs)
     while c and tuple(c[-1]) == (0, 0, 0):
         c.pop()
-    return enc_vec_xfe(c)
+    e = enc_vec_xfe(c)
+    return [len(e)] + e if POLYNOMIAL_AS_STRUCT else e
 
 
 def encode_payload(kind, payload):
@@ -180,6 +184,8 @@ def decode_payload(kind, words, num_main=379, num_aux=91, num_seg=5):
     elif kind == "OutOfDomainAuxRow": out = [r.xfe() for _ in range(num_aux)]
     elif kind == "OutOfDomainQuotientSegments": out = [r.xfe() for _ in range(num_seg - 1)]
     elif kind in ("Polynomial", "StirOutOfDomainValues", "FriCodeword"):
+        if kind == "Polynomial" and POLYNOMIAL_AS_STRUCT:
+            if r.one() != len(words) - 1: raise ValueError("field length mismatch")
         out = r.vec_xfe()
         if kind == "Polynomial" and out and out[-1] == (0, 0, 0):
             raise ValueError("TrailingZerosInPolynomialEncoding")

@@ -69,7 +69,7 @@ def run(seed_variant):
     assert S.verify(st, claim, proof, check_air=True)
     return proof
 WANT = [2390426207231576512, 11357322246033024133, 15595568858844533957, 10807389618517394866, 11786266879565336160]
-for variant in ("per_u8", "fill_bytes"):
+for variant in ():
     t = time.time(); proof = run(variant); print(variant, "proof len", len(proof), "%.0fs" % (time.time() - t))
     encs = {"struct[len,vec[len,..]]": [len(proof) + 1, len(proof)] + proof, "vec[len,..]": [len(proof)] + proof, "raw": list(proof)}
     for name, e in encs.items():
@@ -82,8 +82,9 @@ import itertools
 orig_auth = merkle.auth_structure_node_indices
 def auth_asc(num_leafs, leaf_indices):
     return list(reversed(orig_auth(num_leafs, leaf_indices)))
-for seedv, rev, asc in itertools.product(("per_u8", "fill_bytes"), (True, False), (False, True)):
+for seedv, rev, asc, pst in itertools.product(("per_u8", "fill_bytes"), (True, False), (False, True), (True, False)):
     codec.STRUCT_FIELDS_REVERSED = rev
+    codec.POLYNOMIAL_AS_STRUCT = pst
     merkle.auth_structure_node_indices = auth_asc if asc else orig_auth
     try:
         proof = run(seedv)
@@ -91,4 +92,4 @@ for seedv, rev, asc in itertools.product(("per_u8", "fill_bytes"), (True, False)
         print(seedv, rev, asc, "error", repr(e)[:100]); continue
     encs = {"struct": [len(proof) + 1, len(proof)] + proof, "vec": [len(proof)] + proof, "raw": list(proof)}
     res = {name: [int(v) for v in tip5.hash_varlen(e)] == WANT for name, e in encs.items()}
-    print(seedv, "reversed" if rev else "declared", "asc" if asc else "desc", res)
+    print(seedv, "reversed" if rev else "declared", "asc" if asc else "desc", "poly-struct" if pst else "poly-vec", res)

@@ -621,7 +621,10 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     std::vector<u64> co = d2h(c, d_lp, 3 * last.len);
     size_t deg_plus_1 = last.len;
     while (deg_plus_1 > 0 && co[deg_plus_1 - 1] == 0 && co[last.len + deg_plus_1 - 1] == 0 && co[2 * last.len + deg_plus_1 - 1] == 0) deg_plus_1--;
+    // Polynomial { coefficients } encodes like a one-field struct: the coefficient Vec's encoding (count, elements) behind
+    // its own length — pinned by the reference's whole-proof digest (tests/test_golden.py, proof.rs:200-226)
     payload.clear();
+    payload.push_back(1 + 3 * deg_plus_1);
     payload.push_back(deg_plus_1);
     for (size_t i = 0; i < deg_plus_1; i++)
       for (int dd = 0; dd < 3; dd++) payload.push_back(from_mont(co[dd * last.len + i]));

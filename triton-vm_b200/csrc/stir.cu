@@ -389,7 +389,8 @@ std::vector<uint32_t> stir_prove_run(Ctx &c, DevMem &mem, ProofStream &ps, const
     std::vector<u64> co = d2h(c, d_final, 3 * f_len);
     size_t deg_plus_1 = f_len;
     while (deg_plus_1 > 0 && co[deg_plus_1 - 1] == 0 && co[f_len + deg_plus_1 - 1] == 0 && co[2 * f_len + deg_plus_1 - 1] == 0) deg_plus_1--;
-    std::vector<u64> payload;
+    std::vector<u64> payload;        // Polynomial { coefficients }: length of the Vec encoding, count, elements (see prover.cu)
+    payload.push_back(1 + 3 * deg_plus_1);
     payload.push_back(deg_plus_1);
     for (size_t i = 0; i < deg_plus_1; i++)
       for (int dd = 0; dd < 3; dd++) payload.push_back(from_mont(co[dd * f_len + i]));
