@@ -2,19 +2,17 @@
 
 Restates `triton-vm/src/proof_stream.rs:19-125`, `proof_item.rs:96-147` (variant order =
 discriminant, which items are absorbed into the sponge) and `proof.rs:37-88`; the encoding
-rules themselves come from twenty-first 2.0's `BFieldCodec` (recalled — no
-in-tree known-answer test pins them except the two whole-proof digests, so this module is
-"parity unpinned" at the byte level):
+rules themselves are twenty-first 2.0's `BFieldCodec`.  They were recalled, and are now PINNED by the
+reference's two whole-proof known-answer digests (proof.rs:200-226, stark.rs:2433-2460; tests/test_golden.py):
 
   * BFieldElement -> 1 word; XFieldElement -> 3 words (c0,c1,c2); Digest -> 5; u32 -> 1;
     [T; N] of statically sized T -> N*len(T) words, no prefix;
   * Vec<T>: element count, then the elements; dynamically sized elements are each prefixed
     with their length;
   * derived struct: every dynamically sized field is prefixed with its encoded length;
-    fields are emitted in REVERSE declaration order (STRUCT_FIELDS_REVERSED; recalled from the
-    derive macro — flip the switch if a cargo box shows otherwise);
+    fields are emitted in REVERSE declaration order (STRUCT_FIELDS_REVERSED);
   * derived enum: variant index, then the payload field (length-prefixed when dynamic);
-  * Polynomial<XFE>: the coefficient Vec with trailing zeros stripped.
+  * Polynomial<XFE>: a one-field struct — the coefficient Vec (trailing zeros stripped) behind its encoded length.
 
 TEST INFRASTRUCTURE ONLY."""
 from . import tip5
@@ -22,7 +20,7 @@ from . import tip5
 
 STRUCT_FIELDS_REVERSED = True
 # Polynomial<FF> { coefficients } encoded like a derived one-field struct: the coefficient Vec's encoding prefixed with
-# its length (recalled: twenty-first keeps the manual impl compatible with the derive).  False: the bare Vec encoding.
+# its length (confirmed by the whole-proof digests).  False: the bare Vec encoding (kept for the search tool in tests/golden).
 POLYNOMIAL_AS_STRUCT = True
 
 # proof_item.rs:96-147 — (variant index, absorbed into Fiat-Shamir?)

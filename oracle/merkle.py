@@ -5,7 +5,7 @@ Restates twenty-first 2.0's `MerkleTree` as the reference uses it: `par_new`
 (stark.rs:676-713, fri.rs:311) and the verifier-side `MerkleTreeInclusionProof`
 (stark.rs:1609-1671).  Node i = hash_pair(node 2i, node 2i+1); root = node 1; leaf j =
 node n + j; the authentication structure lists the needed-but-not-computable sibling nodes in
-DESCENDING node-index order (recalled from the crate; parity-unpinned in-tree).
+DESCENDING node-index order (pinned by the reference's whole-proof digests, tests/test_golden.py).
 TEST INFRASTRUCTURE ONLY."""
 from .tip5 import hash_pair
 

@@ -3,7 +3,8 @@
 (`StdRng::seed_from_u64`, `rng.random()`); only needed to reach the AIR known-answer test
 `air_constraints_evaluators_have_not_changed` (master_table.rs:2327-2415).
 
-Recalled from the published crates (not in-tree):
+Recalled from the published crates (not in-tree); pinned by the AIR known-answer test and by the two whole-proof digests
+(tests/test_golden.py), which consume ~10^6 draws:
   * StdRng = ChaCha12, 64-word output buffer (4 blocks), next_u64 = two consecutive words (lo, hi);
   * seed_from_u64 expands the u64 with PCG32 (MUL 6364136223846793005, INC 11634580027462260723);
   * BFieldElement sample = BFieldElement::new(rng.random_range(0..=BFieldElement::MAX)) with

@@ -7,8 +7,8 @@ Parity status: the parameter maths is pinned against the figures the reference s
 n=184" and "u=2^8 -> n=610" in the comment stir.rs:738-746; `stacking` 1528-1539;
 `folding_polynomial_gives_expected_coefficients` 1634-1644).  The prover itself has no golden vector in
 the reference (its tests are prove-then-verify properties), so it is pinned by the restated verifier
-accepting its proofs and rejecting corrupted ones ("parity unpinned" at the byte level, like the
-BFieldCodec layer).
+accepting its proofs and rejecting corrupted ones (no reference vector for STIR proofs; the encoding layer and
+every primitive it shares with FRI are pinned by the reference's whole-proof digests, tests/test_golden.py).
 
 Polynomials are lists of X-field coefficients (tuples of 3 ints, canonical), little-endian.
 """

@@ -3,15 +3,10 @@ program `pick 11 … pick 15 read_io 5 assert_vector halt`, input = its own dige
 StdRng::seed_from_u64(4742841043836029231); expected Tip5::hash(&proof) =
 02390426207231576512,11357322246033024133,15595568858844533957,10807389618517394866,11786266879565336160.
 
-Everything needed exists in the oracle: VM + table fill (oracle/tracegen.py, judged by the AIR), the seeded randomness
-(offset_rng_seed, master_table.rs:630-662; randomizer polynomials 423-434; batch-randomizer column 1017-1025; quotient
-randomizer stark.rs:1316-1322) on top of oracle/rand_compat.py, the extension, the prover and the verifier.  The proof
-verifies (incl. the AIR), but its digest does NOT match for any of the 24 combinations of the recalled conventions tried
-below (seed array sampling, struct field order, authentication-structure order, Proof encoding).  The remaining suspects
-are twenty-first 2.0 internals that no in-tree vector pins individually (BFieldCodec of enums / nested vectors /
-polynomials, `sample_indices`, `sample_scalars`) and table-fill details the AIR leaves free (row order inside the cascade
-table, padding rows).  Kept as a tool: on a box with cargo, dump the reference's intermediate values (program digest,
-main-table Merkle root, challenges) next to the ones printed here to find the first divergence.
+This is the search tool that found the one wrong convention (Polynomial items are encoded as a one-field struct): it proves
+the instance under every combination of the recalled conventions (seed array sampling, struct field order,
+authentication-structure order, Polynomial encoding, Proof encoding) and reports which combination hits the digest —
+`per_u8 reversed desc poly-struct / struct`.  The regression test is tests/test_golden.py; this file stays as a tool.
 
 Run:  python tests/golden/try_reference_proof_digest.py     (≈ 3 min; TEST INFRASTRUCTURE, not collected by pytest)
 """

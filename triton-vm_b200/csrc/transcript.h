@@ -3,8 +3,8 @@
 // Restates triton-vm/src/proof_stream.rs:19-125 (ProofStream: which items alter the sponge,
 // sample_scalars / sample_indices), proof_item.rs:96-147 (variant order, Fiat-Shamir flags) and
 // proof.rs:37-88 (Proof = BFieldCodec encoding of the item list; Claim).  The BFieldCodec rules are
-// twenty-first 2.0's (SURVEY.md A.5 — recalled; the struct-field emission order is the one
-// assumption that can only be confirmed against the reference binary, hence the switch below).
+// twenty-first 2.0's; they are pinned by the reference's two whole-proof known-answer digests
+// (proof.rs:200-226, stark.rs:2433-2460; tests/test_golden.py): struct fields are emitted in reverse declaration order.
 //
 // Words are kept canonical in the item encodings; the sponge state is Montgomery form.
 #pragma once
