@@ -31,7 +31,8 @@ _AIR = None
 def air():
     global _AIR
     if _AIR is None:
-        _AIR = build_air()
+        from . import stark
+        _AIR = stark.air()                     # one build per process (≈ 8 s), shared with the prover / verifier
     return _AIR
 
 
@@ -498,9 +499,11 @@ def table_heights(words, ex):
 
 
 # ---- main table -------------------------------------------------------------------------------------
-def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret_digests=()):
+def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret_digests=(), evaluate_substitutions=False):
     """[379][n] canonical ints: MasterMainTable::new + pad (master_table.rs:881-1004).
-    -> (table, program digest, public output)"""
+    -> (table, program digest, public output).  The 230 degree-lowering columns come from the generated straight-line
+    rules (oracle/c/aux_extend.c) unless `evaluate_substitutions`: then the substitution circuits are evaluated node by
+    node in Python (`fill_derived_main_columns`, ~20x slower; tests/test_aux_extend.py checks the two against each other)."""
     assert n >= 256 and n & (n - 1) == 0
     T = np.zeros((NUM_MAIN, n), dtype=object)
     program = list(words)
@@ -684,7 +687,13 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret
         T[c.CI, k], T[c.LHS, k], T[c.LhsInv, k], T[c.Result, k] = pad_ci, pad_lhs, pad_lhs_inv, pad_result
         T[c.BitsMinus33Inv, k] = F.inv((-33) % P)
 
-    fill_derived_main_columns(T)
+    if evaluate_substitutions:
+        fill_derived_main_columns(T)
+    else:
+        from . import corc
+        filled = corc.fill_derived_main(np.array(T.tolist(), dtype=np.uint64))
+        for q in range(149, NUM_MAIN):
+            T[q, :] = [int(v) for v in filled[q]]
     return T, ex.digest, ex.output
 
 

@@ -103,8 +103,12 @@ def test_derived_columns_of_the_last_row_are_zero():
 def test_generated_derived_main_columns_equal_the_evaluated_substitutions(program, inp):
     # tracegen.fill_derived_main_columns evaluates the substitution circuits node by node; the generated straight-line
     # code (the text the device compiles) must reproduce all 230 columns from the 149 table columns
-    main = tables(program, inp)[4]
+    T, _, _, _, main = tables(program, inp)                  # derived columns from the generated rules (the default)
     scrambled = main.copy()
     scrambled[149:] = 12345
     assert np.array_equal(corc.fill_derived_main(scrambled), main)
+    T2 = T.copy()
+    T2[149:, :] = 0
+    tg.fill_derived_main_columns(T2)                         # node-by-node evaluation of the substitution circuits
+    assert np.array_equal(np.array(T2.tolist(), dtype=np.uint64), main)
     assert main[149:169].any() and main[169:].any() and not main[169:, -1].any()      # last row of the tran section is 0
