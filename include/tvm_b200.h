@@ -33,6 +33,7 @@ extern "C" {
 #define TVM_ERR_LDT_PARAMS (-6)   /* LdtParameterError */
 #define TVM_ERR_STATE (-7)
 #define TVM_ERR_UNSUPPORTED (-8)
+#define TVM_ERR_VERIFICATION (-9) /* VerificationError / LdtVerificationError, error.rs:190-260: the proof is rejected */
 
 typedef struct tvm_ctx tvm_ctx;
 
@@ -200,6 +201,16 @@ int tvm_aux_extend(tvm_ctx *ctx, const uint64_t *main_trace, unsigned log2_n, co
  * degree-lowering columns 149..378 of main_trace [379][n] (canonical, column-major, host or device memory, IN PLACE) from
  * the 149 table columns 0..148, which are not modified. */
 int tvm_fill_derived_main_columns(tvm_ctx *ctx, uint64_t *main_trace, unsigned log2_n);
+/* ---- Stark::verify (stark.rs:1388-1763, Verifier::verify) — SURVEY.md 8(f).4.
+ *      Replays the Fiat-Shamir transcript of `proof` (Proof.0, canonical words) against `claim` under `params`: AIR / quotient
+ *      identity at the out-of-domain point, FRI or STIR, Merkle openings, DEEP combination.  Host code — one proof is a few
+ *      milliseconds of strictly sequential work; needs neither a context nor a GPU.
+ *      Returns TVM_OK if the proof is accepted, TVM_ERR_VERIFICATION if it is rejected (then `failure`, if given, receives the
+ *      name of the reference's error variant, e.g. "VerificationError: CombinationCodewordMismatch").
+ *      skip_air_check != 0 skips only the out-of-domain AIR identity (for proofs over synthetic, non-satisfying traces as
+ *      used by tests and benchmarks); production callers pass 0. --- */
+int tvm_verify(const tvm_params *params, const tvm_claim *claim, const uint64_t *proof, size_t proof_len, int skip_air_check,
+               char *failure, size_t failure_capacity);
 /* device time per stage of the last tvm_prove on this ctx, reference profiler labels; returns #stages */
 int tvm_last_prove_timings(const tvm_ctx *ctx, const char **names /*[20]*/, float *ms /*[20]*/);
 

@@ -1,0 +1,87 @@
+"""tvm_verify — Stark::verify in the library (csrc/verifier.cu, host code: needs no GPU, so these tests run everywhere).
+It must accept what the oracle's verifier accepts — first of all the two proofs whose Tip5 digests are the reference's own
+known-answer values (tests/test_golden.py), i.e. proofs bit-identical to what the reference produces — and reject what it
+rejects: every tampered word, a wrong claim, wrong parameters."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import tvm_b200
+from oracle import reference_prover as RP, stark as S
+import test_golden as tgold
+from test_halt_program import _instance as halt_instance, halt_tables, N as HALT_N
+
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+mg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mg)
+_PROOFS = {}
+
+
+def _c(claim):
+    return (claim.program_digest, claim.input, claim.output)
+
+
+def reference_proof(which):
+    if which not in _PROOFS:
+        inst = tgold.reference_instance() if which == "default" else tgold.every_instruction_instance()
+        _PROOFS[which] = (inst, RP.prove(inst))
+    return _PROOFS[which]
+
+
+@pytest.mark.parametrize("which,security", [("default", 160), ("every_instruction", 32)])
+def test_accepts_the_references_known_answer_proofs(which, security):
+    inst, proof = reference_proof(which)
+    assert RP.proof_digest(proof) == (tgold.REFERENCE_PROOF_DIGEST if which == "default" else tgold.EVERY_INSTRUCTION_PROOF_DIGEST)
+    ok, why = tvm_b200.verify(_c(inst["claim"]), proof, security_level=security, log2_expansion=2)
+    assert ok, why
+
+
+def test_rejects_tampering_wrong_claims_and_wrong_parameters():
+    inst, proof = reference_proof("default")
+    claim = inst["claim"]
+    rng = np.random.default_rng(1)
+    reasons = set()
+    for pos in [0, 1, 2, 3, 9, 40, 1500, 3000, len(proof) // 2, len(proof) - 1] + [int(v) for v in rng.integers(0, len(proof), 12)]:
+        bad = list(proof)
+        bad[pos] = (bad[pos] + 1) % tvm_b200.P
+        ok, why = tvm_b200.verify(_c(claim), bad, 160, 2)
+        assert not ok and why, pos
+        with pytest.raises(Exception):
+            S.verify(inst["stark"], claim, bad, check_air=True)
+        reasons.add(why.split(":")[0])
+    assert {"ProofDecodingError", "VerificationError", "LdtVerificationError"} <= reasons
+    assert tvm_b200.verify(_c(claim), proof[:-1], 160, 2)[0] is False                     # truncated
+    assert tvm_b200.verify((claim.program_digest, claim.input, [7]), proof, 160, 2) == (False, "VerificationError: OutOfDomainQuotientValueMismatch")
+    assert tvm_b200.verify((claim.program_digest[::-1], claim.input, claim.output), proof, 160, 2)[0] is False
+    assert tvm_b200.verify(_c(claim), proof, 80, 2)[0] is False                            # other security level
+    assert tvm_b200.verify(_c(claim), proof, 160, 3)[0] is False                           # other expansion factor
+    assert tvm_b200.verify(_c(claim), proof, 160, 2, ldt_choice=tvm_b200.LDT_STIR)[0] is False
+
+
+@pytest.mark.parametrize("case", mg.CASES, ids=lambda c: c[0])
+def test_accepts_synthetic_fri_and_stir_proofs_without_the_air_check(case):
+    name, sec, le, ldt, ph, seed = case
+    st, d, claim, main, mrand, aux, qrand = mg.instance(sec, le, ldt, ph, seed)
+    proof, _ = S.prove(st, claim, main, mrand, aux, qrand, padded_height=ph)
+    choice = tvm_b200.LDT_STIR if ldt == "stir" else tvm_b200.LDT_FRI
+    assert tvm_b200.verify(_c(claim), proof, sec, le, ldt_choice=choice, skip_air_check=True) == (True, "")
+    ok, why = tvm_b200.verify(_c(claim), proof, sec, le, ldt_choice=choice)             # random tables do not satisfy the AIR
+    assert (ok, why) == (False, "VerificationError: OutOfDomainQuotientValueMismatch")
+    for pos in (len(proof) // 3, len(proof) - 40):
+        bad = list(proof)
+        bad[pos] = (bad[pos] + 1) % tvm_b200.P
+        assert tvm_b200.verify(_c(claim), bad, sec, le, ldt_choice=choice, skip_air_check=True)[0] is False
+
+
+def test_accepts_a_stir_proof_of_a_real_program_with_the_air_check():
+    st, claim, main, mrand, aux_provider, qrand = halt_instance(halt_tables(HALT_N), 8, "stir")
+    proof, _ = S.prove(st, claim, main, mrand, aux_provider, qrand, padded_height=HALT_N)
+    assert tvm_b200.verify(_c(claim), proof, 8, 2, ldt_choice=tvm_b200.LDT_STIR) == (True, "")
+    assert tvm_b200.verify(_c(claim), proof, 8, 2, ldt_choice=tvm_b200.LDT_FRI)[0] is False
+
+
+def test_argument_errors():
+    with pytest.raises(tvm_b200.TvmError):
+        tvm_b200.verify(([1, 2, 3, 4, 5], [], []), [], 160, 2)

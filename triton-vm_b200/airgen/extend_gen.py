@@ -198,8 +198,9 @@ def levels(init_rules, tran_rules):
 class Emitter:
     """straight-line typed code for a set of circuit nodes; shares temporaries inside one block"""
 
-    def __init__(self, indent="    "):
+    def __init__(self, indent="    ", main_is_x=False):
         self.lines, self.name, self.isx, self.cnt, self.indent = [], {}, {}, 0, indent
+        self.main_is_x = main_is_x            # the verifier evaluates the AIR on out-of-domain (X-field) main rows
 
     def tmp(self):
         self.cnt += 1
@@ -223,7 +224,8 @@ class Emitter:
                 row, is_main, col = n.val
                 v = self.tmp()
                 if is_main:
-                    lines.append(f"const u64 {v} = {'MN' if row else 'MC'}({col});"); isx[key] = False
+                    ty = "xfe" if self.main_is_x else "u64"
+                    lines.append(f"const {ty} {v} = {'MN' if row else 'MC'}({col});"); isx[key] = self.main_is_x
                 else:
                     lines.append(f"const xfe {v} = {'AN' if row else 'AC'}({col});"); isx[key] = True
                 name[key] = v

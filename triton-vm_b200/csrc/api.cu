@@ -199,6 +199,7 @@ const char *tvm_strerror(int code) {
     case TVM_ERR_LDT_PARAMS: return "low-degree-test parameter error";
     case TVM_ERR_STATE: return "entry point called out of order";
     case TVM_ERR_UNSUPPORTED: return "unsupported configuration";
+    case TVM_ERR_VERIFICATION: return "proof rejected (VerificationError)";
     default: return "unknown error";
   }
 }

@@ -111,6 +111,8 @@ _SIGNATURES = {
                                  AUX_CALLBACK, _vp, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
     "tvm_fill_derived_main_columns": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint]),
     "tvm_aux_extend": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint, _u64p, _u64p, _u64p]),
+    "tvm_verify": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), _u64p, ctypes.c_size_t, ctypes.c_int,
+                                  ctypes.c_char_p, ctypes.c_size_t]),
     "tvm_last_prove_timings": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]),
     "tvm_air_quotient_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _u64p, _u64p, ctypes.c_uint,
                                             ctypes.c_uint, ctypes.c_uint64, _vp, ctypes.c_size_t]),
@@ -163,6 +165,23 @@ def derive_domains(security_level=160, log2_expansion=2, padded_height=1 << 10, 
     if rc:
         raise TvmError(rc, lib().tvm_strerror(rc).decode())
     return d.as_dict()
+
+
+def verify(claim, proof, security_level=160, log2_expansion=2, ldt_choice=LDT_AUTO, conjectured=False, skip_air_check=False):
+    """Stark::verify (tvm_verify; host code, no GPU needed).  claim = (program_digest[5], input, output[, version]);
+    proof: the proof words.  Returns (accepted: bool, failure: str) — failure names the reference's error variant."""
+    digest, inp, out = claim[0], claim[1], claim[2]
+    version = claim[3] if len(claim) > 3 else 6
+    ia, iap = _np_u64(np.array(list(inp), dtype=np.uint64))
+    oa, oap = _np_u64(np.array(list(out), dtype=np.uint64))
+    cs = ClaimStruct((ctypes.c_uint64 * 5)(*[int(v) for v in digest]), version, iap, ia.size, oap, oa.size)
+    p = Params(security_level, log2_expansion, ldt_choice, int(conjectured))
+    pw, pwp = _np_u64(np.array(proof, dtype=np.uint64))
+    buf = ctypes.create_string_buffer(256)
+    rc = lib().tvm_verify(ctypes.byref(p), ctypes.byref(cs), pwp, pw.size, int(skip_air_check), buf, 256)
+    if rc not in (0, -9):
+        raise TvmError(rc, lib().tvm_strerror(rc).decode())
+    return rc == 0, buf.value.decode()
 
 
 class Backend:
