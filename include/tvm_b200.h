@@ -211,6 +211,8 @@ int tvm_fill_derived_main_columns(tvm_ctx *ctx, uint64_t *main_trace, unsigned l
  *      used by tests and benchmarks); production callers pass 0. --- */
 int tvm_verify(const tvm_params *params, const tvm_claim *claim, const uint64_t *proof, size_t proof_len, int skip_air_check,
                char *failure, size_t failure_capacity);
+/* Proof::padded_height (proof.rs:37-56): TVM_ERR_VERIFICATION unless the proof decodes and holds exactly one such item. */
+int tvm_proof_padded_height(const uint64_t *proof, size_t proof_len, uint64_t *padded_height);
 /* device time per stage of the last tvm_prove on this ctx, reference profiler labels; returns #stages */
 int tvm_last_prove_timings(const tvm_ctx *ctx, const char **names /*[20]*/, float *ms /*[20]*/);
 

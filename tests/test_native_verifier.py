@@ -82,6 +82,12 @@ def test_accepts_a_stir_proof_of_a_real_program_with_the_air_check():
     assert tvm_b200.verify(_c(claim), proof, 8, 2, ldt_choice=tvm_b200.LDT_FRI)[0] is False
 
 
-def test_argument_errors():
+def test_argument_errors_and_padded_height():
     with pytest.raises(tvm_b200.TvmError):
         tvm_b200.verify(([1, 2, 3, 4, 5], [], []), [], 160, 2)
+    inst, proof = reference_proof("default")
+    assert tvm_b200.proof_padded_height(proof) == inst["padded_height"] == 256          # Proof::padded_height, proof.rs:37-56
+    with pytest.raises(tvm_b200.TvmError):
+        tvm_b200.proof_padded_height(proof[:100])
+    l = tvm_b200.lib()                                   # device entry points refuse a missing context before touching CUDA
+    assert l.tvm_aux_extend(None, None, 8, None, None, None) == -1 and l.tvm_fill_derived_main_columns(None, None, 8) == -1

@@ -709,6 +709,25 @@ LdtResult stir_verify(Transcript &ps, const StarkDerived &d) {
 }  // namespace
 }  // namespace tvm
 
+// Proof::padded_height (proof.rs:37-56): the one Log2PaddedHeight item of the proof stream
+extern "C" int tvm_proof_padded_height(const uint64_t *proof, size_t proof_len, uint64_t *padded_height) {
+  using namespace tvm;
+  if (!proof || !proof_len || !padded_height) return TVM_ERR_INVALID_ARG;
+  try {
+    Transcript ps(proof, proof_len);
+    int found = 0;
+    for (const Item &it : ps.items)
+      if (it.kind == (int)ItemKind::Log2PaddedHeight) {
+        if (it.payload_len() != 1 || it.payload()[0] >= 64) return TVM_ERR_VERIFICATION;
+        *padded_height = (uint64_t)1 << it.payload()[0];
+        found++;
+      }
+    return found == 1 ? TVM_OK : TVM_ERR_VERIFICATION;   // NoLog2PaddedHeight / TooManyLog2PaddedHeights
+  } catch (...) {
+    return TVM_ERR_VERIFICATION;
+  }
+}
+
 extern "C" int tvm_verify(const tvm_params *params, const tvm_claim *claim, const uint64_t *proof, size_t proof_len, int skip_air_check,
                           char *failure, size_t failure_capacity) {
   using namespace tvm;

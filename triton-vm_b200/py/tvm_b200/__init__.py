@@ -113,6 +113,7 @@ _SIGNATURES = {
     "tvm_aux_extend": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint, _u64p, _u64p, _u64p]),
     "tvm_verify": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), _u64p, ctypes.c_size_t, ctypes.c_int,
                                   ctypes.c_char_p, ctypes.c_size_t]),
+    "tvm_proof_padded_height": (ctypes.c_int, [_u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]),
     "tvm_last_prove_timings": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]),
     "tvm_air_quotient_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _u64p, _u64p, ctypes.c_uint,
                                             ctypes.c_uint, ctypes.c_uint64, _vp, ctypes.c_size_t]),
@@ -182,6 +183,16 @@ def verify(claim, proof, security_level=160, log2_expansion=2, ldt_choice=LDT_AU
     if rc not in (0, -9):
         raise TvmError(rc, lib().tvm_strerror(rc).decode())
     return rc == 0, buf.value.decode()
+
+
+def proof_padded_height(proof):
+    """Proof::padded_height; raises TvmError if the proof does not decode or holds no / several Log2PaddedHeight items"""
+    pw, pwp = _np_u64(np.array(proof, dtype=np.uint64))
+    out = ctypes.c_uint64(0)
+    rc = lib().tvm_proof_padded_height(pwp, pw.size, ctypes.byref(out))
+    if rc:
+        raise TvmError(rc, lib().tvm_strerror(rc).decode())
+    return int(out.value)
 
 
 class Backend:
