@@ -91,3 +91,40 @@ def test_argument_errors_and_padded_height():
         tvm_b200.proof_padded_height(proof[:100])
     l = tvm_b200.lib()                                   # device entry points refuse a missing context before touching CUDA
     assert l.tvm_aux_extend(None, None, 8, None, None, None) == -1 and l.tvm_fill_derived_main_columns(None, None, 8) == -1
+
+
+def test_untrusted_input_never_crashes_and_is_never_accepted():
+    # the reference's `decoding_arbitrary_proof_data_does_not_panic` (proof.rs:192-197), extended to the whole verifier:
+    # random words, corrupted lengths / counts / discriminants, truncation, extension, absurd padded heights
+    rng = np.random.default_rng(7)
+    cases = []
+    for name, sec, le, ldt, ph, seed in (mg.CASES[0], mg.CASES[3]):
+        st, d, claim, main, mrand, aux, qrand = mg.instance(sec, le, ldt, ph, seed)
+        proof, _ = S.prove(st, claim, main, mrand, aux, qrand, padded_height=ph)
+        cases.append((claim, np.array(proof, dtype=np.uint64), sec, le, tvm_b200.LDT_STIR if ldt == "stir" else tvm_b200.LDT_FRI))
+    outcomes = set()
+    for k in range(6000):
+        claim, proof, sec, le, choice = cases[k % 2]
+        p = proof.copy()
+        kind = k % 6
+        if kind == 0:
+            p[rng.integers(0, len(p))] = rng.integers(0, tvm_b200.P, dtype=np.uint64)
+        elif kind == 1:
+            p[rng.integers(0, len(p))] = rng.integers(0, 70000)
+        elif kind == 2:
+            p = p[:rng.integers(1, len(p))] if k % 4 else np.concatenate([p, rng.integers(0, tvm_b200.P, 17, dtype=np.uint64)])
+        elif kind == 3:
+            p[rng.integers(0, 60)] = rng.integers(0, 40)
+        elif kind == 4:
+            p[rng.integers(0, len(p))] = np.uint64(2 ** 64 - 1 - int(rng.integers(0, 2 ** 33)))
+        else:
+            p = rng.integers(0, tvm_b200.P, int(rng.integers(1, 3000)), dtype=np.uint64)
+        ok, why = tvm_b200.verify(_c(claim), p, sec, le, ldt_choice=choice, skip_air_check=True)
+        assert not ok or np.array_equal(p, proof)
+        outcomes.add(why.split(":")[0])
+    assert {"ProofDecodingError", "VerificationError", "LdtVerificationError", "UnexpectedItem"} <= outcomes
+    claim, proof, sec, le, choice = cases[0]
+    for log2_ph in list(range(5, 34)) + [63, 2 ** 32, tvm_b200.P - 1]:                # absurd heights cost nothing
+        p = proof.copy()
+        p[4] = log2_ph
+        assert tvm_b200.verify(_c(claim), p, sec, le, ldt_choice=choice, skip_air_check=True)[0] is False

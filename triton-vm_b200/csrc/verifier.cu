@@ -405,6 +405,7 @@ void stark_verify(const StarkParams &sp, const ClaimView &claim, const u64 *proo
   StarkDerived d;
   if (stark_derive(sp, (size_t)1 << lp.payload()[0], d) != 0) fail("VerificationError: LdtParameterError");
   const size_t N = d.ldt_len, n = d.trace_len;
+  if (N == 0 || N > ((size_t)1 << 31)) fail("VerificationError: LdtParameterError");   // indices are sampled as u32 below N
   const unsigned height = ilog2z(N);
 
   const std::vector<u64> main_root = ps.digest();
