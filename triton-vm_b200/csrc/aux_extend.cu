@@ -20,6 +20,7 @@
 // per pass and one write of the auxiliary table — no tensor-core shape anywhere.
 //
 // Layout: main table [379][n] Montgomery, auxiliary table [91*3][n] Montgomery planes (the layout the LDE consumes).
+#include <cstdlib>
 #include <cstring>
 #include "prove_common.h"
 
@@ -160,6 +161,39 @@ __global__ void aux_scan_tops_kernel(AuxScanArgs p) {
   }
 }
 
+// CTA-wide variant of the above (TVM_AUX_TOPS_PARALLEL=1; not yet run on a GPU — the sequential kernel is the default until
+// it has been compared): thread t composes its `per` consecutive chunk totals, the CTA scans the 256 thread totals with
+// the same cta_scan the row kernels use, and each thread walks its range again from its exclusive prefix.
+__global__ void __launch_bounds__(AUX_CHUNK) aux_scan_tops_parallel_kernel(AuxScanArgs p) {
+  __shared__ u64 sm[2][6][AUX_CHUNK];
+  __shared__ u64 ex[6][AUX_CHUNK];
+  const int t = threadIdx.x;
+  const size_t per = (p.nchunks + AUX_CHUNK - 1) / AUX_CHUNK;
+  const size_t k0 = (size_t)t * per < p.nchunks ? (size_t)t * per : p.nchunks;
+  const size_t k1 = k0 + per < p.nchunks ? k0 + per : p.nchunks;
+  const u64 *tot = p.tot + (size_t)blockIdx.x * p.nchunks * 6;
+  u64 *vin = p.vin + (size_t)blockIdx.x * p.nchunks * 3;
+  AffMap m;
+  m.a = xone();
+  m.b = xzero();
+  for (size_t k = k0; k < k1; k++) {
+    AffMap x;
+    x.a = xmake(tot[6 * k], tot[6 * k + 1], tot[6 * k + 2]);
+    x.b = xmake(tot[6 * k + 3], tot[6 * k + 4], tot[6 * k + 5]);
+    m = compose(x, m);
+  }
+  const AffMap incl = cta_scan(m, sm);
+  map_store(ex, t, incl);
+  __syncthreads();
+  xfe v = xzero();                                   // value before this thread's first chunk
+  if (t > 0) v = map_load(ex, t - 1).b;              // the prefix map applied to 0 (row 0's map is constant)
+  for (size_t k = k0; k < k1; k++) {
+    vin[3 * k] = v.c0; vin[3 * k + 1] = v.c1; vin[3 * k + 2] = v.c2;
+    xfe a = xmake(tot[6 * k], tot[6 * k + 1], tot[6 * k + 2]), b = xmake(tot[6 * k + 3], tot[6 * k + 4], tot[6 * k + 5]);
+    v = xadd(xmul(a, v), b);
+  }
+}
+
 // the 41 degree-lowering columns: row i from rows i, i+1 of the main table and of the 49 base columns; last row zero
 __global__ void __launch_bounds__(128) aux_derived_kernel(const u64 *main_t, u64 *aux_t, const u64 *ch, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,7 +250,9 @@ void aux_extend_run(Ctx &c, const u64 *d_main, size_t n, const u64 *d_ch, u64 *d
     if (!p.ncols) continue;
     dim3 grid((unsigned)p.nchunks, (unsigned)p.ncols);
     aux_scan_kernel<false><<<grid, AUX_CHUNK, 0, c.stream>>>(p);
-    aux_scan_tops_kernel<<<(unsigned)p.ncols, 32, 0, c.stream>>>(p);
+    static const bool tops_parallel = getenv("TVM_AUX_TOPS_PARALLEL") && atoi(getenv("TVM_AUX_TOPS_PARALLEL"));
+    if (tops_parallel) aux_scan_tops_parallel_kernel<<<(unsigned)p.ncols, AUX_CHUNK, 0, c.stream>>>(p);
+    else aux_scan_tops_kernel<<<(unsigned)p.ncols, 32, 0, c.stream>>>(p);
     aux_scan_kernel<true><<<grid, AUX_CHUNK, 0, c.stream>>>(p);
     c.launches += 3;
     TVM_CUDA(cudaGetLastError());
