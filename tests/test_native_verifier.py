@@ -128,3 +128,30 @@ def test_untrusted_input_never_crashes_and_is_never_accepted():
         p = proof.copy()
         p[4] = log2_ph
         assert tvm_b200.verify(_c(claim), p, sec, le, ldt_choice=choice, skip_air_check=True)[0] is False
+
+
+def test_plain_c_client(tmp_path):
+    # include/tvm_b200.h is a C header: compile examples/verify_proof.c with a C99 compiler and let it judge the reference's
+    # known-answer proof and a corrupted copy
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "triton-vm_b200", "lib")
+    exe = str(tmp_path / "verify_proof")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "verify_proof.c"), "-L" + libdir, "-ltvm_b200", "-Wl,-rpath," + libdir, "-o", exe],
+                   check=True, env=dict(os.environ, CC="gcc"))
+    inst, proof = reference_proof("default")
+    claim = inst["claim"]
+
+    def write(path, words):
+        head = [160, 2, 0, claim.version] + list(claim.program_digest) + [len(claim.input)] + list(claim.input) + \
+               [len(claim.output)] + list(claim.output) + [len(words)] + [int(w) for w in words]
+        path.write_text(" ".join(str(int(v)) for v in head))
+    write(tmp_path / "good.txt", proof)
+    bad = list(proof)
+    bad[len(bad) // 2] ^= 1
+    write(tmp_path / "bad.txt", bad)
+    good = subprocess.run([exe, str(tmp_path / "good.txt")], capture_output=True, text=True)
+    assert good.returncode == 0 and "accepted (padded height 256" in good.stdout, good.stderr
+    rejected = subprocess.run([exe, str(tmp_path / "bad.txt")], capture_output=True, text=True)
+    assert rejected.returncode == 1 and "rejected:" in rejected.stderr
