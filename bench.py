@@ -297,6 +297,16 @@ def run_gpu(args):
                      "ntt_gelems_per_s": (NM + 3 * NA) * 8 * n / (lde_ms * 1e-3) / 1e9 if lde_ms else None},
         "clocks": clocks,
     }
+    # After the timed region: the proof the GPU just produced goes through Stark::verify (tvm_verify, host code).  The tables
+    # are synthetic, so only the out-of-domain AIR identity is skipped; transcript, Merkle openings, DEEP and the low-degree
+    # test are checked in full.  Informational: a rejection is reported, it does not abort the bench line.
+    try:
+        t0 = time.perf_counter()
+        accepted, reason = tvm_b200.verify(claim, proof, 160, 2, ldt_choice=ldt_choice, skip_air_check=True)
+        out["proof_check"] = {"verifier": "tvm_verify (Stark::verify; AIR identity skipped: synthetic tables)", "accepted": bool(accepted),
+                              "reason": reason, "ms": round(1e3 * (time.perf_counter() - t0), 1), "proof_words": int(proof.size)}
+    except Exception as e:  # noqa: BLE001 - never lose the measurement over the post-check
+        out["proof_check"] = {"accepted": None, "reason": "verifier call failed: " + repr(e)[:200]}
     if world == 1 and not args.no_cpu_baseline:
         total, cores, sample, cstages = cpu_baseline(args.log2_height)
         out["cpu_baseline"] = {"value": total, "unit": "ms", "cores": cores, "kind": "port", "sample": sample,
