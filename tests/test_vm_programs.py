@@ -202,3 +202,64 @@ def test_gpu_kitchen_sink_device_extension_and_proof(backend):
     assert S.verify(st, claim, got, check_air=True)
     want, _ = S.prove(st, claim, main, mrand, cpu_extend, qrand, padded_height=ph)
     assert got == want
+
+
+# ---- the reference's workload generator for an exact padded height: ProgramToBench::spin (triton-dev-util/src/lib.rs:49-75) ----
+SPIN = "read_io 1 addi -3 push 2 pow place 5 call spin halt spin: pick 5 addi -1 place 5 recurse_or_return"
+
+
+def spin_instance(log2_padded_height, security, ldt, seed=41):
+    words = tg.assemble(SPIN)
+    inp = [log2_padded_height]
+    ph = tg.padded_height(words, inp)
+    st = S.Stark(security, 2, ldt)
+    d = st.derive(ph)
+    n, h = d["trace_len"], d["num_trace_randomizers"]
+    T, digest, out = tg.main_table(words, inp, n)
+    main = np.array(T.tolist(), dtype=np.uint64)
+    rng = np.random.default_rng(seed)
+    mrand, arand, rcol = rand_bfes(rng, (379, h)), rand_bfes(rng, (91, h, 3)), rand_bfes(rng, (n, 3))
+    qrand = rand_bfes(rng, (d["num_quotient_randomizer_coefficients"], 3))
+    return dict(stark=st, claim=S.Claim(digest, inp, list(out)), main=main, T=T, main_rand=mrand, aux_rand=arand,
+                randomizer_column=rcol, quot_rand=qrand, padded_height=ph, derived=d)
+
+
+def test_spin_reaches_the_requested_padded_height_and_satisfies_the_air():
+    import tvm_b200
+    for k in (8, 9, 11):
+        assert tg.padded_height(tg.assemble(SPIN), [k]) == 1 << k
+    inst = spin_instance(9, 8, "fri")
+    main, claim = inst["main"], inst["claim"]
+    ch = _sink_challenges(claim.program_digest, claim.output)            # any challenges; the claim terms come from `claim`
+    ch = S.derive_challenges(ch[:59], claim)
+    B = corc.aux_extend(main, ch)
+    n = main.shape[1]
+    assert tg.failing_constraints(inst["T"], [[tuple(int(v) for v in B[q][i]) for i in range(n)] for q in range(91)], ch) == []
+    rcol, arand = inst["randomizer_column"], inst["aux_rand"]
+    proof, _ = S.prove(inst["stark"], claim, main, inst["main_rand"],
+                       lambda c: (corc.aux_extend(main, np.asarray(c, dtype=np.uint64).reshape(63, 3), rcol), arand), inst["quot_rand"],
+                       padded_height=inst["padded_height"])
+    assert tvm_b200.verify((claim.program_digest, claim.input, claim.output), proof, 8, 2, ldt_choice=tvm_b200.LDT_FRI) == (True, "")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log2_padded_height,ldt", [(13, "fri"), (14, "stir")])
+def test_gpu_proves_spin_from_the_149_table_columns_and_the_verifier_accepts(backend, log2_padded_height, ldt):
+    """The whole device-side pipeline on the reference's benchmark workload at Stark::default() security, checked by the
+    verifier INCLUDING the AIR — no oracle prover in the loop, so this scales to heights the oracle cannot reach:
+    degree-lowering main columns, auxiliary table, proof: all from the GPU."""
+    import tvm_b200
+    inst = spin_instance(log2_padded_height, 160, ldt)
+    claim, want_main = inst["claim"], inst["main"]
+    main = want_main.copy()
+    main[149:] = 0
+    backend.fill_derived_main_columns(main)
+    assert np.array_equal(main, want_main)
+    rcol, arand = inst["randomizer_column"], inst["aux_rand"]
+    choice = tvm_b200.LDT_STIR if ldt == "stir" else tvm_b200.LDT_FRI
+    got = backend.prove((claim.program_digest, claim.input, claim.output), main, inst["main_rand"],
+                        lambda ch: (backend.aux_extend(main, ch, rcol), arand), inst["quot_rand"], security_level=160,
+                        log2_expansion=2, padded_height=inst["padded_height"], ldt_choice=choice)
+    assert tvm_b200.proof_padded_height(got) == 1 << log2_padded_height
+    assert tvm_b200.verify((claim.program_digest, claim.input, claim.output), got, 160, 2, ldt_choice=choice) == (True, "")
+    assert tvm_b200.verify((claim.program_digest, claim.input, [1]), got, 160, 2, ldt_choice=choice)[0] is False
