@@ -505,7 +505,7 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret
     rules (oracle/c/aux_extend.c) unless `evaluate_substitutions`: then the substitution circuits are evaluated node by
     node in Python (`fill_derived_main_columns`, ~20x slower; tests/test_aux_extend.py checks the two against each other)."""
     assert n >= 256 and n & (n - 1) == 0
-    T = np.zeros((NUM_MAIN, n), dtype=object)
+    T = np.zeros((NUM_MAIN, n), dtype=np.uint64)         # every entry is a canonical field element < p < 2^64
     program = list(words)
     ex = execute(program, public_input, secret_input, initial_ram, secret_digests)
     rows, plen = ex.rows, len(ex.rows)
@@ -523,17 +523,14 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret
 
     # -- program table (program.rs:33-113)
     c = MAIN["program"]
-    for i in range(n):
-        T[c.Address, i] = i
-        T[c.IndexInChunk, i] = i % 10
-        T[c.MaxMinusIndexInChunkInv, i] = inv_or_zero(9 - i % 10)
-        if i < padded_len:
-            T[c.Instruction, i] = padded_program[i]
-            T[c.LookupMultiplicity, i] = ex.multiplicities[i] if i < len(program) else 0
-            T[c.IsHashInputPadding, i] = 0 if i < len(program) else 1
-        else:
-            T[c.IsHashInputPadding, i] = 1
-            T[c.IsTablePadding, i] = 1
+    idx = np.arange(n, dtype=np.uint64)
+    T[c.Address] = idx
+    T[c.IndexInChunk] = idx % 10
+    T[c.MaxMinusIndexInChunkInv] = np.array([inv_or_zero(9 - k) for k in range(10)], dtype=np.uint64)[idx % 10]
+    T[c.Instruction, :padded_len] = padded_program
+    T[c.LookupMultiplicity, :len(program)] = ex.multiplicities
+    T[c.IsHashInputPadding, len(program):] = 1
+    T[c.IsTablePadding, padded_len:] = 1
 
     # -- op stack table (op_stack.rs:179-211): sorted by (stack pointer, clk); padding copies the last row
     c = MAIN["op_stack"]
@@ -545,10 +542,9 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret
             clk_jump_diffs.append(clk - os_sorted[i - 1][0])
     if os_sorted:
         last = len(os_sorted) - 1
-        for i in range(len(os_sorted), n):
-            T[c.CLK, i], T[c.StackPointer, i] = T[c.CLK, last], T[c.StackPointer, last]
-            T[c.FirstUnderflowElement, i] = T[c.FirstUnderflowElement, last]
-            T[c.IB1ShrinkStack, i] = 2
+        for col in (c.CLK, c.StackPointer, c.FirstUnderflowElement):
+            T[col, last + 1:] = T[col, last]
+        T[c.IB1ShrinkStack, last + 1:] = 2
     else:
         T[c.IB1ShrinkStack, :] = 2
         T[c.StackPointer, :] = 16
@@ -572,10 +568,9 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret
             T[c.BezoutCoefficientPolynomialCoefficient0, i], T[c.BezoutCoefficientPolynomialCoefficient1, i] = cur0, cur1
         assert not bez0 and not bez1
         last = len(ram_sorted) - 1
-        for i in range(len(ram_sorted), n):
-            for col in range(c.start, c.start + c.COUNT):
-                T[col, i] = T[col, last]
-            T[c.InstructionType, i] = 2
+        for col in range(c.start, c.start + c.COUNT):
+            T[col, last + 1:] = T[col, last]
+        T[c.InstructionType, last + 1:] = 2
     else:
         T[c.InstructionType, :] = 2
         T[c.BezoutCoefficientPolynomialCoefficient1, :] = 1
@@ -591,32 +586,36 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret
         if js[i][2] == js[i + 1][2]:
             clk_jump_diffs.append(js[i + 1][0] - js[i][0])
     k_max = next(i for i, e in enumerate(js) if e[0] == plen - 1)
-    padded_js = js[:k_max + 1] + [(clk, js[k_max][1], js[k_max][2], js[k_max][3], js[k_max][4]) for clk in range(plen, n)] + js[k_max + 1:]
-    for i, (clk, ci, jsp, jso, jsd) in enumerate(padded_js):
-        T[c.CLK, i], T[c.CI, i], T[c.JSP, i], T[c.JSO, i], T[c.JSD, i] = clk, ci, jsp, jso, jsd
+    head, tail = np.array(js[:k_max + 1], dtype=np.uint64).reshape(-1, 5), np.array(js[k_max + 1:], dtype=np.uint64).reshape(-1, 5)
+    npad = n - plen
+    for k, col in enumerate((c.CLK, c.CI, c.JSP, c.JSO, c.JSD)):
+        T[col, :k_max + 1] = head[:, k]
+        T[col, k_max + 1:k_max + 1 + npad] = np.arange(plen, n, dtype=np.uint64) if k == 0 else head[k_max, k]
+        T[col, k_max + 1 + npad:] = tail[:, k]
 
     # -- processor table (vm.rs:1113-1190, processor.rs:45-95)
     c = MAIN["processor"]
 
-    def put(i, r, padding):
-        T[c.CLK, i], T[c.IP, i], T[c.CI, i], T[c.NIA, i] = r["clk"], r["ip"], r["ci"], r["nia"]
-        for b in range(7):
-            T[c.IB0 + b, i] = (r["ci"] >> b) & 1
-        T[c.JSP, i], T[c.JSO, i], T[c.JSD, i] = r["jsp"], r["jso"], r["jsd"]
-        for k in range(16):
-            T[c.ST0 + k, i] = r["st"][k]
-        T[c.OpStackPointer, i] = r["osp"]
-        for k in range(6):
-            T[c.HV0 + k, i] = r["hv"][k]
-        T[c.IsPadding, i] = 1 if padding else 0
-    for i, r in enumerate(rows):
-        put(i, r, False)
-    for d in clk_jump_diffs:
-        T[c.ClockJumpDifferenceLookupMultiplicity, d] += 1
-    for i in range(plen, n):
-        put(i, dict(rows[-1], clk=i), True)
+    def column(values, col):                               # executed rows, then the last row repeated as padding
+        T[col, :plen] = values
+        T[col, plen:] = values[-1]
+    for key, col in (("clk", c.CLK), ("ip", c.IP), ("ci", c.CI), ("nia", c.NIA), ("jsp", c.JSP), ("jso", c.JSO), ("jsd", c.JSD),
+                     ("osp", c.OpStackPointer)):
+        column(np.array([r[key] for r in rows], dtype=np.uint64), col)
+    T[c.CLK, plen:] = np.arange(plen, n, dtype=np.uint64)
+    ci = T[c.CI]
+    for b in range(7):
+        T[c.IB0 + b] = (ci >> np.uint64(b)) & np.uint64(1)
+    st_cols = np.array([r["st"] for r in rows], dtype=np.uint64)
+    hv_cols = np.array([r["hv"] for r in rows], dtype=np.uint64)
+    for k in range(16):
+        column(st_cols[:, k], c.ST0 + k)
+    for k in range(6):
+        column(hv_cols[:, k], c.HV0 + k)
+    T[c.IsPadding, plen:] = 1
+    np.add.at(T[c.ClockJumpDifferenceLookupMultiplicity], np.array(clk_jump_diffs, dtype=np.int64), np.uint64(1))
     if n > plen:
-        T[c.ClockJumpDifferenceLookupMultiplicity, 1] = (T[c.ClockJumpDifferenceLookupMultiplicity, 1] + (n - plen)) % P
+        T[c.ClockJumpDifferenceLookupMultiplicity, 1] = (int(T[c.ClockJumpDifferenceLookupMultiplicity, 1]) + (n - plen)) % P
 
     # -- hash table (hash.rs:36-302)
     c = MAIN["hash"]
@@ -639,13 +638,13 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret
         for k in range(16):
             T[col(f"Constant{k}"), i] = tip5.ROUND_CONSTANTS[16 * rnd + k] if rnd < 5 else 0
     zero_inv = inv_or_zero((1 << 32) - 1)
-    for i in range(len(hash_rows), n):
-        for e in range(4):
-            T[col(f"State{e}Inv"), i] = zero_inv
-        for k in range(16):
-            T[col(f"Constant{k}"), i] = tip5.ROUND_CONSTANTS[k]
-        T[c.Mode, i] = 0
-        T[c.CI, i] = h_op
+    nh = len(hash_rows)
+    for e in range(4):
+        T[col(f"State{e}Inv"), nh:] = zero_inv
+    for k in range(16):
+        T[col(f"Constant{k}"), nh:] = tip5.ROUND_CONSTANTS[k]
+    T[c.Mode, nh:] = 0
+    T[c.CI, nh:] = h_op
 
     # -- cascade table (cascade.rs:41-66): first-use order of the multiplicity map
     c = MAIN["cascade"]
@@ -655,8 +654,7 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret
         T[c.LookOutLo, i] = lookup8(limb & 0xFF)
         T[c.LookOutHi, i] = lookup8(limb >> 8)
         T[c.LookupMultiplicity, i] = m
-    for i in range(len(cascade_mult), n):
-        T[c.IsPadding, i] = 1
+    T[c.IsPadding, len(cascade_mult):] = 1
 
     # -- lookup table (lookup.rs:84-116)
     c = MAIN["lookup"]
@@ -664,8 +662,7 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret
         T[c.LookIn, i] = i
         T[c.LookOut, i] = lookup8(i)
         T[c.LookupMultiplicity, i] = lookup_mult[i]
-    for i in range(256, n):
-        T[c.IsPadding, i] = 1
+    T[c.IsPadding, 256:] = 1
 
     # -- u32 table (u32.rs:100-154, 193-290): one section per distinct (instruction, operands), first-use order
     c = MAIN["u32"]
@@ -683,17 +680,14 @@ def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret
         pad_ci, pad_lhs, pad_lhs_inv, pad_result = T[c.CI, i - 1], T[c.LHS, i - 1], T[c.LhsInv, i - 1], T[c.Result, i - 1]
         if pad_ci == OPCODES["lt"]:
             pad_result = 2
-    for k in range(i, n):
-        T[c.CI, k], T[c.LHS, k], T[c.LhsInv, k], T[c.Result, k] = pad_ci, pad_lhs, pad_lhs_inv, pad_result
-        T[c.BitsMinus33Inv, k] = F.inv((-33) % P)
+    T[c.CI, i:], T[c.LHS, i:], T[c.LhsInv, i:], T[c.Result, i:] = pad_ci, pad_lhs, pad_lhs_inv, pad_result
+    T[c.BitsMinus33Inv, i:] = F.inv((-33) % P)
 
     if evaluate_substitutions:
         fill_derived_main_columns(T)
     else:
         from . import corc
-        filled = corc.fill_derived_main(np.array(T.tolist(), dtype=np.uint64))
-        for q in range(149, NUM_MAIN):
-            T[q, :] = [int(v) for v in filled[q]]
+        T[149:] = corc.fill_derived_main(T)[149:]
     return T, ex.digest, ex.output
 
 

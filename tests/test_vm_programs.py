@@ -243,7 +243,7 @@ def test_spin_reaches_the_requested_padded_height_and_satisfies_the_air():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("log2_padded_height,ldt", [(13, "fri"), (14, "stir")])
+@pytest.mark.parametrize("log2_padded_height,ldt", [(13, "fri"), (14, "stir"), (16, None)])   # None: Stark::default() picks STIR at 2^16
 def test_gpu_proves_spin_from_the_149_table_columns_and_the_verifier_accepts(backend, log2_padded_height, ldt):
     """The whole device-side pipeline on the reference's benchmark workload at Stark::default() security, checked by the
     verifier INCLUDING the AIR — no oracle prover in the loop, so this scales to heights the oracle cannot reach:
@@ -256,7 +256,8 @@ def test_gpu_proves_spin_from_the_149_table_columns_and_the_verifier_accepts(bac
     backend.fill_derived_main_columns(main)
     assert np.array_equal(main, want_main)
     rcol, arand = inst["randomizer_column"], inst["aux_rand"]
-    choice = tvm_b200.LDT_STIR if ldt == "stir" else tvm_b200.LDT_FRI
+    choice = {"stir": tvm_b200.LDT_STIR, "fri": tvm_b200.LDT_FRI, None: tvm_b200.LDT_AUTO}[ldt]
+    assert inst["derived"]["ldt"] == ("fri" if ldt == "fri" else "stir")
     got = backend.prove((claim.program_digest, claim.input, claim.output), main, inst["main_rand"],
                         lambda ch: (backend.aux_extend(main, ch, rcol), arand), inst["quot_rand"], security_level=160,
                         log2_expansion=2, padded_height=inst["padded_height"], ldt_choice=choice)
