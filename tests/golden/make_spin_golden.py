@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""Regenerates tests/golden/spin_digests.json: Tip5 digests (Tip5::hash(&proof)) of the ORACLE's proofs of the reference's
+benchmark workload ProgramToBench::spin(k) (triton-dev-util/src/lib.rs:49-75) under Stark::default() — at 2^16 that means STIR.
+The oracle is bit-identical to the reference on the reference's own whole-proof known-answer tests (tests/test_golden.py);
+these fixtures extend that anchor to the BASELINE configuration "padded height 2^16" without re-running the oracle
+(≈ 5 minutes) in every test run.  The GPU test compares tvm_prove's proof of the same instance with the digest.
+
+    python tests/golden/make_spin_golden.py [log2_padded_height ...]        (default: 13 16)
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "triton-vm_b200", "py")]
+from oracle import corc, reference_prover as RP, stark as S  # noqa: E402
+import test_vm_programs as tvp  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "spin_digests.json")
+
+
+def main():
+    heights = [int(a) for a in sys.argv[1:]] or [13, 16]
+    out = json.load(open(OUT)) if os.path.exists(OUT) else {}
+    for k in heights:
+        inst = tvp.spin_instance(k, 160, None)
+        claim, main_t, rcol, arand = inst["claim"], inst["main"], inst["randomizer_column"], inst["aux_rand"]
+        t = time.time()
+        proof, _ = S.prove(inst["stark"], claim, main_t, inst["main_rand"],
+                           lambda ch: (corc.aux_extend(main_t, np.asarray(ch, dtype=np.uint64).reshape(63, 3), rcol), arand),
+                           inst["quot_rand"], padded_height=inst["padded_height"])
+        import tvm_b200
+        assert tvm_b200.verify((claim.program_digest, claim.input, claim.output), proof, 160, 2) == (True, "")
+        out[f"spin_{k}"] = {"ldt": inst["derived"]["ldt"], "proof_words": len(proof), "tip5_digest": RP.proof_digest(proof),
+                            "oracle_seconds": round(time.time() - t)}
+        print(k, out[f"spin_{k}"], flush=True)
+        json.dump(out, open(OUT, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

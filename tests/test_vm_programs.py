@@ -262,5 +262,13 @@ def test_gpu_proves_spin_from_the_149_table_columns_and_the_verifier_accepts(bac
                         lambda ch: (backend.aux_extend(main, ch, rcol), arand), inst["quot_rand"], security_level=160,
                         log2_expansion=2, padded_height=inst["padded_height"], ldt_choice=choice)
     assert tvm_b200.proof_padded_height(got) == 1 << log2_padded_height
+    # where the oracle's proof of this very instance has been computed once (tests/golden/make_spin_golden.py, minutes of CPU
+    # time at 2^16), the GPU's proof must hash to the same digest: word-for-word parity at a BASELINE configuration
+    import json, os
+    from oracle import reference_prover as RP
+    fixtures = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spin_digests.json")))
+    fixture = fixtures.get(f"spin_{log2_padded_height}")
+    if fixture and fixture["ldt"] == inst["derived"]["ldt"]:
+        assert len(got) == fixture["proof_words"] and RP.proof_digest([int(v) for v in got]) == fixture["tip5_digest"]
     assert tvm_b200.verify((claim.program_digest, claim.input, claim.output), got, 160, 2, ldt_choice=choice) == (True, "")
     assert tvm_b200.verify((claim.program_digest, claim.input, [1]), got, 160, 2, ldt_choice=choice)[0] is False
