@@ -1,11 +1,12 @@
 #!/usr/bin/env python3
 """Regenerates tests/golden/spin_digests.json: Tip5 digests (Tip5::hash(&proof)) of the ORACLE's proofs of the reference's
-benchmark workload ProgramToBench::spin(k) (triton-dev-util/src/lib.rs:49-75) under Stark::default() — at 2^16 that means STIR.
+benchmark workloads — ProgramToBench::spin(k) (triton-dev-util/src/lib.rs:49-75) and Fibonacci(100) (benches/prove_fib.rs) —
+under Stark::default() — at 2^16 that means STIR.
 The oracle is bit-identical to the reference on the reference's own whole-proof known-answer tests (tests/test_golden.py);
 these fixtures extend that anchor to the BASELINE configuration "padded height 2^16" without re-running the oracle
 (≈ 5 minutes) in every test run.  The GPU test compares tvm_prove's proof of the same instance with the digest.
 
-    python tests/golden/make_spin_golden.py [log2_padded_height ...]        (default: 13 16)
+    python tests/golden/make_spin_golden.py [workload ...]        (default: fib_100 spin_13 spin_16 spin_18)
 """
 import json
 import os
@@ -23,10 +24,11 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "spin_digests.jso
 
 
 def main():
-    heights = [int(a) for a in sys.argv[1:]] or [13, 16]
+    names = sys.argv[1:] or ["fib_100", "spin_13", "spin_16", "spin_18"]
     out = json.load(open(OUT)) if os.path.exists(OUT) else {}
-    for k in heights:
-        inst = tvp.spin_instance(k, 160, None)
+    for name in names:
+        program, inp = tvp._workload(name)
+        inst = tvp.program_instance(program, inp, 160, None)
         claim, main_t, rcol, arand = inst["claim"], inst["main"], inst["randomizer_column"], inst["aux_rand"]
         t = time.time()
         proof, _ = S.prove(inst["stark"], claim, main_t, inst["main_rand"],
@@ -34,9 +36,9 @@ def main():
                            inst["quot_rand"], padded_height=inst["padded_height"])
         import tvm_b200
         assert tvm_b200.verify((claim.program_digest, claim.input, claim.output), proof, 160, 2) == (True, "")
-        out[f"spin_{k}"] = {"ldt": inst["derived"]["ldt"], "proof_words": len(proof), "tip5_digest": RP.proof_digest(proof),
+        out[name] = {"ldt": inst["derived"]["ldt"], "proof_words": len(proof), "tip5_digest": RP.proof_digest(proof),
                             "oracle_seconds": round(time.time() - t)}
-        print(k, out[f"spin_{k}"], flush=True)
+        print(name, out[name], flush=True)
         json.dump(out, open(OUT, "w"), indent=1)
 
 

@@ -209,8 +209,12 @@ SPIN = "read_io 1 addi -3 push 2 pow place 5 call spin halt spin: pick 5 addi -1
 
 
 def spin_instance(log2_padded_height, security, ldt, seed=41):
-    words = tg.assemble(SPIN)
-    inp = [log2_padded_height]
+    return program_instance(SPIN, [log2_padded_height], security, ldt, seed)
+
+
+def program_instance(program, inp, security, ldt, seed=41):
+    words = tg.assemble(program)
+    inp = list(inp)
     ph = tg.padded_height(words, inp)
     st = S.Stark(security, 2, ldt)
     d = st.derive(ph)
@@ -242,14 +246,23 @@ def test_spin_reaches_the_requested_padded_height_and_satisfies_the_air():
     assert tvm_b200.verify((claim.program_digest, claim.input, claim.output), proof, 8, 2, ldt_choice=tvm_b200.LDT_FRI) == (True, "")
 
 
+def _workload(name):
+    from test_fibonacci_program import FIBONACCI
+    kind, arg = name.split("_")
+    return (SPIN, [int(arg)]) if kind == "spin" else (FIBONACCI, [int(arg)])      # fib_100: benches/prove_fib.rs:8-28
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("log2_padded_height,ldt", [(13, "fri"), (14, "stir"), (16, None)])   # None: Stark::default() picks STIR at 2^16
-def test_gpu_proves_spin_from_the_149_table_columns_and_the_verifier_accepts(backend, log2_padded_height, ldt):
-    """The whole device-side pipeline on the reference's benchmark workload at Stark::default() security, checked by the
-    verifier INCLUDING the AIR — no oracle prover in the loop, so this scales to heights the oracle cannot reach:
-    degree-lowering main columns, auxiliary table, proof: all from the GPU."""
+@pytest.mark.parametrize("workload,ldt", [("fib_100", None), ("spin_13", "fri"), ("spin_14", "stir"), ("spin_16", None),
+                                          ("spin_18", None)])    # None: Stark::default() — FRI below 2^16, STIR from there on
+def test_gpu_proves_benchmark_workloads_from_the_149_table_columns(backend, workload, ldt):
+    """The whole device-side pipeline on the reference's benchmark workloads (prove_fib, ProgramToBench::spin) at
+    Stark::default() security, checked by the verifier INCLUDING the AIR — and, where tests/golden/spin_digests.json holds the
+    oracle's digest of the same instance, word for word: degree-lowering main columns, auxiliary table, proof: all from the GPU."""
     import tvm_b200
-    inst = spin_instance(log2_padded_height, 160, ldt)
+    program, inp = _workload(workload)
+    inst = program_instance(program, inp, 160, ldt)
+    log2_padded_height = inst["padded_height"].bit_length() - 1
     claim, want_main = inst["claim"], inst["main"]
     main = want_main.copy()
     main[149:] = 0
@@ -267,7 +280,7 @@ def test_gpu_proves_spin_from_the_149_table_columns_and_the_verifier_accepts(bac
     import json, os
     from oracle import reference_prover as RP
     fixtures = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spin_digests.json")))
-    fixture = fixtures.get(f"spin_{log2_padded_height}")
+    fixture = fixtures.get(workload)
     if fixture and fixture["ldt"] == inst["derived"]["ldt"]:
         assert len(got) == fixture["proof_words"] and RP.proof_digest([int(v) for v in got]) == fixture["tip5_digest"]
     assert tvm_b200.verify((claim.program_digest, claim.input, claim.output), got, 160, 2, ldt_choice=choice) == (True, "")
