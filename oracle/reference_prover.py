@@ -54,7 +54,7 @@ def instance(stark, words, public_input, seed, secret_input=(), initial_ram=None
     d = stark.derive(ph)
     n = d["trace_len"]
     T, digest, out = tg.main_table(words, public_input, n, secret_input, initial_ram, secret_digests)
-    main = np.array(T.tolist(), dtype=np.uint64)
+    main = np.array(T, dtype=np.uint64)
     mrand, arand, rcol, qrand = randomness(seed, n, d["num_trace_randomizers"], d["num_quotient_randomizer_coefficients"])
     claim = S.Claim(digest, list(public_input), list(out))
 

@@ -38,7 +38,7 @@ def tables(program, public_input, n=None, secret_input=()):
         words = tg.assemble(program)
         ph = tg.padded_height(words, public_input, secret_input)
         T, digest, out = tg.main_table(words, public_input, n or ph, secret_input)
-        _CACHE[key] = (T, digest, out, ph, np.array(T.tolist(), dtype=np.uint64))
+        _CACHE[key] = (T, digest, out, ph, np.array(T, dtype=np.uint64))
     return _CACHE[key]
 
 

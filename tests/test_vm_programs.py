@@ -115,7 +115,7 @@ def test_memory_and_merkle_program():
     rng = np.random.default_rng(6)
     sampled = [tuple(int(v) for v in rng.integers(0, P, 3, dtype=np.uint64)) for _ in range(59)]
     ch = S.derive_challenges(sampled, S.Claim(digest, [], list(out)))
-    B = corc.aux_extend(np.array(T.tolist(), dtype=np.uint64), ch)
+    B = corc.aux_extend(np.array(T, dtype=np.uint64), ch)
     assert tg.failing_constraints(T, [[tuple(int(v) for v in B[q][i]) for i in range(n)] for q in range(91)], ch) == []
     executed = {tg._NAME[r["ci"]] for r in ex.rows} | {tg._NAME[r["ci"]] for r in _run(KITCHEN_SINK, SINK_INPUT, SINK_SECRET).rows}
     assert executed | {"skiz", "return", "recurse", "assert", "eq", "mul"} == set(tg.OPCODES)   # the rest: test_fibonacci_program
@@ -220,7 +220,7 @@ def program_instance(program, inp, security, ldt, seed=41):
     d = st.derive(ph)
     n, h = d["trace_len"], d["num_trace_randomizers"]
     T, digest, out = tg.main_table(words, inp, n)
-    main = np.array(T.tolist(), dtype=np.uint64)
+    main = np.array(T, dtype=np.uint64)
     rng = np.random.default_rng(seed)
     mrand, arand, rcol = rand_bfes(rng, (379, h)), rand_bfes(rng, (91, h, 3)), rand_bfes(rng, (n, 3))
     qrand = rand_bfes(rng, (d["num_quotient_randomizer_coefficients"], 3))
