@@ -254,7 +254,8 @@ def _workload(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("workload,ldt", [("fib_100", None), ("spin_13", "fri"), ("spin_14", "stir"), ("spin_16", None),
-                                          ("spin_18", None)])    # None: Stark::default() — FRI below 2^16, STIR from there on
+                                          ("spin_18", None), ("spin_20", None)])   # None: Stark::default() — FRI below 2^16, STIR from
+                                                                                 # there on; spin_20 is the BASELINE headline size
 def test_gpu_proves_benchmark_workloads_from_the_149_table_columns(backend, workload, ldt):
     """The whole device-side pipeline on the reference's benchmark workloads (prove_fib, ProgramToBench::spin) at
     Stark::default() security, checked by the verifier INCLUDING the AIR — and, where tests/golden/spin_digests.json holds the
