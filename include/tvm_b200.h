@@ -211,6 +211,10 @@ int tvm_fill_derived_main_columns(tvm_ctx *ctx, uint64_t *main_trace, unsigned l
  *      used by tests and benchmarks); production callers pass 0. --- */
 int tvm_verify(const tvm_params *params, const tvm_claim *claim, const uint64_t *proof, size_t proof_len, int skip_air_check,
                char *failure, size_t failure_capacity);
+/* `count` independent proofs verified on `num_threads` host threads (0 = all hardware threads); results[i] = what tvm_verify
+ * returns for (claims[i], proofs[i]).  Returns TVM_OK iff all are accepted, else TVM_ERR_VERIFICATION (or TVM_ERR_INVALID_ARG). */
+int tvm_verify_batch(const tvm_params *params, const tvm_claim *claims, const uint64_t *const *proofs, const size_t *proof_lens,
+                     size_t count, int skip_air_check, unsigned num_threads, int *results);
 /* Proof::padded_height (proof.rs:37-56): TVM_ERR_VERIFICATION unless the proof decodes and holds exactly one such item. */
 int tvm_proof_padded_height(const uint64_t *proof, size_t proof_len, uint64_t *padded_height);
 /* device time per stage of the last tvm_prove on this ctx, reference profiler labels; returns #stages */

@@ -155,3 +155,14 @@ def test_plain_c_client(tmp_path):
     assert good.returncode == 0 and "accepted (padded height 256" in good.stdout, good.stderr
     rejected = subprocess.run([exe, str(tmp_path / "bad.txt")], capture_output=True, text=True)
     assert rejected.returncode == 1 and "rejected:" in rejected.stderr
+
+
+def test_batch_verification_on_host_threads():
+    inst, proof = reference_proof("default")
+    claim = _c(inst["claim"])
+    bad = list(proof)
+    bad[777] ^= 1
+    claims = [claim] * 6 + [(claim[0], claim[1], [3])]
+    proofs = [proof, bad, proof, proof, bad, proof, proof]
+    assert tvm_b200.verify_batch(claims, proofs, 160, 2, num_threads=4) == [True, False, True, True, False, True, False]
+    assert tvm_b200.verify_batch(claims[:1], proofs[:1], 160, 2) == [True] and tvm_b200.verify_batch([], [], 160, 2) == []

@@ -11,7 +11,9 @@
 // Failures carry the name of the reference's error variant (VerificationError, error.rs:190-260; LdtVerificationError,
 // low_degree_test/mod.rs).  No CUDA call is made: tvm_verify needs no context and no GPU.
 #include <algorithm>
+#include <atomic>
 #include <map>
+#include <thread>
 #include <set>
 #include <cstring>
 #include "../../include/tvm_b200.h"
@@ -755,4 +757,26 @@ extern "C" int tvm_verify(const tvm_params *params, const tvm_claim *claim, cons
     report("internal error");
     return TVM_ERR_VERIFICATION;
   }
+}
+
+// Many proofs at once: proofs are independent, so the batch is spread over host threads (0 = one per hardware thread).
+// results[i] receives what tvm_verify would return for proof i; the return value is TVM_OK iff every proof is accepted.
+extern "C" int tvm_verify_batch(const tvm_params *params, const tvm_claim *claims, const uint64_t *const *proofs, const size_t *proof_lens,
+                                size_t count, int skip_air_check, unsigned num_threads, int *results) {
+  if (!params || (count && (!claims || !proofs || !proof_lens || !results))) return TVM_ERR_INVALID_ARG;
+  if (!num_threads) num_threads = std::max(1u, std::thread::hardware_concurrency());
+  num_threads = (unsigned)std::min<size_t>(num_threads, std::max<size_t>(count, 1));
+  std::atomic<size_t> next{0};
+  auto worker = [&]() {
+    for (size_t i = next++; i < count; i = next++)
+      results[i] = tvm_verify(params, &claims[i], proofs[i], proof_lens[i], skip_air_check, nullptr, 0);
+  };
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < num_threads; t++) pool.emplace_back(worker);
+  worker();
+  for (auto &th : pool) th.join();
+  int rc = TVM_OK;
+  for (size_t i = 0; i < count; i++)
+    if (results[i] != TVM_OK) rc = results[i] == TVM_ERR_VERIFICATION && rc != TVM_ERR_INVALID_ARG ? TVM_ERR_VERIFICATION : TVM_ERR_INVALID_ARG;
+  return rc;
 }

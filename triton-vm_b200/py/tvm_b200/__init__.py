@@ -113,6 +113,9 @@ _SIGNATURES = {
     "tvm_aux_extend": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint, _u64p, _u64p, _u64p]),
     "tvm_verify": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), _u64p, ctypes.c_size_t, ctypes.c_int,
                                   ctypes.c_char_p, ctypes.c_size_t]),
+    "tvm_verify_batch": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.POINTER(_u64p),
+                                        ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, ctypes.c_int, ctypes.c_uint,
+                                        ctypes.POINTER(ctypes.c_int)]),
     "tvm_proof_padded_height": (ctypes.c_int, [_u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]),
     "tvm_last_prove_timings": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]),
     "tvm_air_quotient_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _u64p, _u64p, ctypes.c_uint,
@@ -183,6 +186,28 @@ def verify(claim, proof, security_level=160, log2_expansion=2, ldt_choice=LDT_AU
     if rc not in (0, -9):
         raise TvmError(rc, lib().tvm_strerror(rc).decode())
     return rc == 0, buf.value.decode()
+
+
+def verify_batch(claims, proofs, security_level=160, log2_expansion=2, ldt_choice=LDT_AUTO, conjectured=False,
+                 skip_air_check=False, num_threads=0):
+    """tvm_verify_batch: independent proofs on host threads -> list of bool (accepted)"""
+    assert len(claims) == len(proofs)
+    keep, cs = [], (ClaimStruct * len(claims))()
+    for i, claim in enumerate(claims):
+        digest, inp, out = claim[0], claim[1], claim[2]
+        ia, iap = _np_u64(np.array(list(inp), dtype=np.uint64))
+        oa, oap = _np_u64(np.array(list(out), dtype=np.uint64))
+        keep += [ia, oa]
+        cs[i] = ClaimStruct((ctypes.c_uint64 * 5)(*[int(v) for v in digest]), claim[3] if len(claim) > 3 else 6, iap, ia.size, oap, oa.size)
+    arrs = [np.ascontiguousarray(np.array(p_, dtype=np.uint64)) for p_ in proofs]
+    ptrs = (_u64p * len(arrs))(*[a.ctypes.data_as(_u64p) for a in arrs])
+    lens = (ctypes.c_size_t * len(arrs))(*[a.size for a in arrs])
+    res = (ctypes.c_int * len(arrs))()
+    p = Params(security_level, log2_expansion, ldt_choice, int(conjectured))
+    rc = lib().tvm_verify_batch(ctypes.byref(p), cs, ptrs, lens, len(arrs), int(skip_air_check), num_threads, res)
+    if rc not in (0, -9):
+        raise TvmError(rc, lib().tvm_strerror(rc).decode())
+    return [r == 0 for r in res]
 
 
 def proof_padded_height(proof):
