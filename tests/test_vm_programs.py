@@ -286,3 +286,31 @@ def test_gpu_proves_benchmark_workloads_from_the_149_table_columns(backend, work
         assert len(got) == fixture["proof_words"] and RP.proof_digest([int(v) for v in got]) == fixture["tip5_digest"]
     assert tvm_b200.verify((claim.program_digest, claim.input, claim.output), got, 160, 2, ldt_choice=choice) == (True, "")
     assert tvm_b200.verify((claim.program_digest, claim.input, [1]), got, 160, 2, ldt_choice=choice)[0] is False
+
+
+# ---- more of the reference's example programs (triton-dev-util/src/example_programs.rs:40-92; token streams) -----------------
+GCD = """read_io 2 dup 1 dup 1 lt skiz swap 1
+  loop_cond: dup 1 push 0 eq skiz call terminate dup 1 dup 1 div_mod swap 2 pop 2 swap 1 call loop_cond
+  terminate: write_io 1 halt"""
+MANY_U32 = """push 1311768464867721216 split push 13387 push 78810 lt push 5 push 7 pow push 69584 push 6796 xor
+  push 64972 push 3915 and push 98668 push 15787 div_mod push 15787 push 98668 div_mod push 98141 push 7397 and
+  push 67749 push 60797 lt push 49528 split push 53483 call lsb push 79655 call is_u32 push 60615 log_2_floor
+  push 13 push 5 pow push 86323 push 37607 xor push 32374 push 20636 pow push 97416 log_2_floor
+  push 14392 push 31589 div_mod halt
+  lsb: push 2 swap 1 div_mod return
+  is_u32: split pop 1 push 0 eq return"""
+
+
+@pytest.mark.parametrize("program,inp,want", [(GCD, [42, 56], [14]), (GCD, [56, 42], [14]), (GCD, [17, 5], [1]), (MANY_U32, [], [])])
+def test_example_programs_satisfy_the_air(program, inp, want):
+    import math
+    words = tg.assemble(program)
+    ex = tg.execute(words, inp)
+    assert ex.output == want and (not inp or want == [math.gcd(*inp)])
+    n = tg.padded_height(words, inp)
+    T, digest, out = tg.main_table(words, inp, n)
+    rng = np.random.default_rng(8)
+    sampled = [tuple(int(v) for v in rng.integers(0, P, 3, dtype=np.uint64)) for _ in range(59)]
+    ch = S.derive_challenges(sampled, S.Claim(digest, list(inp), list(out)))
+    B = corc.aux_extend(np.array(T, dtype=np.uint64), ch)
+    assert tg.failing_constraints(T, [[tuple(int(v) for v in B[q][i]) for i in range(n)] for q in range(91)], ch) == []
