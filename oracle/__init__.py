@@ -9,5 +9,7 @@ routes through it and fails loudly when the CUDA library is missing.
 The oracle restates the reference algorithm (TritonVM/triton-vm @ 8cd9a0eb) and
 the published algorithms of its un-vendored dependency `twenty-first = "2.0.0"`
 (reference `Cargo.toml:104`; field, NTT, Tip5, Merkle tree, BFieldCodec).
-Parity pins: see `oracle/PINNING.md`.
+Parity: PINNED.  The oracle reproduces the reference's Tip5 and Montgomery known answers, the AIR fingerprint and — end to
+end — both whole-proof known-answer digests (proof.rs:200-226, stark.rs:2433-2460; tests/test_golden.py).  Module map and
+pin status: `oracle/README.md`.
 """
