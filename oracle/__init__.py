@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY.  Nothing under `oracle/` is product code: only
 `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` /
 `--impl reference` legs may import, link or execute it, and there only as the
-checker / reported CPU baseline.  The product path (`triton-vm_b200/`) never
+checker / reported CPU baseline (plus the fixture and workload generators under `tests/golden/` and
+`tools/make_workload.py`, which are developer tools).  The product path (`triton-vm_b200/`) never
 routes through it and fails loudly when the CUDA library is missing.
 
 The oracle restates the reference algorithm (TritonVM/triton-vm @ 8cd9a0eb) and
