@@ -204,15 +204,3 @@ def test_plain_c_prover_client_builds_and_fails_loudly_without_a_gpu(tmp_path):
         assert r.returncode == 3 and "no CPU fallback" in r.stderr           # tvm_ctx_create refuses: nothing is computed on the host
     else:
         assert r.returncode == 0 and "verified" in r.stdout, r.stderr
-
-
-@pytest.mark.gpu
-def test_plain_c_prover_client_proves_halt_on_the_gpu(tmp_path):
-    import subprocess
-    exe = _build_example(tmp_path, "prove_tables")
-    digest = _write_prove_tables_dir(tmp_path)
-    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
-    assert r.returncode == 0 and "verified" in r.stdout, r.stderr
-    proof = np.fromfile(str(tmp_path / "proof.u64"), dtype="<u8")
-    assert tvm_b200.verify((digest, [], []), proof, 8, 2, ldt_choice=tvm_b200.LDT_FRI) == (True, "")
-    assert S.verify(S.Stark(8, 2, "fri"), S.Claim(digest, [], []), [int(v) for v in proof], check_air=True)
