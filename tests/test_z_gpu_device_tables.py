@@ -27,7 +27,6 @@ def test_device_fills_derived_main_columns(backend):
     assert np.array_equal(rnd, want)
 
 
-@pytest.mark.xfail(strict=False, reason="non-default kernel variant written after the round's last GPU run; never executed on a GPU yet")
 def test_parallel_scan_of_chunk_totals_variant():
     # TVM_AUX_TOPS_PARALLEL is read once per process: run both variants in fresh interpreters at n = 2^17 (512 chunks, two
     # per thread of the CTA-wide scan) and compare digests of the complete auxiliary table; the default (sequential) variant
