@@ -236,7 +236,21 @@ class Emitter:
                 elif rx: expr, resx = f"xmulb({rn}, {ln})", True
                 else: expr, resx = f"fmul({ln}, {rn})", False
             else:
-                if lx and rx: expr, resx = f"xadd({ln}, {rn})", True
+                # x + (-1) * y is a subtraction: fsub costs 5 instructions, fneg + fadd 11 (the negation is still emitted
+                # above, the compiler drops it when nothing else uses it)
+                sub = None
+                for pos, neg in ((l, r), (r, l)):
+                    if neg.kind == "*" and (self.is_neg_one(neg.lhs) or self.is_neg_one(neg.rhs)):
+                        y = neg.rhs if self.is_neg_one(neg.lhs) else neg.lhs
+                        px, yx = self.isx[id(pos)], self.isx[id(y)]
+                        pn, yn = self.name[id(pos)], self.name[id(y)]
+                        if px and yx: sub = (f"xsub({pn}, {yn})", True)
+                        elif px: sub = (f"xsubb({pn}, {yn})", True)
+                        elif not yx: sub = (f"fsub({pn}, {yn})", False)
+                        if sub:
+                            break
+                if sub: expr, resx = sub
+                elif lx and rx: expr, resx = f"xadd({ln}, {rn})", True
                 elif lx: expr, resx = f"xaddb({ln}, {rn})", True
                 elif rx: expr, resx = f"xaddb({rn}, {ln})", True
                 else: expr, resx = f"fadd({ln}, {rn})", False
@@ -269,6 +283,13 @@ __global__ void __launch_bounds__(AIR_THREADS, %(minb)d) %(kname)s(AirArgs a) {
   (void)mn; (void)an; (void)ac; (void)mc; (void)coset;
 """
 
+BODY_HEADER = """
+// constraints %(first)d..%(last)d of the evaluator order (%(cat)s), %(nops)d operations
+static __device__ __noinline__ void %(bname)s(const u64 *mc, const u64 *mn, const u64 *ac, const u64 *an, const AirStrides a,
+                                              AirAcc &acc_io) {
+  (void)mn; (void)an; (void)ac; (void)mc;
+"""
+
 TU_FOOTER = """
 void %(tuname)s_launch(const AirArgs &a, const u64 *d_wtab, const u64 *d_challenges, cudaStream_t s, unsigned long long *launches) {
   cudaMemcpyToSymbolAsync(c_w, d_wtab, sizeof(u64) * %(nw)d, 0, cudaMemcpyDeviceToDevice, s);
@@ -281,35 +302,96 @@ void %(tuname)s_launch(const AirArgs &a, const u64 *d_wtab, const u64 *d_challen
 """
 
 
-def emit_chunk(air, idx, cat, items):
+def emit_body(air, idx, cat, items, fused):
+    """the straight-line code of one chunk: (lines, accumulate lines, #operations)"""
     b = air.builders[cat]
     em = Emitter(b)
     roots = [n for _, piece in items for n in piece_leaves(piece)]
     for n in reachable_postorder(roots):
         em.emit_node(n)
     results = [em.emit_piece(piece) for _, piece in items]
+    body = []
+    for k, line in enumerate(em.lines):
+        body.append(line)
+        if not fused and SYNC_EVERY and (k + 1) % SYNC_EVERY == 0:
+            body.append("__syncthreads();   // instruction-fetch locality: the CTA's warps share one I-cache window")
+    accs = []
+    for (j, _), (nm, isx) in zip(items, results):
+        accs.append(f"air_acc_{'x' if isx else 'b'}(acc, c_w + {WTAB_WORDS * j}, {nm});")
+    nops = sum(1 for n in reachable_postorder(roots) if n.kind in "+*")
+    return body, accs, nops
+
+
+def emit_chunk(air, idx, cat, items):
+    body, accs, nops = emit_body(air, idx, cat, items, False)
     kname = f"air_chunk_{idx:03d}_{cat}"
     if SYNC_EVERY:
         guard = "  const bool active = m < a.nrows;\n  if (!active) m = 0;   // keep every thread alive for the block-wide barriers below"
     else:
         guard = "  if (m >= a.nrows) return;\n  const bool active = true;"
     src = [KERNEL_HEADER % {"kname": kname, "guard": guard, "minb": MIN_BLOCKS}]
-    body = []
-    for k, line in enumerate(em.lines):
-        body.append(line)
-        if SYNC_EVERY and (k + 1) % SYNC_EVERY == 0:
-            body.append("__syncthreads();   // instruction-fetch locality: the CTA's warps share one I-cache window")
     src.append("  " + "\n  ".join(body))
     src.append("  AirAcc acc; air_acc_zero(acc);")
-    for (j, _), (nm, isx) in zip(items, results):
-        if isx:
-            src.append(f"  air_acc_x(acc, c_w + {WTAB_WORDS * j}, {nm});")
-        else:
-            src.append(f"  air_acc_b(acc, c_w + {WTAB_WORDS * j}, {nm});")
+    src.extend("  " + x for x in accs)
     src.append(f"  if (active) air_accumulate_{cat}(a, m, coset, air_acc_reduce(acc));")
     src.append("}")
-    nops = sum(1 for n in reachable_postorder(roots) if n.kind in "+*")
     return kname, "\n".join(src), nops
+
+
+# ---- fused groups (default) ---------------------------------------------------------------------------------------
+# One kernel per GROUP of consecutive chunks of a category: the chunk bodies stay separate instruction-cache sized
+# functions (`__noinline__`, their own register allocation), the group kernel calls them one after the other on the same
+# rows with a block-wide barrier in between, so that (a) the warps of a CTA execute the same body at the same time and
+# share one instruction-cache window, (b) the weighted sum is carried across bodies in the unreduced accumulator: one
+# reduction, one zerofier multiplication and ONE read-modify-write of the output per group instead of per chunk
+# (147 -> ~16 passes over the 3 output planes), (c) columns touched by several bodies of the group are re-read by the
+# same CTA right away (L1/L2 hits) instead of by another kernel launch from HBM.  Evaluator order keeps the constraints
+# of one table together, so consecutive chunks share their columns.
+FUSED = os.environ.get("TVM_AIR_FUSED", "1") != "0"
+GROUP_BUDGET = float(os.environ.get("TVM_AIR_GROUP_BUDGET", "700"))
+
+
+def emit_group(air, gidx, cat, chunk_ids, chunks):
+    parts, calls, nops_total = [], [], 0
+    for idx in chunk_ids:
+        _, items = chunks[idx]
+        body, accs, nops = emit_body(air, idx, cat, items, True)
+        nops_total += nops
+        bname = f"air_body_{idx:03d}_{cat}"
+        src = [BODY_HEADER % {"bname": bname, "first": items[0][0], "last": items[-1][0], "cat": cat, "nops": nops}]
+        src.append("  " + "\n  ".join(body))
+        src.append("  AirAcc acc = acc_io;")
+        src.extend("  " + x for x in accs)
+        src.append("  acc_io = acc;")
+        src.append("}")
+        parts.append("\n".join(src))
+        calls.append(f"  {bname}(mc, mn, ac, an, st, acc);")
+    kname = f"air_group_{gidx:02d}_{cat}"
+    guard = "  const bool active = m < a.nrows;\n  if (!active) m = a.nrows - 1;   // every thread takes part in the block-wide barriers below"
+    k = [KERNEL_HEADER % {"kname": kname, "guard": guard, "minb": MIN_BLOCKS}]
+    k.append("  const AirStrides st{a.main_stride, a.aux_stride};")
+    k.append("  AirAcc acc; air_acc_zero(acc);")
+    k.append("\n  __syncthreads();   // the CTA's warps share one instruction-cache window\n".join(calls))
+    k.append(f"  if (active) air_accumulate_{cat}(a, m, coset, air_acc_reduce(acc));")
+    k.append("}")
+    parts.append("\n".join(k))
+    return kname, "\n".join(parts), nops_total
+
+
+def group_chunks(air, chunks):
+    """consecutive chunks of one category whose estimated cost stays below GROUP_BUDGET"""
+    groups, cur, cur_cat, cost = [], [], None, 0.0
+    for idx, (cat, items) in enumerate(chunks):
+        b = air.builders[cat]
+        roots = [n for _, piece in items for n in piece_leaves(piece)]
+        c = sum(node_cost(b, x) for x in reachable_postorder(roots) if x.kind in "+*") + 6.0 * len(items)
+        if cur and (cat != cur_cat or cost + c > GROUP_BUDGET):
+            groups.append((cur_cat, cur))
+            cur, cost = [], 0.0
+        cur.append(idx); cur_cat = cat; cost += c
+    if cur:
+        groups.append((cur_cat, cur))
+    return groups
 
 
 def main():
@@ -323,14 +405,18 @@ def main():
     tus = [[] for _ in range(NUM_TUS)]
     load = [0.0] * NUM_TUS
     names, total_ops = [], 0
-    order = sorted(range(len(chunks)), key=lambda i: -len(chunks[i][1]))
-    emitted = {}
-    for idx, (cat, items) in enumerate(chunks):
-        emitted[idx] = emit_chunk(air, idx, cat, items)
+    if FUSED:
+        groups = group_chunks(air, chunks)
+        units = {g: emit_group(air, g, cat, ids, chunks) for g, (cat, ids) in enumerate(groups)}
+        unit_meta = {g: (cat, sum(len(chunks[i][1]) for i in ids)) for g, (cat, ids) in enumerate(groups)}
+    else:
+        units = {idx: emit_chunk(air, idx, cat, items) for idx, (cat, items) in enumerate(chunks)}
+        unit_meta = {idx: (cat, len(items)) for idx, (cat, items) in enumerate(chunks)}
+    order = sorted(units, key=lambda i: -units[i][2])
     for idx in order:
         t = min(range(NUM_TUS), key=lambda i: load[i])
         tus[t].append(idx)
-        load[t] += emitted[idx][2] + 20
+        load[t] += units[idx][2] + 20
     nw = WTAB_WORDS * total_constraints
     tu_names = []
     for t, idxs in enumerate(tus):
@@ -342,9 +428,9 @@ def main():
         parts = [TU_HEADER % {"nw": nw}, "}  // namespace"]
         launches = []
         for idx in idxs:
-            kname, src, nops = emitted[idx]
-            cat, items = chunks[idx]
-            names.append((kname, cat, len(items), nops))
+            kname, src, nops = units[idx]
+            cat, ncons = unit_meta[idx]
+            names.append((kname, cat, ncons, nops))
             total_ops += nops
             parts.append(src)
             launches.append(f"  {kname}<<<grid, AIR_THREADS, 0, s>>>(a);")
@@ -354,8 +440,8 @@ def main():
     unique_ops = sum(sum(1 for n in reachable_postorder(air.constraints[c]) if n.kind in "+*") for c in CATEGORIES)
     with open(os.path.join(OUT_DIR, "air_chunks.inc"), "w") as f:
         f.write("// GENERATED by airgen/codegen_cuda.py - do not edit.\n")
-        f.write(f"// {len(names)} chunk kernels in {len(tu_names)} translation units, {total_ops} binary operations emitted "
-                f"({unique_ops} unique in the circuit), chunk budget {CHUNK_COST_BUDGET:g}\n")
+        f.write(f"// {len(names)} {'group' if FUSED else 'chunk'} kernels ({len(chunks)} chunk bodies) in {len(tu_names)} translation units, "
+                f"{total_ops} binary operations emitted ({unique_ops} unique in the circuit), chunk budget {CHUNK_COST_BUDGET:g}\n")
         for tuname in tu_names:
             f.write(f"TVM_AIR_TU({tuname})\n")
         for kname, cat, ncons, nops in sorted(names):

@@ -75,6 +75,7 @@ void lde_interpolate_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned
                          u64 offset_mont, size_t ncols, u64 *d_coef, size_t coef_stride, u64 *d_tmp) {
   const size_t n = (size_t)1 << log2_trace;
   if (num_rand > n) throw ApiError{TVM_ERR_INVALID_ARG, "more trace randomizers than trace rows"};
+  if (lde_interpolate_tiles(c, d_trace, d_rand, num_rand, rand_pad, log2_trace, offset_mont, ncols, d_coef, coef_stride, d_tmp)) return;
   NttJob inv{};
   inv.in = d_trace; inv.in_cstride = n;
   inv.out = d_coef; inv.out_cstride = coef_stride;
@@ -90,6 +91,9 @@ void lde_interpolate_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned
 void lde_evaluate_run(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_count, unsigned log2_trace, unsigned log2_cosets,
                       unsigned coset_first, unsigned coset_step, unsigned num_cosets, size_t ncols, u64 *d_out, u64 *d_tmp) {
   const size_t n = (size_t)1 << log2_trace;
+  if (lde_evaluate_tiles(c, d_coef, coef_stride, fold_count, log2_trace, log2_cosets, coset_first, coset_step, num_cosets, ncols, d_out,
+                         d_tmp))
+    return;
   NttJob fwd{};
   fwd.in = d_coef; fwd.in_cstride = coef_stride;
   fwd.out = d_out; fwd.out_cstride = n;  // per (col*num_cosets + y)

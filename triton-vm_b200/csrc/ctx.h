@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <functional>
 #include <map>
 #include <string>
 #include <tuple>
@@ -56,6 +57,10 @@ struct Ctx {
   std::map<std::pair<int, int>, u64 *> tile_tw;                     // (LT, inverse) -> omega_{2^LT}^(+-e)
   std::map<std::tuple<u64, int, int>, std::pair<u64 *, u64 *>> pow_tabs;  // (base, log_count, shift)
   std::vector<void *> owned;
+  // coset pre-scale tables of the tile NTT (ntt_tile.cu): key = (log_n, log_r, log_n1, M, first, step, count)
+  std::map<std::tuple<unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned>, u64 *> prescale_tabs;
+  u64 *get_prescale(unsigned log_n, unsigned log_r, unsigned log_n1, unsigned M, unsigned first, unsigned step, unsigned count,
+                    const std::function<void(u64 *, u64 *)> &fill);
 
   // scratch arena (grown on demand, reused)
   DevBuf scratch[4];

@@ -360,6 +360,245 @@ __global__ void __launch_bounds__(HASHQ2_THREADS) tip5_hash_rows_quad2_kernel(Ha
   }
 }
 
+// ---- MDS on the tensor cores: IMMA.16832.U8.U8 -----------------------------------------------------
+// The linear layer y = M x (tip-0005.md:100-104) is a dense 16x16 integer matrix product applied to every state:
+// the one dense contraction on the prover's path.  M's entries are 16-bit and the state words 64-bit, so with
+// byte limbs  x_e = sum_s 2^(8s) X_s[e],  M = M_0 + 2^8 M_1  the product is
+//     y_o = sum_{s=0..8} 2^(8s) T_s[o],      T_s = M_0 X_s + M_1 X_{s-1}      (X_{-1} = X_8 = 0, T_s < 2^21),
+// and T_s for 16 states x 8 outputs is exactly one mma.sync.m16n8k32 (u8 x u8 -> s32): K = 32 = 16 state elements x
+// {limb s against M_0, limb s-1 against M_1}.  Layout: the quad layout of the kernels above with two rows per quad
+// IS the IMMA A-fragment layout (fragment row g / g+8 = first / second row of quad g, fragment k = 4l+t = element
+// l+4t of lane l), and choosing the B-fragment column order as o(j, n) = (n >> 1) + 4 (2j + (n & 1)) makes the
+// D fragment of N-block j land on the lane that owns the output element: c0/c1 = elements l+8j, l+8j+4 of the first row,
+// c2/c3 of the second.  No shuffles, 18 IMMA + 64 IMAD.WIDE (limb recombination) per lane and round instead of
+// 256 IMAD.WIDE + 64 SHFL + 64 SEL.  The M_0 / M_1 fragments are 4 constant registers per lane.
+__device__ __forceinline__ void imma_16832_u8(int (&d)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                              unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+__device__ __forceinline__ u64 mad_wide(unsigned a, unsigned b, u64 c) {
+  u64 d;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+}
+struct MdsFrag { unsigned b[2][2]; };   // [N-block][k < 16 : k >= 16]
+__constant__ unsigned short c_mds_col[16] = TVM_MDS_COL;
+__constant__ unsigned c_pow256[4] = {1u, 1u << 8, 1u << 16, 1u << 24};
+__device__ __forceinline__ MdsFrag mds_fragments(int lane) {
+  const int g = lane >> 2, l = lane & 3;
+  MdsFrag f;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int o = (g >> 1) + 4 * (2 * j + (g & 1));
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const unsigned m = c_mds_col[(o - (l + 4 * i)) & 15];
+      lo |= (m & 0xFF) << (8 * i);
+      hi |= (m >> 8) << (8 * i);
+    }
+    f.b[j][0] = lo; f.b[j][1] = hi;
+  }
+  return f;
+}
+// bytes s of four 32-bit words -> one register per s
+__device__ __forceinline__ void byte_transpose4(unsigned w0, unsigned w1, unsigned w2, unsigned w3, unsigned (&o)[4]) {
+  const unsigned t01l = __byte_perm(w0, w1, 0x5140), t01h = __byte_perm(w0, w1, 0x7362);
+  const unsigned t23l = __byte_perm(w2, w3, 0x5140), t23h = __byte_perm(w2, w3, 0x7362);
+  o[0] = __byte_perm(t01l, t23l, 0x5410); o[1] = __byte_perm(t01l, t23l, 0x7632);
+  o[2] = __byte_perm(t01h, t23h, 0x5410); o[3] = __byte_perm(t01h, t23h, 0x7632);
+}
+// lo + 2^32 hi + rc  (lo < 2^46, hi < 2^54, rc canonical) reduced to canonical form.  Four homogeneous carry chains
+// (16 instructions; the compare/select code nvcc emits for the C formulation is ~45):
+//   V = lo + rc + (hi << 32) = w0 + 2^32 w1 + 2^64 w2 (w2 < 2^23);  2^64 = 2^32 - 1 (mod p):  s = (w0, w1) - w2 + 2^32 w2
+//   tracked as s + n 2^64 with n in {0, 1} (a borrow of the subtraction is always cancelled by the carry of the addition);
+//   result = s + n 2^64 - p if that is >= 0, else s:  u = s + (2^32 - 1) and the carry / n select.
+__device__ __forceinline__ u64 mds_finish(u64 lo, u64 hi, u64 rc) {
+  u64 r;
+  asm("{\n\t"
+      ".reg .u32 l0, l1, h0, h1, r0, r1, w0, w1, w2, s0, s1, m, n, u0, u1, k;\n\t"
+      ".reg .pred q;\n\t"
+      "mov.b64 {l0, l1}, %1;\n\t"
+      "mov.b64 {h0, h1}, %2;\n\t"
+      "mov.b64 {r0, r1}, %3;\n\t"
+      "add.cc.u32 w0, l0, r0;\n\t"
+      "addc.cc.u32 w1, l1, r1;\n\t"
+      "addc.u32 w2, h1, 0;\n\t"
+      "add.cc.u32 w1, w1, h0;\n\t"
+      "addc.u32 w2, w2, 0;\n\t"
+      "sub.cc.u32 s0, w0, w2;\n\t"
+      "subc.cc.u32 s1, w1, 0;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "add.cc.u32 s1, s1, w2;\n\t"
+      "addc.u32 n, m, 0;\n\t"
+      "add.cc.u32 u0, s0, 0xffffffff;\n\t"
+      "addc.cc.u32 u1, s1, 0;\n\t"
+      "addc.u32 k, n, 0;\n\t"
+      "setp.ne.u32 q, k, 0;\n\t"
+      "selp.u32 s0, u0, s0, q;\n\t"
+      "selp.u32 s1, u1, s1, q;\n\t"
+      "mov.b64 %0, {s0, s1};\n\t"
+      "}"
+      : "=l"(r)
+      : "l"(lo), "l"(hi), "l"(rc));
+  return r;
+}
+__device__ __forceinline__ void quad2_mds_mma(u64 (&a)[4], u64 (&b)[4], int l, const MdsFrag &f, const u64 *rc_smem, int rnd) {
+  unsigned La[8], Lb[8];
+  {
+    unsigned o[4];
+    byte_transpose4((unsigned)a[0], (unsigned)a[1], (unsigned)a[2], (unsigned)a[3], o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) La[i] = o[i];
+    byte_transpose4((unsigned)(a[0] >> 32), (unsigned)(a[1] >> 32), (unsigned)(a[2] >> 32), (unsigned)(a[3] >> 32), o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) La[4 + i] = o[i];
+    byte_transpose4((unsigned)b[0], (unsigned)b[1], (unsigned)b[2], (unsigned)b[3], o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) Lb[i] = o[i];
+    byte_transpose4((unsigned)(b[0] >> 32), (unsigned)(b[1] >> 32), (unsigned)(b[2] >> 32), (unsigned)(b[3] >> 32), o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) Lb[4 + i] = o[i];
+  }
+  // 2^8, 2^16, 2^24 from constant memory, which neither nvcc nor ptxas folds: a literal power of two is strength-reduced
+  // from one IMAD.WIDE into SHL + HI + two carry adds
+  const unsigned pw[4] = {1u, c_pow256[1], c_pow256[2], c_pow256[3]};
+  // accumulators: [row a/b][t = 2j + c]
+  u64 lo[2][4], hi[2][4];
+#pragma unroll
+  for (int s = 0; s <= 8; s++) {
+    const unsigned a0 = s < 8 ? La[s] : 0u, a1 = s < 8 ? Lb[s] : 0u;
+    const unsigned a2 = s > 0 ? La[s - 1] : 0u, a3 = s > 0 ? Lb[s - 1] : 0u;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      int d[4];
+      imma_16832_u8(d, a0, a1, a2, a3, f.b[j][0], f.b[j][1]);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int row = c >> 1, t = 2 * j + (c & 1);
+        const unsigned v = (unsigned)d[c];
+        if (s == 0) lo[row][t] = v;
+        else if (s < 4) lo[row][t] = mad_wide(v, pw[s], lo[row][t]);
+        else if (s == 4) hi[row][t] = v;
+        else if (s < 8) hi[row][t] = mad_wide(v, pw[s - 4], hi[row][t]);
+        else hi[row][t] += (u64)v << 32;
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const u64 rc = rc_smem[16 * rnd + l + 4 * t];
+    a[t] = mds_finish(lo[0][t], hi[0][t], rc);
+    b[t] = mds_finish(lo[1][t], hi[1][t], rc);
+  }
+}
+__device__ __forceinline__ void tip5_perm_quad2_mma(u64 (&a)[4], u64 (&b)[4], int l, const MdsFrag &f, const unsigned char *lut,
+                                                    const u64 *rc_smem) {
+#pragma unroll 1
+  for (int rnd = 0; rnd < TIP5_ROUNDS; rnd++) {
+    quad_sbox(a, lut);
+    quad_sbox(b, lut);
+    quad2_mds_mma(a, b, l, f, rc_smem, rnd);
+  }
+}
+
+static constexpr int HASHM_THREADS = 128;   // 32 quads, 64 rows per CTA
+__global__ void __launch_bounds__(HASHM_THREADS) tip5_hash_rows_mma_kernel(HashRowsParams p) {
+  __shared__ unsigned char lut[256];
+  __shared__ u64 rc[80];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
+  for (int i = threadIdx.x; i < 80; i += blockDim.x) rc[i] = c_tip5_rc[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l = lane & 3;
+  const MdsFrag f = mds_fragments(lane);
+  constexpr int QUADS = HASHM_THREADS / 4;
+  size_t mrow[2];
+  bool active[2];
+  const u64 *base[2];
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    size_t m = (size_t)blockIdx.x * (2 * QUADS) + (threadIdx.x >> 2) + (size_t)t * QUADS;
+    active[t] = m < p.nrows;
+    if (!active[t]) m = p.nrows - 1;                              // the whole warp takes part in the IMMA
+    mrow[t] = m;
+    const size_t per_ = p.nrows >> p.log_r, cs_ = m / per_;
+    base[t] = p.table + m + cs_ * (p.coset_mem_stride - 1) * per_;
+  }
+  u64 a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  unsigned c = 0;
+  for (; c + 10 <= p.ncols; c += 10) {
+    a[0] = base[0][(size_t)(c + l) * p.col_stride];
+    b[0] = base[1][(size_t)(c + l) * p.col_stride];
+    a[1] = base[0][(size_t)(c + l + 4) * p.col_stride];
+    b[1] = base[1][(size_t)(c + l + 4) * p.col_stride];
+    if (l < 2) {
+      a[2] = base[0][(size_t)(c + l + 8) * p.col_stride];
+      b[2] = base[1][(size_t)(c + l + 8) * p.col_stride];
+    }
+    tip5_perm_quad2_mma(a, b, l, f, lut, rc);
+  }
+  unsigned rem = p.ncols - c;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    unsigned e = (unsigned)(l + 4 * i);
+    if (e < 10) {
+      u64 va = 0, vb = 0;
+      if (e < rem) { va = base[0][(size_t)(c + e) * p.col_stride]; vb = base[1][(size_t)(c + e) * p.col_stride]; }
+      else if (e == rem) { va = MONT_ONE; vb = MONT_ONE; }
+      a[i] = va; b[i] = vb;
+    }
+  }
+  tip5_perm_quad2_mma(a, b, l, f, lut, rc);
+  const size_t per = p.nrows >> p.log_r;
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    if (!active[t]) continue;
+    size_t m = mrow[t];
+    size_t coset = m / per, k = m - coset * per;
+    u64 *d = p.digests + (coset + (k << p.log_r)) * 5;
+    const u64 *s = t ? b : a;
+    d[l] = s[0];
+    if (l == 0) d[4] = s[1];
+  }
+}
+
+// Inner tree nodes on the same permutation: a quad computes nodes lo + q and lo + q + count/2... (two nodes per quad).
+__global__ void __launch_bounds__(HASHM_THREADS) merkle_level_mma_kernel(u64 *nodes, size_t lo, size_t count) {
+  __shared__ unsigned char lut[256];
+  __shared__ u64 rc[80];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
+  for (int i = threadIdx.x; i < 80; i += blockDim.x) rc[i] = c_tip5_rc[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l = lane & 3;
+  const MdsFrag f = mds_fragments(lane);
+  constexpr int QUADS = HASHM_THREADS / 4;
+  size_t node[2];
+  bool active[2];
+  u64 s[2][4];
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    size_t q = (size_t)blockIdx.x * (2 * QUADS) + (threadIdx.x >> 2) + (size_t)t * QUADS;
+    active[t] = q < count;
+    if (!active[t]) q = count - 1;
+    node[t] = lo + q;
+    const u64 *ch = nodes + 10 * node[t];          // children 2i, 2i+1 are adjacent: 10 words
+    s[t][0] = ch[l];
+    s[t][1] = ch[l + 4];
+    s[t][2] = l < 2 ? ch[l + 8] : MONT_ONE;
+    s[t][3] = MONT_ONE;
+  }
+  tip5_perm_quad2_mma(s[0], s[1], l, f, lut, rc);
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    if (!active[t]) continue;
+    u64 *d = nodes + 5 * node[t];
+    d[l] = s[t][0];
+    if (l == 0) d[4] = s[t][1];
+  }
+}
+
 // ---- two lanes per row ------------------------------------------------------------------------------
 // Measured cost model (tools/microbench/field_ops.cu, SMSP-clocks per warp instruction group): the MDS step
 // of the 4-lane layout costs 635 per round against 355 for the three x^7 - its 32 shuffles (4 clocks
@@ -510,7 +749,13 @@ void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, un
                    unsigned coset_mem_stride) {
   HashRowsParams p{table, col_stride, nrows, ncols, log_r, digests, coset_mem_stride};
   static const bool use_thread_per_row = getenv("TVM_TIP5_THREAD_PER_ROW") != nullptr;
-  if (coset_mem_stride != 1) {   // only the default kernel knows about strided cosets
+  static const bool use_imad_mds = getenv("TVM_TIP5_IMAD_MDS") != nullptr;   // A/B: the round-1 default (MDS on the integer pipe)
+  if (!use_imad_mds && !use_thread_per_row && !getenv("TVM_TIP5_ONE_ROW_PER_QUAD") && !getenv("TVM_TIP5_TWO_LANES") &&
+      !getenv("TVM_TIP5_SMEM_EXCHANGE")) {
+    const size_t rows_per_cta = HASHM_THREADS / 2;
+    unsigned grid = (unsigned)((nrows + rows_per_cta - 1) / rows_per_cta);
+    tip5_hash_rows_mma_kernel<<<grid, HASHM_THREADS, 0, c.stream>>>(p);
+  } else if (coset_mem_stride != 1) {   // of the A/B variants only quad2 knows about strided cosets
     const size_t rows_per_cta = HASHQ2_THREADS / 2;
     unsigned grid = (unsigned)((nrows + rows_per_cta - 1) / rows_per_cta);
     tip5_hash_rows_quad2_kernel<false><<<grid, HASHQ2_THREADS, 0, c.stream>>>(p);
@@ -536,14 +781,25 @@ void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, un
   TVM_CUDA(cudaGetLastError());
 }
 
+static void merkle_level_launch(Ctx &c, u64 *nodes, size_t lo, size_t count, bool thread_per_node) {
+  if (thread_per_node || count < 64) {
+    unsigned grid = (unsigned)((count + HASH_THREADS - 1) / HASH_THREADS);
+    merkle_level_kernel<<<grid, HASH_THREADS, 0, c.stream>>>(nodes, lo, count);
+  } else {
+    const size_t per_cta = HASHM_THREADS / 2;
+    unsigned grid = (unsigned)((count + per_cta - 1) / per_cta);
+    merkle_level_mma_kernel<<<grid, HASHM_THREADS, 0, c.stream>>>(nodes, lo, count);
+  }
+  c.launches++;
+}
+
 // leaves already stored at nodes[nleaves .. 2*nleaves)
 void merkle_run(Ctx &c, u64 *nodes, size_t nleaves) {
   size_t w = nleaves / 2;
   const size_t TOP = 64;
+  static const bool thread_per_node = getenv("TVM_TIP5_IMAD_MDS") != nullptr;
   for (; w > TOP; w >>= 1) {
-    unsigned grid = (unsigned)((w + HASH_THREADS - 1) / HASH_THREADS);
-    merkle_level_kernel<<<grid, HASH_THREADS, 0, c.stream>>>(nodes, w, w);
-    c.launches++;
+    merkle_level_launch(c, nodes, w, w, thread_per_node);
   }
   if (w >= 1) {
     merkle_top_kernel<<<1, HASH_THREADS, 0, c.stream>>>(nodes, w);
@@ -559,9 +815,8 @@ void merkle_run_sharded(Ctx &c, u64 *nodes, size_t nleaves, unsigned rank, unsig
   if (W <= 1 || nleaves < 2 * (size_t)W) { merkle_run(c, nodes, nleaves); return; }
   for (size_t w = nleaves / 2; w >= W; w >>= 1) {
     const size_t cnt = w / W;
-    unsigned grid = (unsigned)((cnt + HASH_THREADS - 1) / HASH_THREADS);
-    merkle_level_kernel<<<grid, HASH_THREADS, 0, c.stream>>>(nodes, w + rank * cnt, cnt);
-    c.launches++;
+    static const bool thread_per_node = getenv("TVM_TIP5_IMAD_MDS") != nullptr;
+    merkle_level_launch(c, nodes, w + rank * cnt, cnt, thread_per_node);
   }
   TVM_CUDA(cudaGetLastError());
   c.all_gather(nodes + 5 * (size_t)W, 40);

@@ -40,6 +40,11 @@ void lde_interpolate_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned
                          u64 offset_mont, size_t ncols, u64 *d_coef, size_t coef_stride, u64 *d_tmp);
 void lde_evaluate_run(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_count, unsigned log2_trace, unsigned log2_cosets,
                       unsigned coset_first, unsigned coset_step, unsigned num_cosets, size_t ncols, u64 *d_out, u64 *d_tmp);
+// ntt_tile.cu: the same contracts on the two-round tile kernels; false = size not covered, use the kernels of ntt.cu
+bool lde_evaluate_tiles(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_count, unsigned log_n, unsigned log_r,
+                        unsigned coset_first, unsigned coset_step, unsigned num_cosets, size_t ncols, u64 *d_out, u64 *d_tmp);
+bool lde_interpolate_tiles(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned num_rand, unsigned rand_pad, unsigned log_n,
+                           u64 offset_mont, size_t ncols, u64 *d_coef, size_t coef_stride, u64 *d_tmp);
 // row i = coset + (k << log_r) of the nrows rows is read from table coset `coset * coset_mem_stride` ([col][coset][k])
 void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, unsigned ncols, int log_r, u64 *digests,
                    unsigned coset_mem_stride = 1);

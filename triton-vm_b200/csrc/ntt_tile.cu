@@ -1,0 +1,281 @@
+// Round-2 NTT kernels: square two-round tiles with register-resident radix-R DFTs (R = 8, 16, 32).
+//
+// A transform of size n = n2 * n1 (reference semantics: ntt.cu header; call sites stark.rs:872-877,
+// arithmetic_domain.rs:141-212, master_table.rs:258-322) is two passes over HBM/L2:
+//   pass A: n1/T tiles; a tile is T adjacent strided rows (fixed j1, elements j = j1 + n1 j2) -> n2-point NTT over j2,
+//           times the inter-pass twist, stored transposed (tmp[K n1 + j1]);
+//   pass B: n2/T tiles of T contiguous rows of tmp -> n1-point NTT over j1, stored to natural order (k = K + n2 K_B).
+// A tile row of M = R*R points is transformed in TWO rounds: thread (t, a) holds the R points j = a + R b in registers,
+// does an R-point DFT whose twiddles are all powers of two (ntt_radix.cuh), multiplies by w_M^(a k2) and hands the
+// results over through shared memory; thread (t, k2) then does the R-point DFT over a and owns X[k2 + R k1].  Per point
+// and pass: one generic twiddle multiplication, one shared-memory round trip, no bit reversal (the register index
+// permutation is free), against 3.3 rounds, 2.6 twiddles and the bit-reversed addressing of the radix-8 tiles in ntt.cu.
+// The row index t occupies the low lane bits, so every warp-wide global access covers whole 32/64-byte runs of adjacent
+// rows and the exchange buffer ((k2 (R+1) + a) T + t) is bank-conflict free in both directions.
+//
+// Pre-/post-operations fused into the passes (each costs what its arithmetic costs, no extra pass over memory):
+//   * coset evaluation (LDE): pass A multiplies point j2 by S_c[j2] = w_{r n2}^(c j2) (a table of n2 entries per
+//     coset) and folds the randomizer chunk (c'_j += w_r^c c'_{n+j}, j < fold_count); the factor w_{rn}^(c j1) that
+//     remains of the coset shift is one more term in the twist exponent: twist = w_{rn}^(j1 (r K + c)).
+//   * interpolation: pass B multiplies by n^-1 offset^k (the coefficients are kept pre-scaled by offset^k).
+//   Both are geometric in k1 for a fixed thread: factor = base * step^k1, two table look-ups per thread and tile.
+#include <algorithm>
+#include <cstdlib>
+#include "ctx.h"
+#include "launch.h"
+#include "ntt_radix.cuh"
+
+namespace tvm {
+
+struct TileJob {
+  const u64 *in;
+  u64 *out;
+  size_t in_col_stride, in_coset_stride, out_col_stride, out_coset_stride;   // per blockIdx.z (column), blockIdx.y (coset)
+  size_t in_row_stride, in_elem_stride, out_row_stride, out_elem_stride;     // element idx of row r at r*row + idx*elem
+  const u64 *tw;             // w_M^(+-e), e < M = R*R
+  // pre-operation (coset evaluation)
+  const u64 *prescale;       // [gridDim.y][M] or nullptr
+  const u64 *fold_factor;    // [gridDim.y]
+  unsigned fold_count;       // input elements at offset < fold_count receive + fold_factor * in[fold_offset + offset]
+  size_t fold_offset;
+  // post-operation: 0 none; 1 twist G^(row (mul K + c_y)), c_y = coset_first + coset_step y; 2 scalar * G^(row + mul K)
+  int post_mode;
+  PowTab G;
+  u64 exp_mask;
+  u64 mul;
+  unsigned coset_first, coset_step;
+  u64 scalar;
+};
+
+__device__ __forceinline__ u64 powtab_at(const PowTab &t, u64 e) {
+  const u64 lo = __ldg(t.lo + (e & ((1ULL << t.shift) - 1)));
+  const u64 hi = __ldg(t.hi + (e >> t.shift));
+  return fmul(lo, hi);
+}
+
+static constexpr int TILE_THREADS = 256;
+
+template <int LOGR, bool INV>
+__global__ void __launch_bounds__(TILE_THREADS, 2) ntt_tile_kernel(TileJob p) {
+  constexpr int R = 1 << LOGR, M = R * R, LOGT = 8 - LOGR, T = 1 << LOGT;
+  extern __shared__ u64 smem[];
+  u64 *tw = smem;            // [M]
+  u64 *ex = smem + M;        // [(k2 (R+1) + a) T + t]
+  const int tid = threadIdx.x, t = tid & (T - 1), a = tid >> LOGT;
+  const size_t row = (size_t)blockIdx.x * T + t;
+  const unsigned y = blockIdx.y;
+  const u64 *in = p.in + (size_t)blockIdx.z * p.in_col_stride + (size_t)y * p.in_coset_stride;
+  u64 *out = p.out + (size_t)blockIdx.z * p.out_col_stride + (size_t)y * p.out_coset_stride;
+  for (int i = tid; i < M; i += TILE_THREADS) tw[i] = __ldg(p.tw + i);
+
+  u64 v[R];
+  {
+    const size_t off0 = row * p.in_row_stride + (size_t)a * p.in_elem_stride;
+    const size_t step = (size_t)R * p.in_elem_stride;
+#pragma unroll
+    for (int b = 0; b < R; b++) v[b] = in[off0 + b * step];
+    if (p.prescale) {
+      if (off0 < p.fold_count) v[0] = fadd(v[0], fmul(__ldg(p.fold_factor + y), in[p.fold_offset + off0]));
+      const u64 *S = p.prescale + (size_t)y * M + a;
+#pragma unroll
+      for (int b = 0; b < R; b++) v[b] = fmul(v[b], __ldg(S + b * R));
+    }
+  }
+  dft_pow2<LOGR, INV>(v);
+  __syncthreads();           // tw[] complete
+#pragma unroll
+  for (int k2 = 0; k2 < R; k2++) {
+    u64 z = v[bitrev_c(k2, LOGR)];
+    if (k2) z = fmul(z, tw[a * k2]);          // a == 0: tw[0] = 1 (kept branch-free)
+    ex[(k2 * (R + 1) + a) * T + t] = z;
+  }
+  __syncthreads();
+  const int k2 = a;          // second round: this thread owns outputs K = k2 + R k1 of row t
+#pragma unroll
+  for (int i = 0; i < R; i++) v[i] = ex[(k2 * (R + 1) + i) * T + t];
+  dft_pow2<LOGR, INV>(v);
+  const size_t ooff0 = row * p.out_row_stride + (size_t)k2 * p.out_elem_stride;
+  const size_t ostep = (size_t)R * p.out_elem_stride;
+  if (p.post_mode == 0) {
+#pragma unroll
+    for (int k1 = 0; k1 < R; k1++) out[ooff0 + k1 * ostep] = v[bitrev_c(k1, LOGR)];
+  } else {
+    u64 f, st;
+    if (p.post_mode == 1) {
+      const u64 c = p.coset_first + p.coset_step * y;
+      f = powtab_at(p.G, (row * (p.mul * k2 + c)) & p.exp_mask);
+      st = powtab_at(p.G, (row * p.mul * R) & p.exp_mask);
+    } else {
+      f = fmul(p.scalar, powtab_at(p.G, row + p.mul * k2));
+      st = powtab_at(p.G, p.mul * R);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R; k1++) {
+      out[ooff0 + k1 * ostep] = fmul(v[bitrev_c(k1, LOGR)], f);
+      if (k1 + 1 < R) f = fmul(f, st);
+    }
+  }
+}
+
+// randomizer fold-in after the interpolation (master_table.rs:392-403: interpolant + zerofier * randomizer, zerofier
+// X^n - 1 on the trace domain): coef[k] -= rand[k] post^k, coef[n + k] = rand[k] post^(n + k), zero up to rand_pad.
+__global__ void lde_randomizer_kernel(u64 *coef, size_t coef_stride, size_t n, const u64 *rand, unsigned rand_count,
+                                      unsigned rand_pad, PowTab post) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= rand_pad) return;
+  u64 *c = coef + (size_t)blockIdx.y * coef_stride;
+  if (k < rand_count) {
+    const u64 r = rand[(size_t)blockIdx.y * rand_count + k];
+    c[k] = fsub(c[k], fmul(r, powtab_at(post, k)));
+    c[n + k] = fmul(r, powtab_at(post, n + k));
+  } else {
+    c[n + k] = 0;
+  }
+}
+
+__global__ void prescale_table_kernel(u64 *S, u64 *ff, PowTab pre, unsigned log_n, unsigned log_n1, unsigned M, unsigned coset_first,
+                                      unsigned coset_step, u64 exp_mask) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const u64 c = coset_first + coset_step * y;
+  if (i < M) S[(size_t)y * M + i] = powtab_at(pre, ((c << log_n1) * i) & exp_mask);
+  if (i == 0) ff[y] = powtab_at(pre, (c << log_n) & exp_mask);
+}
+
+u64 *Ctx::get_prescale(unsigned log_n, unsigned log_r, unsigned log_n1, unsigned M, unsigned first, unsigned step, unsigned count,
+                        const std::function<void(u64 *, u64 *)> &fill) {
+  auto key = std::make_tuple(log_n, log_r, log_n1, M, first, step, count);
+  auto it = prescale_tabs.find(key);
+  if (it != prescale_tabs.end()) return it->second;
+  u64 *d = (u64 *)alloc(((size_t)count * M + count) * sizeof(u64));
+  fill(d, d + (size_t)count * M);
+  prescale_tabs[key] = d;
+  return d;
+}
+
+static int tile_logr(int log_m) { return (log_m == 6 || log_m == 8 || log_m == 10) ? log_m / 2 : 0; }
+
+template <bool INV>
+static void launch_tile(int logr, dim3 grid, cudaStream_t s, const TileJob &j) {
+  const int R = 1 << logr, M = R * R, T = TILE_THREADS / R;
+  const size_t smem = ((size_t)M + (size_t)R * (R + 1) * T) * sizeof(u64);
+  auto go = [&](auto kernel) {
+    TVM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, TILE_THREADS, smem, s>>>(j);
+  };
+  if (logr == 5) go(ntt_tile_kernel<5, INV>);
+  else if (logr == 4) go(ntt_tile_kernel<4, INV>);
+  else go(ntt_tile_kernel<3, INV>);
+  TVM_CUDA(cudaGetLastError());
+}
+
+// Picks n = n2 * n1 with both factors in {2^6, 2^8, 2^10}; false if this size is left to ntt.cu's kernels.
+bool ntt_tile_supported(int log_n, int *log_n2, int *log_n1) {
+  static const bool off = getenv("TVM_NTT_RADIX8_TILES") != nullptr;   // A/B: the round-1 kernels
+  if (off) return false;
+  for (int la = 10; la >= 6; la -= 2) {
+    const int lb = log_n - la;
+    if (lb > la) return false;
+    if (lb == 6 || lb == 8 || lb == 10) { *log_n2 = la; *log_n1 = lb; return true; }
+  }
+  return false;
+}
+
+// Coset evaluation of pre-scaled coefficient columns (lde_evaluate_run's contract).
+bool lde_evaluate_tiles(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_count, unsigned log_n, unsigned log_r,
+                        unsigned coset_first, unsigned coset_step, unsigned num_cosets, size_t ncols, u64 *d_out, u64 *d_tmp) {
+  int la, lb;
+  if (!ntt_tile_supported((int)log_n, &la, &lb)) return false;
+  const size_t n = (size_t)1 << log_n, n2 = (size_t)1 << la, n1 = (size_t)1 << lb;
+  const int ra = tile_logr(la), rb = tile_logr(lb);
+  if (fold_count > (n1 << ra) || fold_count > n) return false;
+  const unsigned TA = TILE_THREADS >> ra, TB = TILE_THREADS >> rb;
+  if (n1 % TA || n2 % TB) return false;
+  const u64 wrn = root_of_unity_mont(log_n + log_r);
+  PowTab pre = c.get_pow_tab(wrn, (int)(log_n + log_r));
+  const u64 mask = ((u64)1 << (log_n + log_r)) - 1;
+  // prescale table + fold factors of this coset set (cached per job shape)
+  u64 *S = c.get_prescale(log_n, log_r, (unsigned)lb, (unsigned)n2, coset_first, coset_step, num_cosets, [&](u64 *dS, u64 *dff) {
+    prescale_table_kernel<<<dim3((unsigned)((n2 + 255) / 256), num_cosets), 256, 0, c.stream>>>(dS, dff, pre, log_n, (unsigned)lb,
+                                                                                                  (unsigned)n2, coset_first, coset_step, mask);
+    c.launches++;
+    TVM_CUDA(cudaGetLastError());
+  });
+  u64 *ff = S + (size_t)num_cosets * n2;
+  TileJob a{};
+  a.in = d_coef; a.out = d_tmp;
+  a.in_col_stride = coef_stride; a.in_coset_stride = 0;
+  a.out_col_stride = (size_t)num_cosets * n; a.out_coset_stride = n;
+  a.in_row_stride = 1; a.in_elem_stride = n1;
+  a.out_row_stride = 1; a.out_elem_stride = n1;
+  a.tw = c.get_tile_tw(la, false);
+  a.prescale = S; a.fold_factor = ff; a.fold_count = fold_count; a.fold_offset = n;
+  a.post_mode = 1; a.G = pre; a.exp_mask = mask; a.mul = (u64)1 << log_r;
+  a.coset_first = coset_first; a.coset_step = coset_step;
+  TileJob b{};
+  b.in = d_tmp; b.out = d_out;
+  b.in_col_stride = (size_t)num_cosets * n; b.in_coset_stride = n;
+  b.out_col_stride = (size_t)num_cosets * n; b.out_coset_stride = n;
+  b.in_row_stride = n1; b.in_elem_stride = 1;
+  b.out_row_stride = 1; b.out_elem_stride = n2;
+  b.tw = c.get_tile_tw(lb, false);
+  b.post_mode = 0;
+  // one column per launch pair: the transposed intermediate (num_cosets * n words) of pass A is consumed by pass B
+  // while it is still resident in the 126 MB L2 (64 MB at n = 2^20, 8 cosets)
+  size_t group = std::max<size_t>(1, ((size_t)8 << 20) / ((size_t)num_cosets * n));
+  for (size_t c0 = 0; c0 < ncols; c0 += group) {
+    const size_t g = std::min(group, ncols - c0);
+    TileJob aa = a, bb = b;
+    aa.in += c0 * coef_stride;
+    bb.out += c0 * (size_t)num_cosets * n;
+    launch_tile<false>(ra, dim3((unsigned)(n1 / TA), num_cosets, (unsigned)g), c.stream, aa);
+    launch_tile<false>(rb, dim3((unsigned)(n2 / TB), num_cosets, (unsigned)g), c.stream, bb);
+    c.launches += 2;
+  }
+  return true;
+}
+
+// Interpolation of trace columns to pre-scaled coefficients (lde_interpolate_run's contract).
+bool lde_interpolate_tiles(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned num_rand, unsigned rand_pad, unsigned log_n,
+                           u64 offset_mont, size_t ncols, u64 *d_coef, size_t coef_stride, u64 *d_tmp) {
+  int la, lb;
+  if (!ntt_tile_supported((int)log_n, &la, &lb)) return false;
+  const size_t n = (size_t)1 << log_n, n2 = (size_t)1 << la, n1 = (size_t)1 << lb;
+  const int ra = tile_logr(la), rb = tile_logr(lb);
+  const unsigned TA = TILE_THREADS >> ra, TB = TILE_THREADS >> rb;
+  if (n1 % TA || n2 % TB) return false;
+  const u64 wn_inv = finv(root_of_unity_mont(log_n));
+  TileJob a{};
+  a.in = d_trace; a.out = d_tmp;
+  a.in_col_stride = n; a.out_col_stride = n;
+  a.in_row_stride = 1; a.in_elem_stride = n1;
+  a.out_row_stride = 1; a.out_elem_stride = n1;
+  a.tw = c.get_tile_tw(la, true);
+  a.post_mode = 1; a.G = c.get_pow_tab(wn_inv, (int)log_n); a.exp_mask = n - 1; a.mul = 1;
+  TileJob b{};
+  b.in = d_tmp; b.out = d_coef;
+  b.in_col_stride = n; b.out_col_stride = coef_stride;
+  b.in_row_stride = n1; b.in_elem_stride = 1;
+  b.out_row_stride = 1; b.out_elem_stride = n2;
+  b.tw = c.get_tile_tw(lb, true);
+  b.post_mode = 2; b.G = c.get_pow_tab(offset_mont, (int)log_n + 1); b.mul = n2;
+  b.scalar = finv(to_mont((u64)n));
+  size_t group = std::max<size_t>(1, ((size_t)8 << 20) / n);
+  for (size_t c0 = 0; c0 < ncols; c0 += group) {
+    const size_t g = std::min(group, ncols - c0);
+    TileJob aa = a, bb = b;
+    aa.in += c0 * n;
+    bb.out += c0 * coef_stride;
+    launch_tile<true>(ra, dim3((unsigned)(n1 / TA), 1, (unsigned)g), c.stream, aa);
+    launch_tile<true>(rb, dim3((unsigned)(n2 / TB), 1, (unsigned)g), c.stream, bb);
+    c.launches += 2;
+  }
+  const unsigned pad = d_rand ? std::max(rand_pad, num_rand) : 0;
+  if (pad) {
+    lde_randomizer_kernel<<<dim3((pad + 127) / 128, (unsigned)ncols), 128, 0, c.stream>>>(d_coef, coef_stride, n, d_rand, num_rand, pad, b.G);
+    c.launches++;
+    TVM_CUDA(cudaGetLastError());
+  }
+  return true;
+}
+
+}  // namespace tvm
