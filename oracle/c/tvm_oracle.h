@@ -59,6 +59,23 @@ void orc_set_num_threads(int n);   /* OpenMP team size of the parallel loops (no
 #ifdef __cplusplus
 }
 #endif
+/* xpoly.c: array stages of a complete prove (X-field arrays interleaved [k][3], Montgomery form) */
+void orc_xpoly_eval(const u64 *c, size_t len, const u64 x[3], u64 out[3]);
+void orc_bpoly_eval_x(const u64 *c, size_t len, const u64 x[3], u64 out[3]);
+void orc_xpoly_fold(const u64 *c, size_t len, size_t ff, const u64 r[3], u64 *out);
+void orc_xpoly_mul(const u64 *a, size_t la, const u64 *b, size_t lb, u64 *out);
+void orc_xpoly_div(u64 *num, size_t ln, const u64 *den, size_t ld, u64 *q);
+void orc_xzerofier(const u64 *pts, size_t k, u64 *out);
+void orc_xinterpolate(const u64 *xs, const u64 *ys, size_t k, u64 *out);
+void orc_xpoly_axpy(u64 *dst, const u64 *src, size_t len, const u64 w[3]);
+void orc_xpoly_add_scaled_arg(u64 *dst, const u64 *src, size_t len, u64 scale, u64 arg);
+void orc_interpolants_table(const u64 *trace, unsigned log2n, size_t ncols, const u64 *rand, size_t h, u64 *out);
+void orc_bary_weights(unsigned log2n, const u64 alpha[3], u64 *dods, u64 denom_inv[3]);
+void orc_ood_row(const u64 *cols, size_t ncols, unsigned log2n, int xf, const u64 *dods, const u64 denom_inv[3], const u64 *rand,
+                 size_t h, const u64 alpha[3], u64 *out);
+void orc_weighted_colsum(const u64 *main_coef, size_t nmain, const u64 *aux_coef, size_t naux, size_t len, const u64 *w, u64 *out);
+void orc_deep_combination(const u64 *cw_ma, const u64 *cw_p, const u64 *cw_r, unsigned log2N, u64 offset, const u64 *points,
+                          const u64 *values, const u64 *weights, u64 *out);
 /* auxiliary-table extension from the AIR-derived rules (aux_extend.c); Montgomery form, column-major planes */
 void orc_aux_extend(const u64 *main_t, size_t n, const u64 *ch, u64 *aux_t);
 void orc_fill_derived_main(u64 *main_t, size_t n);

@@ -400,7 +400,8 @@ def main():
     total_constraints = sum(len(air.constraints[c]) for c in CATEGORIES)
     os.makedirs(OUT_DIR, exist_ok=True)
     for f in os.listdir(OUT_DIR):
-        os.remove(os.path.join(OUT_DIR, f))
+        if f != "air_verify_gen.inc":                # written by airgen.codegen_verify
+            os.remove(os.path.join(OUT_DIR, f))
     # pack chunks into translation units, balancing the estimated cost (compile time)
     tus = [[] for _ in range(NUM_TUS)]
     load = [0.0] * NUM_TUS

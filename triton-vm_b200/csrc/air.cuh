@@ -35,6 +35,11 @@ struct AirArgs {
   u64 cons_zerofier_inv[AIR_MAX_COSETS];  // 1 / (x^n - 1), constant on a coset   (1204-1214)
 };
 
+// strides handed to the chunk bodies of a fused group kernel (generated code refers to them as a.main_stride / a.aux_stride)
+struct AirStrides {
+  size_t main_stride, aux_stride;
+};
+
 // ---- unreduced accumulation of  sum_j w_j * c_j ------------------------------------------------
 // (c * w)_0 = c0 b0 - c1 b2 - c2 b1;  (c * w)_1 = c0 b1 + c1 (b0 + b2) + c2 (b1 - b2);
 // (c * w)_2 = c0 b2 + c1 b1 + c2 (b0 + b2)           (X^3 = X - 1)
