@@ -184,6 +184,21 @@ typedef struct tvm_claim {
 int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height,
               const uint64_t *main_trace, const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user,
               const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len);
+/* ---- Stark::prove with the table stages on the device: what Prover::prove does between
+ *      MasterMainTable::new/pad and the proof (stark.rs:331-719 together with master_table.rs:975-983, 1006-1075).  The main
+ *      trace is uploaded once and stays resident: MasterMainTable::extend (the nine tables' `extend` +
+ *      fill_derived_aux_columns) runs on it as soon as the challenges are known, no callback, no host round trip of the
+ *      auxiliary table.
+ *      main_table   [379][trace_len] canonical, column-major; with fill_derived_main_columns != 0 only columns 0..148 (the
+ *                   nine tables) are read and uploaded, the 230 degree-lowering columns are computed on the device
+ *                   (DegreeLoweringTable::fill_derived_main_columns, substitutions.rs:128-161)
+ *      aux_rand     [91][h][3]  trace-randomizer coefficients of the auxiliary columns
+ *      randomizer_column [trace_len][3]  auxiliary column 90 (master_table.rs:1019-1025); NULL = zeros
+ *      other arguments and the proof: as tvm_prove (identical proof words for identical tables and randomness).
+ *      Single GPU (a context with tvm_ctx_set_comm world > 1 returns TVM_ERR_UNSUPPORTED). --- */
+int tvm_prove_tables(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height,
+                     const uint64_t *main_table, int fill_derived_main_columns, const uint64_t *main_rand, const uint64_t *aux_rand,
+                     const uint64_t *randomizer_column, const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len);
 /* ---- auxiliary table: MasterMainTable::extend (master_table.rs:1006-1075) = the nine tables' `extend`
  *      (TraceTable::extend, table.rs:29-48; e.g. processor.rs:97-137, hash.rs:304-460, ram.rs:105-255) followed by
  *      DegreeLoweringTable::fill_derived_aux_columns (substitutions.rs:163-205).  SURVEY.md 8(f).1: the stage a host

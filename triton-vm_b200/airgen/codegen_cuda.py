@@ -338,7 +338,12 @@ def emit_chunk(air, idx, cat, items):
     return kname, "\n".join(src), nops
 
 
-# ---- fused groups (default) ---------------------------------------------------------------------------------------
+# ---- fused groups (A/B variant) ---------------------------------------------------------------------------------------
+# MEASURED AND REJECTED (B200, 2^21 rows, gpurun_out/r02d_air_ab.log -> profiles/r02_air_variants.md): 167.7 ms (147 chunk
+# kernels, budget 100) vs 173.7 ms (budget 160) vs 198.5 ms (83 groups of <= 220 cost units) vs 224 ms (28 groups of
+# <= 700) at 2^23 rows.  ncu on a large group: `stalled_no_instruction` 3.4 per issue - a group's bodies total 100-300 KB
+# of SASS, every CTA streams through all of it once, so the instruction cache misses on every body, and with 174+
+# registers there are only 8 warps per SM to hide the fetches.  Kept as an A/B switch (TVM_AIR_FUSED=1); default off.
 # One kernel per GROUP of consecutive chunks of a category: the chunk bodies stay separate instruction-cache sized
 # functions (`__noinline__`, their own register allocation), the group kernel calls them one after the other on the same
 # rows with a block-wide barrier in between, so that (a) the warps of a CTA execute the same body at the same time and
@@ -347,7 +352,7 @@ def emit_chunk(air, idx, cat, items):
 # (147 -> ~16 passes over the 3 output planes), (c) columns touched by several bodies of the group are re-read by the
 # same CTA right away (L1/L2 hits) instead of by another kernel launch from HBM.  Evaluator order keeps the constraints
 # of one table together, so consecutive chunks share their columns.
-FUSED = os.environ.get("TVM_AIR_FUSED", "1") != "0"
+FUSED = os.environ.get("TVM_AIR_FUSED", "0") != "0"
 GROUP_BUDGET = float(os.environ.get("TVM_AIR_GROUP_BUDGET", "700"))
 
 

@@ -483,6 +483,24 @@ int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, ui
   TVM_API_END
 }
 
+int tvm_prove_tables(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height, const uint64_t *main_table,
+                     int fill_derived_main_columns, const uint64_t *main_rand, const uint64_t *aux_rand, const uint64_t *randomizer_column,
+                     const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len) {
+  if (!ctx || !params || !claim || !main_table || !main_rand || !aux_rand || !quot_rand || !proof_len) return TVM_ERR_INVALID_ARG;
+  if (params->ldt_choice > 2) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  ClaimView cv{claim->program_digest, claim->version, claim->input, claim->num_input, claim->output, claim->num_output};
+  std::vector<u64> proof;
+  DeviceTables dt{(const u64 *)aux_rand, (const u64 *)randomizer_column, fill_derived_main_columns != 0};
+  stark_prove(*c__, StarkParams{params->security_level, params->log2_ldt_expansion_factor, params->ldt_choice, params->soundness}, cv, padded_height,
+              (const u64 *)main_table, (const u64 *)main_rand, nullptr, nullptr, (const u64 *)quot_rand, proof, &ctx->timings, &dt);
+  size_t cap = *proof_len;
+  *proof_len = proof.size();
+  if (!proof_out || cap < proof.size()) throw ApiError{TVM_ERR_INVALID_ARG, "proof buffer too small"};
+  memcpy(proof_out, proof.data(), proof.size() * 8);
+  TVM_API_END
+}
+
 int tvm_last_prove_timings(const tvm_ctx *ctx, const char **names, float *ms) {
   if (!ctx) return 0;
   int n = 0;

@@ -17,6 +17,7 @@
 #include "launch.h"
 #include "stark.h"
 #include "transcript.h"
+#include <functional>
 #include "prove_common.h"
 
 namespace tvm {
@@ -194,7 +195,7 @@ void evaluate_cols(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_
 
 void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t padded_height, const u64 *h_main_trace,
                  const u64 *h_main_rand, AuxCallback aux_cb, void *aux_user, const u64 *h_quot_rand, std::vector<u64> &proof,
-                 ProveTimings *timings) {
+                 ProveTimings *timings, const DeviceTables *dev_tables) {
   StarkDerived d{};
   int rc = stark_derive(sp, padded_height, d);
   if (rc) throw ApiError{rc, "parameter derivation failed"};
@@ -235,10 +236,15 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     jit = need > (double)(free_b + pooled);
   }
   if (timings) timings->low_memory = jit;
-  cudaEvent_t ev[20];
-  int nev = 0;
+  struct StageEvents {           // destroyed on every exit path (an exception used to leak them)
+    cudaEvent_t ev[20];
+    int n = 0;
+    ~StageEvents() { for (int i = 0; i < n; i++) cudaEventDestroy(ev[i]); }
+  } se;
+  cudaEvent_t *ev = se.ev;
+  int &nev = se.n;
   auto mark = [&]() {
-    if (!timings) return;
+    if (!timings || nev >= 20) return;
     cudaEventCreate(&ev[nev]);
     cudaEventRecord(ev[nev], c.stream);
     nev++;
@@ -262,16 +268,29 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   // transforms them (source pointers may be host or device memory).  With W > 1 ranks each rank uploads and
   // interpolates only its block of columns; the coefficient blocks are then all-gathered and every rank evaluates
   // all columns on its own cosets.
-  auto extend_table = [&](const u64 *src_trace, const u64 *src_rand, size_t ncols, int xf, u64 *&d_coef, u64 *&d_lde) {
+  // Device-table mode (dev_tables): `upload_cols` < ncols columns are read from src_trace, `after_upload(d_in)` produces
+  // the remaining ones in place on the device ([ncols][n] Montgomery) before they are transformed; `d_ready` = the whole
+  // planar Montgomery trace already sits on the device (nothing but the randomizers is uploaded); `keep_in` receives the
+  // Montgomery trace buffer instead of it being released.
+  struct ExtendOpts {
+    size_t upload_cols = (size_t)-1;
+    std::function<void(u64 *)> after_upload;
+    u64 *d_ready = nullptr;
+    u64 **keep_in = nullptr;
+  };
+  auto extend_table = [&](const u64 *src_trace, const u64 *src_rand, size_t ncols, int xf, u64 *&d_coef, u64 *&d_lde,
+                          const ExtendOpts &opt) {
     const size_t cpr = (ncols + W - 1) / W;             // columns per rank (the last block may be short)
     const size_t own0 = std::min(ncols, rank * cpr), own1 = std::min(ncols, own0 + cpr), nown = own1 - own0;
     const size_t bcols = ncols * xf;                    // B-field columns
+    const size_t up_cols = std::min(nown, opt.upload_cols);   // (device-table mode is single-GPU: own0 == 0)
     d_coef = mem.words(cpr * W * xf * cs);
     d_lde = jit ? nullptr : mem.words(bcols * NLe);
-    u64 *d_in = mem.words(std::max<size_t>(1, nown) * xf * n + ncols * xf * h);
-    u64 *d_rand_in = d_in + std::max<size_t>(1, nown) * xf * n;
-    u64 *d_planar = xf == 3 ? mem.words(std::max<size_t>(1, nown) * 3 * n + ncols * 3 * h) : d_in;
-    u64 *d_rand = xf == 3 ? d_planar + std::max<size_t>(1, nown) * 3 * n : d_rand_in;
+    u64 *d_in = opt.d_ready ? mem.words(ncols * xf * h) : mem.words(std::max<size_t>(1, nown) * xf * n + ncols * xf * h);
+    u64 *d_rand_in = opt.d_ready ? d_in : d_in + std::max<size_t>(1, nown) * xf * n;
+    u64 *d_planar = opt.d_ready ? opt.d_ready : (xf == 3 ? mem.words(std::max<size_t>(1, nown) * 3 * n + ncols * 3 * h) : d_in);
+    u64 *d_rand_planar = opt.d_ready ? (xf == 3 ? mem.words(ncols * 3 * h) : d_rand_in) : nullptr;
+    u64 *d_rand = opt.d_ready ? d_rand_planar : (xf == 3 ? d_planar + std::max<size_t>(1, nown) * 3 * n : d_rand_in);
     {
       cudaEvent_t e = c.get_copy_event(nevt++);   // the pool may hand out blocks the compute stream still uses
       TVM_CUDA(cudaEventRecord(e, c.stream));
@@ -280,22 +299,32 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     TVM_CUDA(cudaMemcpyAsync(d_rand_in, src_rand, ncols * xf * h * 8, cudaMemcpyDefault, cs_copy));
     const size_t bstep = std::max<size_t>(1, tmp_cols / xf);   // columns per batch
     const size_t evt0 = nevt;
-    for (size_t c0 = 0; c0 < nown; c0 += bstep) {
-      size_t b = std::min(bstep, nown - c0);
-      TVM_CUDA(cudaMemcpyAsync(d_in + c0 * xf * n, src_trace + (own0 + c0) * xf * n, b * xf * n * 8, cudaMemcpyDefault, cs_copy));
-      TVM_CUDA(cudaEventRecord(c.get_copy_event(nevt++), cs_copy));
-    }
-    if (nown == 0) TVM_CUDA(cudaEventRecord(c.get_copy_event(nevt++), cs_copy));
-    for (size_t c0 = 0, bi = 0; c0 < std::max<size_t>(1, nown); c0 += bstep, bi++) {
-      TVM_CUDA(cudaStreamWaitEvent(c.stream, c.get_copy_event(evt0 + bi), 0));
-      if (c0 == 0) {
+    // batches: [0, up_cols) uploaded, [up_cols, nown) produced on the device (a batch never straddles the boundary)
+    std::vector<std::pair<size_t, size_t>> batches;
+    for (size_t c0 = 0; c0 < up_cols; c0 += bstep) batches.push_back({c0, std::min(bstep, up_cols - c0)});
+    const size_t nup = batches.size();
+    for (size_t c0 = up_cols; c0 < nown; c0 += bstep) batches.push_back({c0, std::min(bstep, nown - c0)});
+    if (!opt.d_ready)
+      for (size_t bi = 0; bi < nup; bi++) {
+        const size_t c0 = batches[bi].first, b = batches[bi].second;
+        TVM_CUDA(cudaMemcpyAsync(d_in + c0 * xf * n, src_trace + (own0 + c0) * xf * n, b * xf * n * 8, cudaMemcpyDefault, cs_copy));
+        TVM_CUDA(cudaEventRecord(c.get_copy_event(nevt++), cs_copy));
+      }
+    if (opt.d_ready || nup == 0) TVM_CUDA(cudaEventRecord(c.get_copy_event(nevt++), cs_copy));   // "randomizers landed"
+    for (size_t bi = 0; bi < std::max<size_t>(1, batches.size()); bi++) {
+      const bool uploaded = !opt.d_ready && bi < nup;
+      if (uploaded || bi == 0) TVM_CUDA(cudaStreamWaitEvent(c.stream, c.get_copy_event(evt0 + (uploaded ? bi : 0)), 0));
+      if (bi == 0) {
         to_mont_run(c, d_rand_in, ncols * xf * h);
         if (xf == 3) deinterleave3_run(c, d_rand_in, d_rand, h, ncols);
       }
-      if (nown == 0) break;
-      size_t b = std::min(bstep, nown - c0);
-      to_mont_run(c, d_in + c0 * xf * n, b * xf * n);
-      if (xf == 3) deinterleave3_run(c, d_in + c0 * 3 * n, d_planar + c0 * 3 * n, n, b);
+      if (batches.empty()) break;
+      if (bi == nup && !opt.d_ready && opt.after_upload) opt.after_upload(d_in);
+      const size_t c0 = batches[bi].first, b = batches[bi].second;
+      if (uploaded) {
+        to_mont_run(c, d_in + c0 * xf * n, b * xf * n);
+        if (xf == 3) deinterleave3_run(c, d_in + c0 * 3 * n, d_planar + c0 * 3 * n, n, b);
+      }
       const size_t q0 = (own0 + c0) * xf;               // first B-field column of the batch
       lde_interpolate_run(c, d_planar + c0 * xf * n, d_rand + q0 * h, (unsigned)h, (unsigned)hpad, log_n, off, b * xf,
                           d_coef + q0 * cs, cs, d_tmp);
@@ -306,8 +335,14 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
       c.all_gather(d_coef, cpr * xf * cs * 8);
       if (!jit) evaluate_cols(c, d_coef, cs, (unsigned)h, bcols, log_n, log_re, she, d_lde, d_tmp, tmp_cols);
     }
-    if (xf == 3) mem.release(d_planar);
-    mem.release(d_in);
+    if (opt.d_ready) {
+      if (xf == 3) mem.release(d_rand_planar);
+      mem.release(d_in);
+    } else {
+      if (xf == 3) mem.release(d_planar);
+      if (opt.keep_in) *opt.keep_in = d_in;
+      else mem.release(d_in);
+    }
   };
   // Row digests of this rank's rows -> leaves of the full tree (all-gathered across ranks), then the tree.
   // one local evaluation-domain coset y of a table, evaluated from its coefficients (low-memory mode): [ncols][n]
@@ -348,8 +383,20 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     ps.enqueue(ItemKind::MerkleRoot, root);
   };
 
+  if (dev_tables && W > 1) throw ApiError{TVM_ERR_UNSUPPORTED, "device-side table stages are single-GPU"};
   u64 *d_main_coef = nullptr, *d_main_lde = nullptr;
-  extend_table(h_main_trace, h_main_rand, NM, 1, d_main_coef, d_main_lde);
+  u64 *d_main_trace = nullptr;          // device-table mode: the Montgomery main trace stays resident for the extension
+  {
+    ExtendOpts o;
+    if (dev_tables) {
+      o.keep_in = &d_main_trace;
+      if (dev_tables->fill_derived_main) {
+        o.upload_cols = TVM_NUM_MAIN_TABLE_COLUMNS;
+        o.after_upload = [&](u64 *d_in) { main_derived_run(c, d_in, n); };
+      }
+    }
+    extend_table(h_main_trace, h_main_rand, NM, 1, d_main_coef, d_main_lde, o);
+  }
   mark();  // 1: main LDE
   u64 *d_main_nodes = mem.words(2 * N * 5);
   commit_rows(d_main_lde, d_main_coef, (unsigned)NM, d_main_nodes);
@@ -373,14 +420,39 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   }
 
   // ---- auxiliary table (stark.rs:380-392) ---------------------------------------------------------------
-  if (!aux_cb) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback missing"};
-  u64 *h_aux_trace = nullptr, *h_aux_rand = nullptr;   // the callee hands back pointers to its own buffers
-  TVM_CUDA(cudaStreamSynchronize(c.stream));
-  if (int crc = aux_cb(aux_user, ch_canon.data(), &h_aux_trace, &h_aux_rand)) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback failed: " + std::to_string(crc)};
-  if (!h_aux_trace || !h_aux_rand) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback returned a null buffer"};
-  mark();  // extend (caller)
   u64 *d_aux_coef = nullptr, *d_aux_lde = nullptr;
-  extend_table(h_aux_trace, h_aux_rand, NA, 3, d_aux_coef, d_aux_lde);
+  if (dev_tables) {
+    // MasterMainTable::extend on the resident main trace (aux_extend.cu); the planes feed the interpolation directly
+    u64 *d_aux_planes = mem.words(NA3 * n);
+    u64 *d_misc = mem.words(3 * TVM_NUM_CHALLENGES + 3 * n + aux_extend_scratch_words(n));
+    u64 *d_ch = d_misc, *d_rc = d_misc + 3 * TVM_NUM_CHALLENGES, *d_scratch = d_rc + 3 * n;
+    TVM_CUDA(cudaMemcpyAsync(d_ch, ch_mont.data(), 3 * TVM_NUM_CHALLENGES * 8, cudaMemcpyHostToDevice, c.stream));
+    u64 *d_rplanes = d_aux_planes + 3 * (NA - 1) * n;
+    if (dev_tables->randomizer_column) {
+      TVM_CUDA(cudaMemcpyAsync(d_rc, dev_tables->randomizer_column, 3 * n * 8, cudaMemcpyDefault, c.stream));
+      to_mont_run(c, d_rc, 3 * n);
+      deinterleave3_run(c, d_rc, d_rplanes, n, 1);
+    } else {
+      TVM_CUDA(cudaMemsetAsync(d_rplanes, 0, 3 * n * 8, c.stream));
+    }
+    aux_extend_run(c, d_main_trace, n, d_ch, d_aux_planes, d_scratch);
+    TVM_CUDA(cudaStreamSynchronize(c.stream));          // ch_mont is host memory of this frame
+    mem.release(d_misc);
+    mem.release(d_main_trace);
+    mark();  // extend (device)
+    ExtendOpts o;
+    o.d_ready = d_aux_planes;
+    extend_table(nullptr, dev_tables->aux_rand, NA, 3, d_aux_coef, d_aux_lde, o);
+    mem.release(d_aux_planes);
+  } else {
+    if (!aux_cb) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback missing"};
+    u64 *h_aux_trace = nullptr, *h_aux_rand = nullptr;   // the callee hands back pointers to its own buffers
+    TVM_CUDA(cudaStreamSynchronize(c.stream));
+    if (int crc = aux_cb(aux_user, ch_canon.data(), &h_aux_trace, &h_aux_rand)) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback failed: " + std::to_string(crc)};
+    if (!h_aux_trace || !h_aux_rand) throw ApiError{TVM_ERR_INVALID_ARG, "aux callback returned a null buffer"};
+    mark();  // extend (caller)
+    extend_table(h_aux_trace, h_aux_rand, NA, 3, d_aux_coef, d_aux_lde, ExtendOpts{});
+  }
   mark();  // 4: aux LDE
   u64 *d_aux_nodes = mem.words(2 * N * 5);
   commit_rows(d_aux_lde, d_aux_coef, (unsigned)NA3, d_aux_nodes);
@@ -716,16 +788,16 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   proof = ps.encode();
   if (timings) {
     TVM_CUDA(cudaStreamSynchronize(c.stream));
-    static const char *names[] = {"setup", "upload+LDE(main)", "Merkle(main)", "extend(caller)", "upload+LDE(aux)", "Merkle(aux)",
-                                  "quotient(AIR)", "quotient LDE", "Merkle(quot)", "OOD rows", "linear combination+DEEP", "low-degree test",
-                                  "open"};
+    const char *names[] = {"setup", dev_tables && dev_tables->fill_derived_main ? "upload+derived columns+LDE(main)" : "upload+LDE(main)",
+                           "Merkle(main)", dev_tables ? "extend(device)" : "extend(caller)", dev_tables ? "LDE(aux)" : "upload+LDE(aux)",
+                           "Merkle(aux)", "quotient(AIR)", "quotient LDE", "Merkle(quot)", "OOD rows", "linear combination+DEEP",
+                           "low-degree test", "open"};
     timings->stages.clear();
     for (int i = 1; i < nev; i++) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
       timings->stages.push_back({names[i - 1], ms});
     }
-    for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
   }
 }
 

@@ -51,9 +51,18 @@ struct ProveTimings {
   bool low_memory = false;                             // the last prove() ran in low-memory (just-in-time LDE) mode
 };
 
+// Table stages on the device (tvm_prove_tables): MasterMainTable::extend (master_table.rs:1006-1075) runs inside the prove
+// on the resident main trace instead of in a host callback; optionally the 230 degree-lowering main columns
+// (fill_derived_main_columns, substitutions.rs:128-161) are computed on the device too and never uploaded.
+struct DeviceTables {
+  const u64 *aux_rand;            // [91][h][3] canonical (host or device)
+  const u64 *randomizer_column;   // [n][3] canonical: aux column 90 (master_table.rs:1019-1025); nullptr = zeros
+  bool fill_derived_main;         // columns 149..378 of the main trace are computed, not read
+};
+
 void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t padded_height, const u64 *h_main_trace,
                  const u64 *h_main_rand, AuxCallback aux_cb, void *aux_user, const u64 *h_quot_rand, std::vector<u64> &proof,
-                 ProveTimings *timings);
+                 ProveTimings *timings, const DeviceTables *dev_tables = nullptr);
 
 // ---- stark_kernels.cu ----
 struct SegmentArgs {
