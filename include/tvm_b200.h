@@ -199,6 +199,22 @@ int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, ui
 int tvm_prove_tables(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height,
                      const uint64_t *main_table, int fill_derived_main_columns, const uint64_t *main_rand, const uint64_t *aux_rand,
                      const uint64_t *randomizer_column, const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len);
+/* ---- STIR as a stand-alone low-degree test: Stir::prove / Stir::verify (low_degree_test/stir.rs:885-993, 995-1108) of the sealed
+ *      `LowDegreeTest` trait (mod.rs:48-100) for ARBITRARY StirParameters (stir.rs:395-435; folding factor 2^2 as Stark::ldt fixes
+ *      it, stark.rs:2023).  Used by the restated property tests of the reference (stir.rs:1813-2010) and by hosts that keep
+ *      Prover::prove's orchestration.  The initial domain has 2^(log2_high_degree_bound + log2_initial_expansion_factor) points and
+ *      offset BFieldElement::generator() (stir.rs:589).
+ *      codeword   [len][3] canonical X-field evaluations on that domain (host or device memory)
+ *      proof_out  the encoded proof stream of the STIR items alone (Proof.0 layout; same capacity protocol as tvm_prove)
+ *      indices_out (optional) receives the revealed first-round indices; *num_indices in: capacity, out: count. --- */
+int tvm_stir_prove(tvm_ctx *ctx, uint32_t security_level, uint32_t soundness, uint32_t log2_initial_expansion_factor,
+                   uint32_t log2_high_degree_bound, const uint64_t *codeword, uint64_t *proof_out, size_t *proof_len,
+                   uint32_t *indices_out, size_t *num_indices);
+/* host code, no GPU; TVM_OK = accepted, TVM_ERR_VERIFICATION = rejected (`failure` names the LdtVerificationError variant);
+ * on acceptance the verifier's postscript: first-round indices and the partial first codeword [count][3] (optional outputs) */
+int tvm_stir_verify(uint32_t security_level, uint32_t soundness, uint32_t log2_initial_expansion_factor, uint32_t log2_high_degree_bound,
+                    const uint64_t *proof, size_t proof_len, uint32_t *indices_out, uint64_t *values_out, size_t *num_indices,
+                    char *failure, size_t failure_capacity);
 /* ---- auxiliary table: MasterMainTable::extend (master_table.rs:1006-1075) = the nine tables' `extend`
  *      (TraceTable::extend, table.rs:29-48; e.g. processor.rs:97-137, hash.rs:304-460, ram.rs:105-255) followed by
  *      DegreeLoweringTable::fill_derived_aux_columns (substitutions.rs:163-205).  SURVEY.md 8(f).1: the stage a host

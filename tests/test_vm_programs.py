@@ -277,6 +277,14 @@ def test_gpu_proves_benchmark_workloads_from_the_149_table_columns(backend, work
                         lambda ch: (backend.aux_extend(main, ch, rcol), arand), inst["quot_rand"], security_level=160,
                         log2_expansion=2, padded_height=inst["padded_height"], ldt_choice=choice)
     assert tvm_b200.proof_padded_height(got) == 1 << log2_padded_height
+    # the same instance through tvm_prove_tables: derived columns and MasterMainTable::extend INSIDE the prove, on the resident
+    # main trace (no callback, columns 149.. never uploaded) - identical proof words
+    blank = want_main.copy()
+    blank[149:] = 0
+    got_tables = backend.prove_tables((claim.program_digest, claim.input, claim.output), blank, inst["main_rand"], arand, rcol,
+                                      inst["quot_rand"], security_level=160, log2_expansion=2, padded_height=inst["padded_height"],
+                                      ldt_choice=choice)
+    assert np.array_equal(got_tables, got)
     # where the oracle's proof of this very instance has been computed once (tests/golden/make_spin_golden.py, minutes of CPU
     # time at 2^16), the GPU's proof must hash to the same digest: word-for-word parity at a BASELINE configuration
     import json, os

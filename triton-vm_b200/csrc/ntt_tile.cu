@@ -55,7 +55,9 @@ __device__ __forceinline__ u64 powtab_at(const PowTab &t, u64 e) {
 
 static constexpr int TILE_THREADS = 256;
 
-template <int LOGR, bool INV>
+// PRE: coset pre-scale + randomizer fold on the way in; POST: 0 none, 1 twist, 2 scalar * power on the way out (compile-time:
+// the unused variants would otherwise double the unrolled code, ~100 KB of SASS, past the instruction cache)
+template <int LOGR, bool INV, bool PRE, int POST, bool LOOPED>
 __global__ void __launch_bounds__(TILE_THREADS, 2) ntt_tile_kernel(TileJob p) {
   constexpr int R = 1 << LOGR, M = R * R, LOGT = 8 - LOGR, T = 1 << LOGT;
   extern __shared__ u64 smem[];
@@ -68,51 +70,61 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) ntt_tile_kernel(TileJob p) {
   u64 *out = p.out + (size_t)blockIdx.z * p.out_col_stride + (size_t)y * p.out_coset_stride;
   for (int i = tid; i < M; i += TILE_THREADS) tw[i] = __ldg(p.tw + i);
 
+  // LOOPED: both rounds run through ONE copy of the unrolled R-point DFT (`unroll 1`), which keeps the kernel within the
+  // instruction cache (ncu on the fully unrolled version: 97 KB of SASS for pass A, `stalled_no_instruction` 0.75 per
+  // issued instruction) at the price of ~50 spilled words per thread; !LOOPED: two specialised copies, no spills.
   u64 v[R];
-  {
-    const size_t off0 = row * p.in_row_stride + (size_t)a * p.in_elem_stride;
-    const size_t step = (size_t)R * p.in_elem_stride;
+#pragma unroll(LOOPED ? 1 : 2)
+  for (int rnd = 0; rnd < 2; rnd++) {
+    if (rnd == 0) {
+      const size_t off0 = row * p.in_row_stride + (size_t)a * p.in_elem_stride;
+      const size_t step = (size_t)R * p.in_elem_stride;
 #pragma unroll
-    for (int b = 0; b < R; b++) v[b] = in[off0 + b * step];
-    if (p.prescale) {
-      if (off0 < p.fold_count) v[0] = fadd(v[0], fmul(__ldg(p.fold_factor + y), in[p.fold_offset + off0]));
-      const u64 *S = p.prescale + (size_t)y * M + a;
+      for (int b = 0; b < R; b++) v[b] = in[off0 + b * step];
+      if (PRE) {
+        if (off0 < p.fold_count) v[0] = fadd(v[0], fmul(__ldg(p.fold_factor + y), in[p.fold_offset + off0]));
+        const u64 *S = p.prescale + (size_t)y * M + a;
 #pragma unroll
-      for (int b = 0; b < R; b++) v[b] = fmul(v[b], __ldg(S + b * R));
-    }
-  }
-  dft_pow2<LOGR, INV>(v);
-  __syncthreads();           // tw[] complete
-#pragma unroll
-  for (int k2 = 0; k2 < R; k2++) {
-    u64 z = v[bitrev_c(k2, LOGR)];
-    if (k2) z = fmul(z, tw[a * k2]);          // a == 0: tw[0] = 1 (kept branch-free)
-    ex[(k2 * (R + 1) + a) * T + t] = z;
-  }
-  __syncthreads();
-  const int k2 = a;          // second round: this thread owns outputs K = k2 + R k1 of row t
-#pragma unroll
-  for (int i = 0; i < R; i++) v[i] = ex[(k2 * (R + 1) + i) * T + t];
-  dft_pow2<LOGR, INV>(v);
-  const size_t ooff0 = row * p.out_row_stride + (size_t)k2 * p.out_elem_stride;
-  const size_t ostep = (size_t)R * p.out_elem_stride;
-  if (p.post_mode == 0) {
-#pragma unroll
-    for (int k1 = 0; k1 < R; k1++) out[ooff0 + k1 * ostep] = v[bitrev_c(k1, LOGR)];
-  } else {
-    u64 f, st;
-    if (p.post_mode == 1) {
-      const u64 c = p.coset_first + p.coset_step * y;
-      f = powtab_at(p.G, (row * (p.mul * k2 + c)) & p.exp_mask);
-      st = powtab_at(p.G, (row * p.mul * R) & p.exp_mask);
+        for (int b = 0; b < R; b++) v[b] = fmul(v[b], __ldg(S + b * R));
+      }
     } else {
-      f = fmul(p.scalar, powtab_at(p.G, row + p.mul * k2));
-      st = powtab_at(p.G, p.mul * R);
-    }
+      // second round: this thread owns outputs K = k2 + R k1 of row t, k2 = a
 #pragma unroll
-    for (int k1 = 0; k1 < R; k1++) {
-      out[ooff0 + k1 * ostep] = fmul(v[bitrev_c(k1, LOGR)], f);
-      if (k1 + 1 < R) f = fmul(f, st);
+      for (int i = 0; i < R; i++) v[i] = ex[(a * (R + 1) + i) * T + t];
+    }
+    dft_pow2<LOGR, INV>(v);
+    if (rnd == 0) {
+      __syncthreads();           // tw[] complete
+#pragma unroll
+      for (int k2 = 0; k2 < R; k2++) {
+        u64 z = v[bitrev_c(k2, LOGR)];
+        if (k2) z = fmul(z, tw[a * k2]);          // a == 0: tw[0] = 1 (kept branch-free)
+        ex[(k2 * (R + 1) + a) * T + t] = z;
+      }
+      __syncthreads();
+    } else {
+      const int k2 = a;
+      const size_t ooff0 = row * p.out_row_stride + (size_t)k2 * p.out_elem_stride;
+      const size_t ostep = (size_t)R * p.out_elem_stride;
+      if (POST == 0) {
+#pragma unroll
+        for (int k1 = 0; k1 < R; k1++) out[ooff0 + k1 * ostep] = v[bitrev_c(k1, LOGR)];
+      } else {
+        u64 f, st;
+        if (POST == 1) {
+          const u64 c = p.coset_first + p.coset_step * y;
+          f = powtab_at(p.G, (row * (p.mul * k2 + c)) & p.exp_mask);
+          st = powtab_at(p.G, (row * p.mul * R) & p.exp_mask);
+        } else {
+          f = fmul(p.scalar, powtab_at(p.G, row + p.mul * k2));
+          st = powtab_at(p.G, p.mul * R);
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < R; k1++) {
+          out[ooff0 + k1 * ostep] = fmul(v[bitrev_c(k1, LOGR)], f);
+          if (k1 + 1 < R) f = fmul(f, st);
+        }
+      }
     }
   }
 }
@@ -154,7 +166,7 @@ u64 *Ctx::get_prescale(unsigned log_n, unsigned log_r, unsigned log_n1, unsigned
 
 static int tile_logr(int log_m) { return (log_m == 6 || log_m == 8 || log_m == 10) ? log_m / 2 : 0; }
 
-template <bool INV>
+template <bool INV, bool PRE, int POST>
 static void launch_tile(int logr, dim3 grid, cudaStream_t s, const TileJob &j) {
   const int R = 1 << logr, M = R * R, T = TILE_THREADS / R;
   const size_t smem = ((size_t)M + (size_t)R * (R + 1) * T) * sizeof(u64);
@@ -162,9 +174,11 @@ static void launch_tile(int logr, dim3 grid, cudaStream_t s, const TileJob &j) {
     TVM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<grid, TILE_THREADS, smem, s>>>(j);
   };
-  if (logr == 5) go(ntt_tile_kernel<5, INV>);
-  else if (logr == 4) go(ntt_tile_kernel<4, INV>);
-  else go(ntt_tile_kernel<3, INV>);
+  static const bool looped = getenv("TVM_NTT_LOOPED_ROUNDS") != nullptr;   // A/B switch
+  if (logr == 5 && looped) go(ntt_tile_kernel<5, INV, PRE, POST, true>);
+  else if (logr == 5) go(ntt_tile_kernel<5, INV, PRE, POST, false>);
+  else if (logr == 4) go(ntt_tile_kernel<4, INV, PRE, POST, false>);
+  else go(ntt_tile_kernel<3, INV, PRE, POST, false>);
   TVM_CUDA(cudaGetLastError());
 }
 
@@ -227,8 +241,8 @@ bool lde_evaluate_tiles(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned 
     TileJob aa = a, bb = b;
     aa.in += c0 * coef_stride;
     bb.out += c0 * (size_t)num_cosets * n;
-    launch_tile<false>(ra, dim3((unsigned)(n1 / TA), num_cosets, (unsigned)g), c.stream, aa);
-    launch_tile<false>(rb, dim3((unsigned)(n2 / TB), num_cosets, (unsigned)g), c.stream, bb);
+    launch_tile<false, true, 1>(ra, dim3((unsigned)(n1 / TA), num_cosets, (unsigned)g), c.stream, aa);
+    launch_tile<false, false, 0>(rb, dim3((unsigned)(n2 / TB), num_cosets, (unsigned)g), c.stream, bb);
     c.launches += 2;
   }
   return true;
@@ -265,8 +279,8 @@ bool lde_interpolate_tiles(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsign
     TileJob aa = a, bb = b;
     aa.in += c0 * n;
     bb.out += c0 * coef_stride;
-    launch_tile<true>(ra, dim3((unsigned)(n1 / TA), 1, (unsigned)g), c.stream, aa);
-    launch_tile<true>(rb, dim3((unsigned)(n2 / TB), 1, (unsigned)g), c.stream, bb);
+    launch_tile<true, false, 1>(ra, dim3((unsigned)(n1 / TA), 1, (unsigned)g), c.stream, aa);
+    launch_tile<true, false, 2>(rb, dim3((unsigned)(n2 / TB), 1, (unsigned)g), c.stream, bb);
     c.launches += 2;
   }
   const unsigned pad = d_rand ? std::max(rand_pad, num_rand) : 0;

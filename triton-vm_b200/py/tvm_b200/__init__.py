@@ -109,6 +109,8 @@ _SIGNATURES = {
     "tvm_derive_domains": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_uint64, ctypes.POINTER(Domains)]),
     "tvm_prove": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, _u64p, _u64p,
                                  AUX_CALLBACK, _vp, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
+    "tvm_prove_tables": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, _u64p, ctypes.c_int,
+                                        _u64p, _u64p, _u64p, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
     "tvm_fill_derived_main_columns": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint]),
     "tvm_aux_extend": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint, _u64p, _u64p, _u64p]),
     "tvm_verify": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), _u64p, ctypes.c_size_t, ctypes.c_int,
@@ -135,6 +137,18 @@ def lib():
             f.argtypes = args
         _lib = l
     return _lib
+
+
+def _proof_capacity(dom):
+    """upper bound of the proof length in words for the derived parameters `dom`"""
+    nfq = dom["num_first_round_queries"]
+    est = 64 + nfq * (379 + 273 + 15 + 3 * 40 * (dom["fri_num_rounds"] + 4)) + \
+        3 * (dom["ldt_len"] >> dom["fri_num_rounds"]) * 2 + 3 * 470 * 2 + 4096
+    if dom["ldt"] == LDT_STIR:   # per round: stacked leaves (4 XFE + framing) and authentication paths of every query
+        height = dom["ldt_len"].bit_length()
+        est += sum(q * (16 + 5 * height) + 64 for q, _ in dom["stir_round_queries"]) + \
+            dom["stir_final_num_queries"] * (16 + 5 * height) + 3 * (dom["stir_final_degree"] + 2) + 1024
+    return est
 
 
 def _u64_arg(x):
@@ -371,19 +385,47 @@ class Backend:
 
         p = Params(security_level, log2_expansion, ldt_choice, int(conjectured))
         cap = ctypes.c_size_t(0)
-        nfq = dom["num_first_round_queries"]
-        est = 64 + nfq * (379 + 273 + 15 + 3 * 40 * (dom["fri_num_rounds"] + 4)) + \
-            3 * (dom["ldt_len"] >> dom["fri_num_rounds"]) * 2 + 3 * 470 * 2 + 4096
-        if dom["ldt"] == LDT_STIR:   # per round: stacked leaves (4 XFE + framing) and authentication paths of every query
-            height = dom["ldt_len"].bit_length()
-            est += sum(q * (16 + 5 * height) + 64 for q, _ in dom["stir_round_queries"]) + \
-                dom["stir_final_num_queries"] * (16 + 5 * height) + 3 * (dom["stir_final_degree"] + 2) + 1024
+        est = _proof_capacity(dom)
         buf = np.empty(est, dtype=np.uint64)
         cap.value = est
         rc = self._l.tvm_prove(self._h, ctypes.byref(p), ctypes.byref(cs), ph, mtp, mrp, AUX_CALLBACK(cb), None, qrp,
                                buf.ctypes.data_as(_u64p), ctypes.byref(cap))
         if err:
             raise err[0]
+        self._chk(rc)
+        return buf[:cap.value].copy()
+
+    def prove_tables(self, claim, main_table, main_rand, aux_rand, randomizer_column, quot_rand, security_level=160, log2_expansion=2,
+                     padded_height=None, ldt_choice=LDT_AUTO, conjectured=False, fill_derived_main_columns=True):
+        """tvm_prove_tables: Stark::prove with the table stages on the device — the degree-lowering main columns (when
+        fill_derived_main_columns) and MasterMainTable::extend run inside the prove on the resident main trace.
+        main_table [379, n] (columns 149.. ignored when they are filled on the device), main_rand [379, h], aux_rand [91, h, 3],
+        randomizer_column [n, 3] or None, quot_rand [(h+1)*5, 3]; numpy or contiguous torch tensors (host or CUDA)."""
+        mt, mtp, mt_shape = _u64_arg(main_table)
+        mr, mrp, mr_shape = _u64_arg(main_rand)
+        ar, arp, ar_shape = _u64_arg(aux_rand)
+        qr, qrp = _np_u64(quot_rand)
+        n = mt_shape[1]
+        ph = padded_height or n
+        dom = derive_domains(security_level, log2_expansion, ph, ldt_choice, conjectured)
+        h = dom["num_trace_randomizers"]
+        assert mt_shape == (379, dom["trace_len"]) and mr_shape == (379, h) and int(np.prod(ar_shape)) == 91 * h * 3, (mt_shape, mr_shape, ar_shape)
+        assert qr.size == 3 * dom["num_quotient_randomizer_coefficients"]
+        rcp = None
+        if randomizer_column is not None:
+            rc_, rcp, rc_shape = _u64_arg(randomizer_column)
+            assert int(np.prod(rc_shape)) == 3 * n
+        digest, inp, out = claim[0], claim[1], claim[2]
+        version = claim[3] if len(claim) > 3 else 6
+        ia, iap = _np_u64(np.array(list(inp), dtype=np.uint64))
+        oa, oap = _np_u64(np.array(list(out), dtype=np.uint64))
+        cs = ClaimStruct((ctypes.c_uint64 * 5)(*[int(v) for v in digest]), version, iap, ia.size, oap, oa.size)
+        p = Params(security_level, log2_expansion, ldt_choice, int(conjectured))
+        est = _proof_capacity(dom)
+        buf = np.empty(est, dtype=np.uint64)
+        cap = ctypes.c_size_t(est)
+        rc = self._l.tvm_prove_tables(self._h, ctypes.byref(p), ctypes.byref(cs), ph, mtp, int(bool(fill_derived_main_columns)), mrp, arp,
+                                      rcp, qrp, buf.ctypes.data_as(_u64p), ctypes.byref(cap))
         self._chk(rc)
         return buf[:cap.value].copy()
 
