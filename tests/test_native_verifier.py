@@ -204,3 +204,28 @@ def test_plain_c_prover_client_builds_and_fails_loudly_without_a_gpu(tmp_path):
         assert r.returncode == 3 and "no CPU fallback" in r.stderr           # tvm_ctx_create refuses: nothing is computed on the host
     else:
         assert r.returncode == 0 and "verified" in r.stdout, r.stderr
+
+
+def test_different_ldts_and_proximity_regimes_are_mutually_incompatible():
+    """different_ldts_are_mutually_incompatible / different_proximty_regimes_are_mutually_incompatible (stark.rs:4840-4876) on the
+    program `halt`: a proof verifies under exactly the (low-degree test, proximity regime) it was made for"""
+    from oracle import fast
+    tables = halt_tables(HALT_N)
+    proofs = {}
+    for ldt in ("fri", "stir"):
+        for regime in ("proven", "conjectured"):
+            st, claim, main, mrand, aux_provider, qrand = halt_instance(tables, 8, ldt)
+            st = S.Stark(8, 2, ldt, regime)
+            d = st.derive(HALT_N)
+            rng = np.random.default_rng(5)
+            h = d["num_trace_randomizers"]
+            mrand = rng.integers(0, tvm_b200.P, size=(379, h), dtype=np.uint64)
+            arand = rng.integers(0, tvm_b200.P, size=(91, h, 3), dtype=np.uint64)
+            qrand = rng.integers(0, tvm_b200.P, size=(d["num_quotient_randomizer_coefficients"], 3), dtype=np.uint64)
+            proofs[(ldt, regime)] = (claim, fast.prove(st, claim, main, mrand, lambda ch: (aux_provider(ch)[0], arand), qrand, padded_height=HALT_N))
+    choice = {"fri": tvm_b200.LDT_FRI, "stir": tvm_b200.LDT_STIR}
+    for (ldt, regime), (claim, proof) in proofs.items():
+        for v_ldt in ("fri", "stir"):
+            for v_regime in ("proven", "conjectured"):
+                ok, why = tvm_b200.verify(_c(claim), proof, 8, 2, ldt_choice=choice[v_ldt], conjectured=v_regime == "conjectured")
+                assert ok == ((v_ldt, v_regime) == (ldt, regime)), (ldt, regime, v_ldt, v_regime, why)

@@ -85,3 +85,33 @@ def test_oracle_stir_prove_then_verify(security, hdb):
     bad[len(bad) // 3] = (bad[len(bad) // 3] + 1) % F.P
     with pytest.raises((ValueError, KeyError, IndexError)):
         stir.verify(codec.decode_proof(bad), sp)
+
+
+def test_ldt_parameter_table_of_the_reference_range():
+    """print_various_ldt_parameters (stark.rs:4901-4958): Stark::default() at padded heights 2^8..2^29, both low-degree tests,
+    both proximity regimes.  The committed table comes from the oracle (tests/golden/make_ldt_parameter_table.py); the
+    product's derivation (tvm_derive_domains) must reproduce every row."""
+    import json, os
+    table = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ldt_parameter_table.json")))
+    assert len(table) == 2 * 2 * 22
+    for key, want in table.items():
+        ldt, soundness, h = key.split("/")
+        got = tvm_b200.derive_domains(160, 2, 1 << int(h), {"fri": 1, "stir": 2}[ldt], conjectured=soundness == "conjectured")
+        assert got["ldt_len"].bit_length() - 1 == want["log2_initial_domain_len"], key
+        assert got["num_trace_randomizers"] == want["num_trace_randomizers"] and got["trace_len"] == want["trace_len"], key
+        if ldt == "fri":
+            assert got["fri_num_rounds"] == want["num_rounds"] and got["num_collinearity_checks"] == want["first_round_queries"], key
+            assert (got["fri_last_round_max_degree"] + 1).bit_length() - 1 == want["log2_final_degree_plus_1"], key
+        else:
+            rq = got["stir_round_queries"]
+            assert len(rq) == want["num_rounds"] and got["num_first_round_queries"] == want["first_round_queries"], key
+            assert sum(a + b for a, b in rq) + got["stir_final_num_queries"] == want["total_queries"], key
+            assert (got["stir_final_degree"] + 1).bit_length() - 1 == want["log2_final_degree_plus_1"], key
+
+
+def test_different_ldts_are_used_for_different_padded_heights():
+    """stark.rs:4880-4899: with no forced choice both low-degree tests occur over padded heights 2^0..2^20 (FRI below 2^16)"""
+    used = {tvm_b200.derive_domains(8, 2, 1 << h, tvm_b200.LDT_AUTO)["ldt"] for h in range(0, 21)}
+    assert used == {tvm_b200.LDT_FRI, tvm_b200.LDT_STIR}
+    assert tvm_b200.derive_domains(160, 2, 1 << 15, tvm_b200.LDT_AUTO)["ldt"] == tvm_b200.LDT_FRI
+    assert tvm_b200.derive_domains(160, 2, 1 << 16, tvm_b200.LDT_AUTO)["ldt"] == tvm_b200.LDT_STIR

@@ -2,6 +2,8 @@
 #include "../../include/tvm_b200.h"
 #include "ctx.h"
 #include "launch.h"
+#include "transcript.h"
+#include "prove_common.h"
 #include "stark.h"
 #include <cstring>
 #include <new>
@@ -123,6 +125,16 @@ void lde_run(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsigned num_rand, u
   } catch (...) { \
     return translate_exception(c__); \
   }
+
+// proof.rs:68-88: a claim's words are field elements; NULL with a non-zero count or a word >= p is an argument error (a
+// non-canonical word would otherwise alias the claim [x] with [x + p] in the transcript)
+static bool claim_ok(const tvm_claim *c) {
+  if ((c->num_input && !c->input) || (c->num_output && !c->output)) return false;
+  for (int i = 0; i < 5; i++) if (c->program_digest[i] >= tvm::P) return false;
+  for (size_t i = 0; i < c->num_input; i++) if (c->input[i] >= tvm::P) return false;
+  for (size_t i = 0; i < c->num_output; i++) if (c->output[i] >= tvm::P) return false;
+  return true;
+}
 
 extern "C" {
 
@@ -470,7 +482,7 @@ int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, ui
               const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user, const uint64_t *quot_rand, uint64_t *proof_out,
               size_t *proof_len) {
   if (!ctx || !params || !claim || !main_trace || !main_rand || !aux_cb || !quot_rand || !proof_len) return TVM_ERR_INVALID_ARG;
-  if (params->ldt_choice > 2) return TVM_ERR_INVALID_ARG;
+  if (params->ldt_choice > 2 || !claim_ok(claim)) return TVM_ERR_INVALID_ARG;
   TVM_API_BEGIN(ctx)
   ClaimView cv{claim->program_digest, claim->version, claim->input, claim->num_input, claim->output, claim->num_output};
   std::vector<u64> proof;
@@ -487,7 +499,7 @@ int tvm_prove_tables(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *cl
                      int fill_derived_main_columns, const uint64_t *main_rand, const uint64_t *aux_rand, const uint64_t *randomizer_column,
                      const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len) {
   if (!ctx || !params || !claim || !main_table || !main_rand || !aux_rand || !quot_rand || !proof_len) return TVM_ERR_INVALID_ARG;
-  if (params->ldt_choice > 2) return TVM_ERR_INVALID_ARG;
+  if (params->ldt_choice > 2 || !claim_ok(claim)) return TVM_ERR_INVALID_ARG;
   TVM_API_BEGIN(ctx)
   ClaimView cv{claim->program_digest, claim->version, claim->input, claim->num_input, claim->output, claim->num_output};
   std::vector<u64> proof;
@@ -495,6 +507,42 @@ int tvm_prove_tables(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *cl
   stark_prove(*c__, StarkParams{params->security_level, params->log2_ldt_expansion_factor, params->ldt_choice, params->soundness}, cv, padded_height,
               (const u64 *)main_table, (const u64 *)main_rand, nullptr, nullptr, (const u64 *)quot_rand, proof, &ctx->timings, &dt);
   size_t cap = *proof_len;
+  *proof_len = proof.size();
+  if (!proof_out || cap < proof.size()) throw ApiError{TVM_ERR_INVALID_ARG, "proof buffer too small"};
+  memcpy(proof_out, proof.data(), proof.size() * 8);
+  TVM_API_END
+}
+
+int tvm_stir_prove(tvm_ctx *ctx, uint32_t security_level, uint32_t soundness, uint32_t log2_initial_expansion_factor,
+                   uint32_t log2_high_degree_bound, const uint64_t *codeword, uint64_t *proof_out, size_t *proof_len,
+                   uint32_t *indices_out, size_t *num_indices) {
+  if (!ctx || !codeword || !proof_len || soundness > 1) return TVM_ERR_INVALID_ARG;
+  if (log2_high_degree_bound + log2_initial_expansion_factor > 26) return TVM_ERR_DOMAIN;
+  StirDerived sd{};
+  if (int rc = stir_derive(security_level, STIR_LOG2_FOLDING_FACTOR, log2_initial_expansion_factor, log2_high_degree_bound, soundness == 1, sd))
+    return rc;
+  TVM_API_BEGIN(ctx)
+  Ctx &c = *c__;
+  const size_t len = (size_t)1 << (log2_high_degree_bound + log2_initial_expansion_factor);
+  std::vector<u64> proof;
+  std::vector<uint32_t> revealed;
+  {
+    DevMem mem(c);
+    u64 *d_in = mem.words(3 * len), *d_cw = mem.words(3 * len), *d_tmp = mem.words(3 * len);
+    TVM_CUDA(cudaMemcpyAsync(d_in, codeword, 3 * len * 8, cudaMemcpyDefault, c.stream));
+    to_mont_run(c, d_in, 3 * len);
+    deinterleave3_run(c, d_in, d_cw, len, 1);
+    ProofStream ps;
+    revealed = stir_prove_run(c, mem, ps, d_cw, len, to_mont(7), sd, d_tmp);
+    proof = ps.encode();
+  }
+  const size_t icap = num_indices ? *num_indices : 0;
+  if (num_indices) *num_indices = revealed.size();
+  if (indices_out) {
+    if (icap < revealed.size()) throw ApiError{TVM_ERR_INVALID_ARG, "index buffer too small"};
+    memcpy(indices_out, revealed.data(), revealed.size() * sizeof(uint32_t));
+  }
+  const size_t cap = *proof_len;
   *proof_len = proof.size();
   if (!proof_out || cap < proof.size()) throw ApiError{TVM_ERR_INVALID_ARG, "proof buffer too small"};
   memcpy(proof_out, proof.data(), proof.size() * 8);

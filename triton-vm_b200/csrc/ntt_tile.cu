@@ -57,7 +57,9 @@ static constexpr int TILE_THREADS = 256;
 
 // PRE: coset pre-scale + randomizer fold on the way in; POST: 0 none, 1 twist, 2 scalar * power on the way out (compile-time:
 // the unused variants would otherwise double the unrolled code, ~100 KB of SASS, past the instruction cache)
-template <int LOGR, bool INV, bool PRE, int POST, bool LOOPED>
+// STREAM: second pass - its input is the intermediate that should live in L2 only (last use: ld.global.cs = evict first) and
+// its output is not read again by the LDE (st.global.cs), so that the NEXT column's intermediate finds room in the L2.
+template <int LOGR, bool INV, bool PRE, int POST, bool LOOPED, bool STREAM>
 __global__ void __launch_bounds__(TILE_THREADS, 2) ntt_tile_kernel(TileJob p) {
   constexpr int R = 1 << LOGR, M = R * R, LOGT = 8 - LOGR, T = 1 << LOGT;
   extern __shared__ u64 smem[];
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) ntt_tile_kernel(TileJob p) {
       const size_t off0 = row * p.in_row_stride + (size_t)a * p.in_elem_stride;
       const size_t step = (size_t)R * p.in_elem_stride;
 #pragma unroll
-      for (int b = 0; b < R; b++) v[b] = in[off0 + b * step];
+      for (int b = 0; b < R; b++) v[b] = STREAM ? __ldcs(in + off0 + b * step) : in[off0 + b * step];
       if (PRE) {
         if (off0 < p.fold_count) v[0] = fadd(v[0], fmul(__ldg(p.fold_factor + y), in[p.fold_offset + off0]));
         const u64 *S = p.prescale + (size_t)y * M + a;
@@ -108,7 +110,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) ntt_tile_kernel(TileJob p) {
       const size_t ostep = (size_t)R * p.out_elem_stride;
       if (POST == 0) {
 #pragma unroll
-        for (int k1 = 0; k1 < R; k1++) out[ooff0 + k1 * ostep] = v[bitrev_c(k1, LOGR)];
+        for (int k1 = 0; k1 < R; k1++) {
+          if (STREAM) __stcs(out + ooff0 + k1 * ostep, v[bitrev_c(k1, LOGR)]);
+          else out[ooff0 + k1 * ostep] = v[bitrev_c(k1, LOGR)];
+        }
       } else {
         u64 f, st;
         if (POST == 1) {
@@ -121,7 +126,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) ntt_tile_kernel(TileJob p) {
         }
 #pragma unroll
         for (int k1 = 0; k1 < R; k1++) {
-          out[ooff0 + k1 * ostep] = fmul(v[bitrev_c(k1, LOGR)], f);
+          const u64 o = fmul(v[bitrev_c(k1, LOGR)], f);
+          if (STREAM) __stcs(out + ooff0 + k1 * ostep, o);
+          else out[ooff0 + k1 * ostep] = o;
           if (k1 + 1 < R) f = fmul(f, st);
         }
       }
@@ -166,7 +173,7 @@ u64 *Ctx::get_prescale(unsigned log_n, unsigned log_r, unsigned log_n1, unsigned
 
 static int tile_logr(int log_m) { return (log_m == 6 || log_m == 8 || log_m == 10) ? log_m / 2 : 0; }
 
-template <bool INV, bool PRE, int POST>
+template <bool INV, bool PRE, int POST, bool STREAM>
 static void launch_tile(int logr, dim3 grid, cudaStream_t s, const TileJob &j) {
   const int R = 1 << logr, M = R * R, T = TILE_THREADS / R;
   const size_t smem = ((size_t)M + (size_t)R * (R + 1) * T) * sizeof(u64);
@@ -174,12 +181,20 @@ static void launch_tile(int logr, dim3 grid, cudaStream_t s, const TileJob &j) {
     TVM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<grid, TILE_THREADS, smem, s>>>(j);
   };
-  static const bool looped = getenv("TVM_NTT_LOOPED_ROUNDS") != nullptr;   // A/B switch
-  if (logr == 5 && looped) go(ntt_tile_kernel<5, INV, PRE, POST, true>);
-  else if (logr == 5) go(ntt_tile_kernel<5, INV, PRE, POST, false>);
-  else if (logr == 4) go(ntt_tile_kernel<4, INV, PRE, POST, false>);
-  else go(ntt_tile_kernel<3, INV, PRE, POST, false>);
+  static const bool looped = getenv("TVM_NTT_LOOPED_ROUNDS") != nullptr;   // A/B switch (measured 10 % slower at 2^20: spills)
+  if (logr == 5 && looped) go(ntt_tile_kernel<5, INV, PRE, POST, true, STREAM>);
+  else if (logr == 5) go(ntt_tile_kernel<5, INV, PRE, POST, false, STREAM>);
+  else if (logr == 4) go(ntt_tile_kernel<4, INV, PRE, POST, false, STREAM>);
+  else go(ntt_tile_kernel<3, INV, PRE, POST, false, STREAM>);
   TVM_CUDA(cudaGetLastError());
+}
+
+// bytes of transposed intermediate one launch pair may produce: it has to survive in the L2 (126 MB, shared with the
+// streaming output) between the two passes.  ncu with the caches left alone, 64 MB per pair: pass A wrote 53 MB of it back to
+// DRAM and pass B read all 67 MB from DRAM (profiles/r02f_ntt_tile_traffic.md).
+static size_t tile_tmp_budget() {
+  static const size_t mb = getenv("TVM_NTT_TMP_MB") ? (size_t)atoi(getenv("TVM_NTT_TMP_MB")) : 32;
+  return std::max<size_t>(1, mb) << 20;
 }
 
 // Picks n = n2 * n1 with both factors in {2^6, 2^8, 2^10}; false if this size is left to ntt.cu's kernels.
@@ -233,17 +248,25 @@ bool lde_evaluate_tiles(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned 
   b.out_row_stride = 1; b.out_elem_stride = n2;
   b.tw = c.get_tile_tw(lb, false);
   b.post_mode = 0;
-  // one column per launch pair: the transposed intermediate (num_cosets * n words) of pass A is consumed by pass B
-  // while it is still resident in the 126 MB L2 (64 MB at n = 2^20, 8 cosets)
-  size_t group = std::max<size_t>(1, ((size_t)8 << 20) / ((size_t)num_cosets * n));
+  // launch pairs of (columns x cosets) whose transposed intermediate fits the L2 budget: pass B consumes it from the L2
+  const size_t budget_words = tile_tmp_budget() / 8;
+  size_t cos_per = std::min<size_t>(num_cosets, std::max<size_t>(1, budget_words / n));
+  while (num_cosets % cos_per) cos_per--;
+  const size_t group = cos_per == num_cosets ? std::max<size_t>(1, budget_words / ((size_t)num_cosets * n)) : 1;
   for (size_t c0 = 0; c0 < ncols; c0 += group) {
     const size_t g = std::min(group, ncols - c0);
-    TileJob aa = a, bb = b;
-    aa.in += c0 * coef_stride;
-    bb.out += c0 * (size_t)num_cosets * n;
-    launch_tile<false, true, 1>(ra, dim3((unsigned)(n1 / TA), num_cosets, (unsigned)g), c.stream, aa);
-    launch_tile<false, false, 0>(rb, dim3((unsigned)(n2 / TB), num_cosets, (unsigned)g), c.stream, bb);
-    c.launches += 2;
+    for (size_t y0 = 0; y0 < num_cosets; y0 += cos_per) {
+      TileJob aa = a, bb = b;
+      aa.in += c0 * coef_stride;
+      aa.prescale += y0 * n2; aa.fold_factor += y0;
+      aa.coset_first = coset_first + coset_step * (unsigned)y0;
+      aa.out_col_stride = cos_per * n;                       // the intermediate of this pair only
+      bb.in_col_stride = cos_per * n;
+      bb.out += (c0 * (size_t)num_cosets + y0) * n;
+      launch_tile<false, true, 1, false>(ra, dim3((unsigned)(n1 / TA), (unsigned)cos_per, (unsigned)g), c.stream, aa);
+      launch_tile<false, false, 0, true>(rb, dim3((unsigned)(n2 / TB), (unsigned)cos_per, (unsigned)g), c.stream, bb);
+      c.launches += 2;
+    }
   }
   return true;
 }
@@ -273,14 +296,14 @@ bool lde_interpolate_tiles(Ctx &c, const u64 *d_trace, const u64 *d_rand, unsign
   b.tw = c.get_tile_tw(lb, true);
   b.post_mode = 2; b.G = c.get_pow_tab(offset_mont, (int)log_n + 1); b.mul = n2;
   b.scalar = finv(to_mont((u64)n));
-  size_t group = std::max<size_t>(1, ((size_t)8 << 20) / n);
+  size_t group = std::max<size_t>(1, tile_tmp_budget() / 8 / n);
   for (size_t c0 = 0; c0 < ncols; c0 += group) {
     const size_t g = std::min(group, ncols - c0);
     TileJob aa = a, bb = b;
     aa.in += c0 * n;
     bb.out += c0 * coef_stride;
-    launch_tile<true, false, 1>(ra, dim3((unsigned)(n1 / TA), 1, (unsigned)g), c.stream, aa);
-    launch_tile<true, false, 2>(rb, dim3((unsigned)(n2 / TB), 1, (unsigned)g), c.stream, bb);
+    launch_tile<true, false, 1, false>(ra, dim3((unsigned)(n1 / TA), 1, (unsigned)g), c.stream, aa);
+    launch_tile<true, false, 2, false>(rb, dim3((unsigned)(n2 / TB), 1, (unsigned)g), c.stream, bb);
     c.launches += 2;
   }
   const unsigned pad = d_rand ? std::max(rand_pad, num_rand) : 0;

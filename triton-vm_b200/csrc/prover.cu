@@ -1,7 +1,7 @@
 // Stark::prove on one B200: orchestration of the device kernels + host Fiat-Shamir transcript.
 //
 // Restates Prover::prove (triton-vm/src/stark.rs:331-719) step by step for the cached-LDE branch
-// with the FRI low-degree test (stark.with_ldt_choice(LdtChoice::Fri); STIR is not built yet) and
+// with the FRI low-degree test (stark.with_ldt_choice(LdtChoice::Fri); STIR: csrc/stir.cu) and
 // the parameter derivation of stark.rs:1885-2089, fri.rs:799-924, low_degree_test/mod.rs:250-300.
 // Trace generation stays with the caller: the main trace and all randomizer
 // coefficients are inputs; the auxiliary trace is requested through a callback once the

@@ -712,6 +712,52 @@ LdtResult stir_verify(Transcript &ps, const StarkDerived &d) {
 }  // namespace
 }  // namespace tvm
 
+// Stir::verify as a stand-alone low-degree test (stir.rs:995-1108) for arbitrary StirParameters
+extern "C" int tvm_stir_verify(uint32_t security_level, uint32_t soundness, uint32_t log2_initial_expansion_factor,
+                               uint32_t log2_high_degree_bound, const uint64_t *proof, size_t proof_len, uint32_t *indices_out,
+                               uint64_t *values_out, size_t *num_indices, char *failure, size_t failure_capacity) {
+  using namespace tvm;
+  if (failure && failure_capacity) failure[0] = 0;
+  if (!proof || !proof_len || soundness > 1) return TVM_ERR_INVALID_ARG;
+  auto report = [&](const char *what) {
+    if (failure && failure_capacity) {
+      std::strncpy(failure, what, failure_capacity - 1);
+      failure[failure_capacity - 1] = 0;
+    }
+  };
+  StarkDerived d{};
+  if (int rc = stir_derive(security_level, STIR_LOG2_FOLDING_FACTOR, log2_initial_expansion_factor, log2_high_degree_bound, soundness == 1,
+                           d.stir))
+    return rc;
+  d.ldt = 2;
+  d.ldt_len = (size_t)1 << (log2_high_degree_bound + log2_initial_expansion_factor);
+  d.ldt_offset = 7;                                   // BFieldElement::generator(), stir.rs:589
+  try {
+    Transcript ps(proof, proof_len);
+    LdtResult r = stir_verify(ps, d);
+    if (ps.index != ps.items.size()) fail("VerificationError: SuperfluousProofItems");
+    const size_t cap = num_indices ? *num_indices : 0;
+    if (num_indices) *num_indices = r.indices.size();
+    if (indices_out || values_out) {
+      if (cap < r.indices.size()) return TVM_ERR_INVALID_ARG;
+      for (size_t i = 0; i < r.indices.size(); i++) {
+        if (indices_out) indices_out[i] = r.indices[i];
+        if (values_out) { values_out[3 * i] = from_mont(r.values[i].c0); values_out[3 * i + 1] = from_mont(r.values[i].c1); values_out[3 * i + 2] = from_mont(r.values[i].c2); }
+      }
+    }
+    return TVM_OK;
+  } catch (const VerifyFailure &f) {
+    report(f.what);
+    return TVM_ERR_VERIFICATION;
+  } catch (const std::exception &e) {
+    report(e.what());
+    return TVM_ERR_VERIFICATION;
+  } catch (...) {
+    report("internal error");
+    return TVM_ERR_VERIFICATION;
+  }
+}
+
 // Proof::padded_height (proof.rs:37-56): the one Log2PaddedHeight item of the proof stream
 extern "C" int tvm_proof_padded_height(const uint64_t *proof, size_t proof_len, uint64_t *padded_height) {
   using namespace tvm;
@@ -736,6 +782,10 @@ extern "C" int tvm_verify(const tvm_params *params, const tvm_claim *claim, cons
   using namespace tvm;
   if (failure && failure_capacity) failure[0] = 0;
   if (!params || !claim || !proof || !proof_len || params->ldt_choice > 2) return TVM_ERR_INVALID_ARG;
+  if ((claim->num_input && !claim->input) || (claim->num_output && !claim->output)) return TVM_ERR_INVALID_ARG;
+  for (int i = 0; i < 5; i++) if (claim->program_digest[i] >= P) return TVM_ERR_INVALID_ARG;
+  for (size_t i = 0; i < claim->num_input; i++) if (claim->input[i] >= P) return TVM_ERR_INVALID_ARG;
+  for (size_t i = 0; i < claim->num_output; i++) if (claim->output[i] >= P) return TVM_ERR_INVALID_ARG;
   auto report = [&](const char *what) {
     if (failure && failure_capacity) {
       std::strncpy(failure, what, failure_capacity - 1);
@@ -772,7 +822,11 @@ extern "C" int tvm_verify_batch(const tvm_params *params, const tvm_claim *claim
       results[i] = tvm_verify(params, &claims[i], proofs[i], proof_lens[i], skip_air_check, nullptr, 0);
   };
   std::vector<std::thread> pool;
-  for (unsigned t = 1; t < num_threads; t++) pool.emplace_back(worker);
+  try {
+    for (unsigned t = 1; t < num_threads; t++) pool.emplace_back(worker);
+  } catch (...) {
+    // std::system_error (no more threads): the threads already started plus this one finish the batch
+  }
   worker();
   for (auto &th : pool) th.join();
   int rc = TVM_OK;

@@ -111,6 +111,10 @@ _SIGNATURES = {
                                  AUX_CALLBACK, _vp, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
     "tvm_prove_tables": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, _u64p, ctypes.c_int,
                                         _u64p, _u64p, _u64p, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
+    "tvm_stir_prove": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u64p, _u64p,
+                                      ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_size_t)]),
+    "tvm_stir_verify": (ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u64p, ctypes.c_size_t,
+                                       ctypes.POINTER(ctypes.c_uint32), _u64p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t]),
     "tvm_fill_derived_main_columns": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint]),
     "tvm_aux_extend": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint, _u64p, _u64p, _u64p]),
     "tvm_verify": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), _u64p, ctypes.c_size_t, ctypes.c_int,
@@ -137,6 +141,23 @@ def lib():
             f.argtypes = args
         _lib = l
     return _lib
+
+
+def stir_verify(security_level, log2_expansion, log2_high_degree_bound, proof, conjectured=False):
+    """Stir::verify for arbitrary StirParameters (host code, no GPU) -> (accepted, failure, first-round indices, partial first codeword [k,3])"""
+    pr, prp = _np_u64(proof)
+    cap = ctypes.c_size_t(8192)
+    idx = (ctypes.c_uint32 * 8192)()
+    vals = np.zeros((8192, 3), dtype=np.uint64)
+    msg = ctypes.create_string_buffer(256)
+    rc = lib().tvm_stir_verify(security_level, int(conjectured), log2_expansion, log2_high_degree_bound, prp, pr.size, idx,
+                               vals.ctypes.data_as(_u64p), ctypes.byref(cap), msg, 256)
+    if rc == 0:
+        k = cap.value
+        return True, "", [int(idx[i]) for i in range(k)], vals[:k].copy()
+    if rc == -9:
+        return False, msg.value.decode(), [], vals[:0]
+    raise TvmError(rc, lib().tvm_strerror(rc).decode())
 
 
 def _proof_capacity(dom):
@@ -175,7 +196,7 @@ def hash_varlen(words):
     return [int(v) for v in d]
 
 
-def derive_domains(security_level=160, log2_expansion=2, padded_height=1 << 10, ldt_choice=LDT_FRI, conjectured=False):
+def derive_domains(security_level=160, log2_expansion=2, padded_height=1 << 10, ldt_choice=LDT_AUTO, conjectured=False):
     """Stark::{fri, stir, max_degree, ...} + ProverDomains::derive; pure host function."""
     p = Params(security_level, log2_expansion, ldt_choice, int(conjectured))
     d = Domains()
@@ -344,8 +365,8 @@ class Backend:
         return out
 
     def prove(self, claim, main_trace, main_rand, aux_provider, quot_rand, security_level=160, log2_expansion=2,
-              padded_height=None, ldt_choice=LDT_FRI, conjectured=False):
-        """Stark::prove; `ldt_choice` LDT_FRI / LDT_STIR / LDT_AUTO (the reference's heuristic).  claim = (program_digest[5], input, output[, version]);
+              padded_height=None, ldt_choice=LDT_AUTO, conjectured=False):
+        """Stark::prove; `ldt_choice` LDT_AUTO (default: the reference's heuristic, what Stark::default() does) / LDT_FRI / LDT_STIR.  claim = (program_digest[5], input, output[, version]);
         main_trace [379, n], main_rand [379, h] canonical uint64; aux_provider(challenges [63,3]) ->
         (aux_trace [91, n, 3], aux_rand [91, h, 3]); quot_rand [(h+1)*5, 3].  Returns the proof words.
         The traces may be numpy arrays (host) or contiguous torch int64 tensors (pinned host or CUDA:
@@ -428,6 +449,21 @@ class Backend:
                                       rcp, qrp, buf.ctypes.data_as(_u64p), ctypes.byref(cap))
         self._chk(rc)
         return buf[:cap.value].copy()
+
+    def stir_prove(self, security_level, log2_expansion, log2_high_degree_bound, codeword, conjectured=False):
+        """Stir::prove on the device for arbitrary StirParameters: codeword [2^(hdb+exp), 3] canonical -> (proof words, revealed indices)"""
+        cw, cwp, shape = _u64_arg(codeword)
+        n = 1 << (log2_high_degree_bound + log2_expansion)
+        assert int(np.prod(shape)) == 3 * n
+        cap = ctypes.c_size_t(0)
+        icap = ctypes.c_size_t(8192)
+        idx = (ctypes.c_uint32 * 8192)()
+        est = 1 << 22
+        buf = np.empty(est, dtype=np.uint64)
+        cap.value = est
+        self._chk(self._l.tvm_stir_prove(self._h, security_level, int(conjectured), log2_expansion, log2_high_degree_bound, cwp,
+                                         buf.ctypes.data_as(_u64p), ctypes.byref(cap), idx, ctypes.byref(icap)))
+        return buf[:cap.value].copy(), [int(idx[i]) for i in range(icap.value)]
 
     def set_low_memory(self, mode):
         """0 = automatic, 1 = always just-in-time LDE (tables never stored), 2 = always cache."""
