@@ -252,6 +252,14 @@ void Ctx::all_reduce_sum(u64 *dev_buf, size_t count) {
     throw ApiError{TVM_ERR_INVALID_ARG, "all_reduce callback failed"};
 }
 
+cudaStream_t Ctx::get_pair_stream() {
+  if (!pair_stream) {
+    TVM_CUDA(cudaStreamCreateWithFlags(&pair_stream, cudaStreamNonBlocking));
+    TVM_CUDA(cudaEventCreateWithFlags(&pair_fork, cudaEventDisableTiming));
+    TVM_CUDA(cudaEventCreateWithFlags(&pair_join, cudaEventDisableTiming));
+  }
+  return pair_stream;
+}
 cudaStream_t Ctx::get_copy_stream() {
   if (!copy_stream) TVM_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
   return copy_stream;
@@ -300,6 +308,9 @@ Ctx::~Ctx() {
   for (void *p : owned) cudaFree(p);
   for (auto &s : scratch)
     if (s.p) cudaFree(s.p);
+  if (pair_stream) { cudaStreamDestroy(pair_stream); cudaEventDestroy(pair_fork); cudaEventDestroy(pair_join); }
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  for (cudaEvent_t e : copy_events) cudaEventDestroy(e);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 

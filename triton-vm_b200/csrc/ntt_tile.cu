@@ -189,12 +189,19 @@ static void launch_tile(int logr, dim3 grid, cudaStream_t s, const TileJob &j) {
   TVM_CUDA(cudaGetLastError());
 }
 
-// bytes of transposed intermediate one launch pair may produce: it has to survive in the L2 (126 MB, shared with the
-// streaming output) between the two passes.  ncu with the caches left alone, 64 MB per pair: pass A wrote 53 MB of it back to
-// DRAM and pass B read all 67 MB from DRAM (profiles/r02f_ntt_tile_traffic.md).
+// bytes of transposed intermediate one launch pair may produce: pass B should find it in the L2 (126 MB, shared with the
+// streaming output).  Measured DRAM traffic per column at 2^20, 8 cosets (ncu, caches left alone, no replay;
+// profiles/r02h_ntt_tile_traffic.md): 157 MB with 64 MB pairs, 137 MB with 32 MB pairs on two streams (algorithmic: 72 MB;
+// the L2 writes the dirty intermediate back once in any case: 8 + 64 + 64 = 136 MB is the floor of a two-pass transform).
 static size_t tile_tmp_budget() {
   static const size_t mb = getenv("TVM_NTT_TMP_MB") ? (size_t)atoi(getenv("TVM_NTT_TMP_MB")) : 32;
   return std::max<size_t>(1, mb) << 20;
+}
+// launch pairs alternate between the context's stream and a second one (each with its own half of the intermediate buffer):
+// a pair is 1024 CTAs = 3.46 waves of the 296 resident CTAs, the other stream's CTAs fill the partial last wave
+static int tile_streams() {
+  static const int k = getenv("TVM_NTT_STREAMS") ? atoi(getenv("TVM_NTT_STREAMS")) : 2;
+  return k >= 2 ? 2 : 1;
 }
 
 // Picks n = n2 * n1 with both factors in {2^6, 2^8, 2^10}; false if this size is left to ntt.cu's kernels.
@@ -248,25 +255,42 @@ bool lde_evaluate_tiles(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned 
   b.out_row_stride = 1; b.out_elem_stride = n2;
   b.tw = c.get_tile_tw(lb, false);
   b.post_mode = 0;
-  // launch pairs of (columns x cosets) whose transposed intermediate fits the L2 budget: pass B consumes it from the L2
+  // launch pairs of (columns x cosets) whose transposed intermediate fits the budget
   const size_t budget_words = tile_tmp_budget() / 8;
   size_t cos_per = std::min<size_t>(num_cosets, std::max<size_t>(1, budget_words / n));
   while (num_cosets % cos_per) cos_per--;
   const size_t group = cos_per == num_cosets ? std::max<size_t>(1, budget_words / ((size_t)num_cosets * n)) : 1;
+  const size_t pair_words = group * cos_per * n;
+  const size_t npairs = ((ncols + group - 1) / group) * (num_cosets / cos_per);
+  const bool two = tile_streams() == 2 && npairs >= 2 && 2 * pair_words <= ncols * (size_t)num_cosets * n;
+  cudaStream_t st[2] = {c.stream, c.stream};
+  if (two) {
+    st[1] = c.get_pair_stream();
+    TVM_CUDA(cudaEventRecord(c.pair_fork, c.stream));
+    TVM_CUDA(cudaStreamWaitEvent(st[1], c.pair_fork, 0));
+  }
+  size_t pi = 0;
   for (size_t c0 = 0; c0 < ncols; c0 += group) {
     const size_t g = std::min(group, ncols - c0);
-    for (size_t y0 = 0; y0 < num_cosets; y0 += cos_per) {
+    for (size_t y0 = 0; y0 < num_cosets; y0 += cos_per, pi++) {
+      const int k = two ? (int)(pi & 1) : 0;
       TileJob aa = a, bb = b;
       aa.in += c0 * coef_stride;
+      aa.out += (size_t)k * pair_words;
       aa.prescale += y0 * n2; aa.fold_factor += y0;
       aa.coset_first = coset_first + coset_step * (unsigned)y0;
       aa.out_col_stride = cos_per * n;                       // the intermediate of this pair only
+      bb.in += (size_t)k * pair_words;
       bb.in_col_stride = cos_per * n;
       bb.out += (c0 * (size_t)num_cosets + y0) * n;
-      launch_tile<false, true, 1, false>(ra, dim3((unsigned)(n1 / TA), (unsigned)cos_per, (unsigned)g), c.stream, aa);
-      launch_tile<false, false, 0, true>(rb, dim3((unsigned)(n2 / TB), (unsigned)cos_per, (unsigned)g), c.stream, bb);
+      launch_tile<false, true, 1, false>(ra, dim3((unsigned)(n1 / TA), (unsigned)cos_per, (unsigned)g), st[k], aa);
+      launch_tile<false, false, 0, true>(rb, dim3((unsigned)(n2 / TB), (unsigned)cos_per, (unsigned)g), st[k], bb);
       c.launches += 2;
     }
+  }
+  if (two) {
+    TVM_CUDA(cudaEventRecord(c.pair_join, st[1]));
+    TVM_CUDA(cudaStreamWaitEvent(c.stream, c.pair_join, 0));
   }
   return true;
 }
