@@ -1,5 +1,6 @@
 #!/bin/bash
-# builds lib/variants/libtvm_b200_<name>.so for A/B runs of the generated AIR kernels (TVM_B200_LIB selects one at run time)
+# builds lib/variants/libtvm_b200_<name>.so for A/B runs of the generated AIR kernels (TVM_B200_LIB selects one at run time);
+# restores the default generation at the end
 set -e
 cd "$(dirname "$0")/../triton-vm_b200"
 mkdir -p lib/variants
@@ -10,6 +11,13 @@ build() {  # name, env...
   cp lib/libtvm_b200.so lib/variants/libtvm_b200_$name.so
   echo "built $name: $(head -2 csrc/air_gen/air_chunks.inc | tail -1)"
 }
-build chunks100 TVM_AIR_FUSED=0 TVM_AIR_BUDGET=100
-build chunks160 TVM_AIR_FUSED=0 TVM_AIR_BUDGET=160
-build groups220 TVM_AIR_FUSED=1 TVM_AIR_BUDGET=100 TVM_AIR_GROUP_BUDGET=220
+for v in "$@"; do
+  case $v in
+    chunks160) build chunks160 TVM_AIR_FUSED=0 TVM_AIR_BUDGET=160 ;;
+    groups220) build groups220 TVM_AIR_FUSED=1 TVM_AIR_GROUP_BUDGET=220 ;;
+    minb2) build minb2 TVM_AIR_MIN_BLOCKS=2 ;;
+    minb3) build minb3 TVM_AIR_MIN_BLOCKS=3 ;;
+    budget60) build budget60 TVM_AIR_BUDGET=60 ;;
+  esac
+done
+python -m airgen.codegen_cuda > /dev/null && make -j8 > /dev/null 2>&1 && echo "default restored: $(head -2 csrc/air_gen/air_chunks.inc | tail -1)"

@@ -33,7 +33,7 @@ OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 CHUNK_COST_BUDGET = float(os.environ.get("TVM_AIR_BUDGET", "100"))
 SYNC_EVERY = int(os.environ.get("TVM_AIR_SYNC_EVERY", "0"))
 NUM_TUS = int(os.environ.get("TVM_AIR_TUS", "8"))
-MIN_BLOCKS = int(os.environ.get("TVM_AIR_MIN_BLOCKS", "1"))
+MIN_BLOCKS = int(os.environ.get("TVM_AIR_MIN_BLOCKS", "2"))   # measured at 2^21 rows: 1 -> 41.3 ms, 2 -> 39.5 ms, 3 -> 42.4 ms (profiles/r02_air_variants.md)
 # measured at 2^20: splitting the few oversized constraints (up to 1079 operations in one kernel) raises the emitted
 # operations by 8-29 % (shared sub-expressions are recomputed per piece) and does not pay: 168.6 ms unsplit,
 # 171.6 ms with 400-cost pieces, 240.7 ms with 250-cost pieces.  Off by default.

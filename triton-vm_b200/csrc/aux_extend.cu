@@ -8,9 +8,13 @@
 // logarithmic derivative: a = 1, b = multiplicity / (indeterminate - value)), so on the device a column is the inclusive
 // SCAN of its row maps under composition, parallel over rows as well as columns:
 //
-//   aux_scan_kernel<false>   one CTA per (256-row chunk, column): row maps, CTA scan, chunk total      -> tot
+//   aux_scan_kernel          one CTA per (256-row chunk, column): row maps, CTA scan; stores the scanned map of every row
+//                            (48 B per row and column) and the chunk total                                 -> maps, tot
 //   aux_scan_tops_kernel     one warp per column: the chunk totals in order                            -> value entering each chunk
-//   aux_scan_kernel<true>    row maps again (cheaper than spilling 48 B per row and column), CTA scan, apply, store
+//   aux_apply_kernel         scanned map of the row applied to the value entering its chunk, store
+//                            (round 1 recomputed the row maps and the scan here: ncu r02i, 2^18 rows, 47 columns: 6 780
+//                            instructions per row and column in EACH pass, half of them the map itself - logarithmic
+//                            derivatives cost a field inversion per row; 48 B of traffic are far cheaper)
 //
 // twice: 47 columns depend on the main table only, two (program table: send-chunk evaluation; RAM table: formal
 // derivative) read a finished column of the first pass.  The row maps (a_i, b_i) are not hand-written: airgen/extend_gen.py
@@ -107,12 +111,12 @@ struct AuxScanArgs {
   size_t n, nchunks;
   u64 *tot;   // [ncols][nchunks][6]   chunk totals
   u64 *vin;   // [ncols][nchunks][3]   value of the column before the chunk's first row
+  u64 *maps;  // [ncols][6][n]         scanned (within its chunk) map of every row
   int ncols;
   int cols[AUXGEN_NUM_BASE];
 };
 
-template <bool APPLY>
-__global__ void __launch_bounds__(AUX_CHUNK) aux_scan_kernel(AuxScanArgs p) {
+__global__ void __launch_bounds__(AUX_CHUNK, 2) aux_scan_kernel(AuxScanArgs p) {
   __shared__ u64 sm[2][6][AUX_CHUNK];
   const int q = p.cols[blockIdx.y];
   const size_t i = (size_t)blockIdx.x * AUX_CHUNK + threadIdx.x;
@@ -133,17 +137,26 @@ __global__ void __launch_bounds__(AUX_CHUNK) aux_scan_kernel(AuxScanArgs p) {
   }
   m = cta_scan(m, sm);
   const size_t slot = (size_t)blockIdx.y * p.nchunks + blockIdx.x;
-  if (!APPLY) {
-    if (threadIdx.x == AUX_CHUNK - 1) {
-      u64 *o = p.tot + slot * 6;
-      o[0] = m.a.c0; o[1] = m.a.c1; o[2] = m.a.c2; o[3] = m.b.c0; o[4] = m.b.c1; o[5] = m.b.c2;
-    }
-  } else if (i < p.n) {
-    const u64 *vi = p.vin + slot * 3;
-    xfe v = xadd(xmul(m.a, xmake(vi[0], vi[1], vi[2])), m.b);
-    auxctx c{const_cast<u64 *>(p.main_t), p.aux_t, p.ch, p.n, i, i};
-    aux_store(c, q, i, v);
+  if (i < p.n) {                        // scanned map of row i: planes [column of the level][6][n]
+    u64 *o = p.maps + (size_t)blockIdx.y * 6 * p.n + i;
+    o[0] = m.a.c0; o[p.n] = m.a.c1; o[2 * p.n] = m.a.c2; o[3 * p.n] = m.b.c0; o[4 * p.n] = m.b.c1; o[5 * p.n] = m.b.c2;
   }
+  if (threadIdx.x == AUX_CHUNK - 1) {
+    u64 *o = p.tot + slot * 6;
+    o[0] = m.a.c0; o[1] = m.a.c1; o[2] = m.a.c2; o[3] = m.b.c0; o[4] = m.b.c1; o[5] = m.b.c2;
+  }
+}
+
+__global__ void __launch_bounds__(AUX_CHUNK) aux_apply_kernel(AuxScanArgs p) {
+  const int q = p.cols[blockIdx.y];
+  const size_t i = (size_t)blockIdx.x * AUX_CHUNK + threadIdx.x;
+  if (i >= p.n) return;
+  const u64 *o = p.maps + (size_t)blockIdx.y * 6 * p.n + i;
+  const xfe a = xmake(o[0], o[p.n], o[2 * p.n]), b = xmake(o[3 * p.n], o[4 * p.n], o[5 * p.n]);
+  const u64 *vi = p.vin + ((size_t)blockIdx.y * p.nchunks + blockIdx.x) * 3;
+  const xfe v = xadd(xmul(a, xmake(vi[0], vi[1], vi[2])), b);
+  u64 *w = p.aux_t + (size_t)(3 * q) * p.n + i;
+  w[0] = v.c0; w[p.n] = v.c1; w[2 * p.n] = v.c2;
 }
 
 // one warp per column, lane 0 walks the chunk totals in order (n / 256 compositions: 4096 at 2^20, ~1.5 ms for all columns
@@ -234,7 +247,7 @@ __global__ void interleave3_from_mont_kernel(const u64 *in, u64 *out, size_t n, 
 
 }  // namespace
 
-size_t aux_extend_scratch_words(size_t n) { return (size_t)AUXGEN_NUM_BASE * ((n + AUX_CHUNK - 1) / AUX_CHUNK) * 9; }
+size_t aux_extend_scratch_words(size_t n) { return (size_t)AUXGEN_NUM_BASE * (((n + AUX_CHUNK - 1) / AUX_CHUNK) * 9 + 6 * n); }
 
 // d_main [379][n], d_ch [63*3], d_aux [273][n] (all Montgomery; the batch-randomizer planes 270..272 are the caller's)
 void aux_extend_run(Ctx &c, const u64 *d_main, size_t n, const u64 *d_ch, u64 *d_aux, u64 *d_scratch) {
@@ -243,17 +256,18 @@ void aux_extend_run(Ctx &c, const u64 *d_main, size_t n, const u64 *d_ch, u64 *d
   p.nchunks = (n + AUX_CHUNK - 1) / AUX_CHUNK;
   p.tot = d_scratch;
   p.vin = d_scratch + (size_t)AUXGEN_NUM_BASE * p.nchunks * 6;
+  p.maps = d_scratch + (size_t)AUXGEN_NUM_BASE * p.nchunks * 9;
   for (int level = 0; level < AUXGEN_NUM_LEVELS; level++) {
     p.ncols = 0;
     for (int q = 0; q < AUXGEN_NUM_BASE; q++)
       if (AUXGEN_LEVEL[q] == level) p.cols[p.ncols++] = q;
     if (!p.ncols) continue;
     dim3 grid((unsigned)p.nchunks, (unsigned)p.ncols);
-    aux_scan_kernel<false><<<grid, AUX_CHUNK, 0, c.stream>>>(p);
+    aux_scan_kernel<<<grid, AUX_CHUNK, 0, c.stream>>>(p);
     static const bool tops_parallel = getenv("TVM_AUX_TOPS_PARALLEL") && atoi(getenv("TVM_AUX_TOPS_PARALLEL"));
     if (tops_parallel) aux_scan_tops_parallel_kernel<<<(unsigned)p.ncols, AUX_CHUNK, 0, c.stream>>>(p);
     else aux_scan_tops_kernel<<<(unsigned)p.ncols, 32, 0, c.stream>>>(p);
-    aux_scan_kernel<true><<<grid, AUX_CHUNK, 0, c.stream>>>(p);
+    aux_apply_kernel<<<grid, AUX_CHUNK, 0, c.stream>>>(p);
     c.launches += 3;
     TVM_CUDA(cudaGetLastError());
   }
