@@ -194,13 +194,18 @@ __device__ __forceinline__ void tip5_perm_quad(u64 (&s)[4], int l, int group_bas
 // stream the two pipes are used alternately rather than concurrently (ncu r01b: issue 54 %,
 // `math_pipe_throttle` the top stall).  Each quad therefore carries two independent rows, half a
 // round out of phase: the MDS of one state is scheduled together with the S-box of the other.
+// split-and-lookup (tip-0005.md:52-61) of one 32-bit half: byte extraction and re-assembly with PRMT (the shift/mask/or
+// form costs ~6 instructions per byte, this one 11 per four bytes); the looked-up values are zero-extended bytes, so
+// "byte 1 of l" is a zero for the unused selector positions
+__device__ __forceinline__ unsigned lookup_word(unsigned w, const unsigned char *lut) {
+  const unsigned l0 = lut[w & 0xFF], l1 = lut[__byte_perm(w, 0, 0x4441)], l2 = lut[__byte_perm(w, 0, 0x4442)], l3 = lut[w >> 24];
+  return __byte_perm(__byte_perm(l0, l1, 0x1140), __byte_perm(l2, l3, 0x1140), 0x5410);
+}
+__device__ __forceinline__ u64 lookup_u64(u64 v, const unsigned char *lut) {
+  return ((u64)lookup_word((unsigned)(v >> 32), lut) << 32) | lookup_word((unsigned)v, lut);
+}
 __device__ __forceinline__ void quad_sbox(u64 (&s)[4], const unsigned char *lut) {
-  {  // slot 0: split-and-lookup
-    u64 v = s[0], o = 0;
-#pragma unroll
-    for (int b = 0; b < 8; b++) o |= (u64)lut[(unsigned)((v >> (8 * b)) & 0xFF)] << (8 * b);
-    s[0] = o;
-  }
+  s[0] = lookup_u64(s[0], lut);   // slot 0: split-and-lookup
 #pragma unroll
   for (int i = 1; i < 4; i++) {
     u64 x = s[i], x2 = fmul(x, x), x3 = fmul(x2, x), x4 = fmul(x2, x2);
