@@ -212,14 +212,14 @@ def spin_instance(log2_padded_height, security, ldt, seed=41):
     return program_instance(SPIN, [log2_padded_height], security, ldt, seed)
 
 
-def program_instance(program, inp, security, ldt, seed=41):
+def program_instance(program, inp, security, ldt, seed=41, ram=None):
     words = tg.assemble(program)
     inp = list(inp)
-    ph = tg.padded_height(words, inp)
+    ph = tg.padded_height(words, inp, [], ram) if ram else tg.padded_height(words, inp)
     st = S.Stark(security, 2, ldt)
     d = st.derive(ph)
     n, h = d["trace_len"], d["num_trace_randomizers"]
-    T, digest, out = tg.main_table(words, inp, n)
+    T, digest, out = tg.main_table(words, inp, n, [], ram) if ram else tg.main_table(words, inp, n)
     main = np.array(T, dtype=np.uint64)
     rng = np.random.default_rng(seed)
     mrand, arand, rcol = rand_bfes(rng, (379, h)), rand_bfes(rng, (91, h, 3)), rand_bfes(rng, (n, 3))
@@ -246,14 +246,63 @@ def test_spin_reaches_the_requested_padded_height_and_satisfies_the_air():
     assert tvm_b200.verify((claim.program_digest, claim.input, claim.output), proof, 8, 2, ldt_choice=tvm_b200.LDT_FRI) == (True, "")
 
 
+# A verifier-shaped program as the stand-in for BASELINE's "recursive-verifier program" (its TASM lives in the external tasm-lib,
+# SURVEY 8(d).5): per iteration eight 10-word absorptions from memory (the hash table grows by 48 rows), u32 comparisons and
+# bit operations, a division, X-field multiplication / inversion, RAM writes and reads - the instruction mix of a STARK
+# verifier (Merkle/sponge hashing, index arithmetic, extension-field arithmetic), sized by its public input.
+# (sponge_absorb_mem overwrites st1..st4 with the first absorbed words, vm.rs:699-729: four scratch words sit under the pointer)
+VERIFIER_LIKE = """
+    read_io 1 sponge_init call body sponge_squeeze write_io 5 pop 5 pop 1 halt
+  body:
+    dup 0 push 0 eq skiz return
+    push 0 push 0 push 0 push 0 push 400 sponge_absorb_mem sponge_absorb_mem sponge_absorb_mem sponge_absorb_mem pop 5
+    push 0 push 0 push 0 push 0 push 440 sponge_absorb_mem sponge_absorb_mem sponge_absorb_mem sponge_absorb_mem pop 5
+    push 1234567 push 89 lt pop 1
+    push 61680 push 65280 and push 12345 xor pop 1
+    push 7 push 100 div_mod pop 2
+    push 1000 log_2_floor pop_count pop 1
+    push 1 push 2 push 3 push 4 push 5 push 6 xx_mul x_invert push 11 xb_mul
+    push 100 write_mem 3 pop 1
+    push 102 read_mem 3 pop 4
+    addi -1 recurse
+"""
+VERIFIER_LIKE_RAM = {400 + k: 1000 + 7 * k for k in range(80)}
+
+
 def _workload(name):
+    """(program, public input, initial RAM) of a named workload: spin_K, fib_N (benches/prove_fib.rs:8-28), verifier_N"""
     from test_fibonacci_program import FIBONACCI
     kind, arg = name.split("_")
-    return (SPIN, [int(arg)]) if kind == "spin" else (FIBONACCI, [int(arg)])      # fib_100: benches/prove_fib.rs:8-28
+    if kind == "verifier":
+        return VERIFIER_LIKE, [int(arg)], VERIFIER_LIKE_RAM
+    return (SPIN, [int(arg)], None) if kind == "spin" else (FIBONACCI, [int(arg)], None)
+
+
+def verifier_like_instance(iterations, security, ldt, seed=41):
+    return program_instance(VERIFIER_LIKE, [iterations], security, ldt, seed, ram=VERIFIER_LIKE_RAM)
+
+
+def test_verifier_like_program_runs_and_satisfies_the_air():
+    words = tg.assemble(VERIFIER_LIKE)
+    ex = tg.execute(words, [3], [], VERIFIER_LIKE_RAM)
+    assert len(ex.output) == 5
+    used = {tg._NAME[r["ci"]] for r in ex.rows}
+    assert {"sponge_absorb_mem", "lt", "and", "xor", "div_mod", "log_2_floor", "pop_count", "xx_mul", "x_invert", "xb_mul", "write_mem",
+            "read_mem", "recurse"} <= used
+    inst = verifier_like_instance(3, 8, "fri")
+    n = inst["main"].shape[1]
+    rng = np.random.default_rng(3)
+    sampled = [tuple(int(v) for v in rng.integers(0, P, 3, dtype=np.uint64)) for _ in range(59)]
+    ch = S.derive_challenges(sampled, inst["claim"])
+    B = corc.aux_extend(inst["main"], ch)
+    assert tg.failing_constraints(inst["T"], [[tuple(int(v) for v in B[q][i]) for i in range(n)] for q in range(91)], ch) == []
+    # sized for BASELINE heights by its input: 700 iterations pad to 2^16 (3 000 to 2^18, 11 500 to 2^20)
+    assert tg.padded_height(words, [700], [], VERIFIER_LIKE_RAM) == 1 << 16
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("workload,ldt", [("fib_100", None), ("spin_13", "fri"), ("spin_14", "stir"), ("spin_16", None),
+                                          ("verifier_700", None),      # verifier-shaped stand-in for the recursive verifier, 2^16
                                           ("spin_18", None), ("spin_20", None)])   # None: Stark::default() — FRI below 2^16, STIR from
                                                                                  # there on; spin_20 is the BASELINE headline size
 def test_gpu_proves_benchmark_workloads_from_the_149_table_columns(backend, workload, ldt):
@@ -261,8 +310,8 @@ def test_gpu_proves_benchmark_workloads_from_the_149_table_columns(backend, work
     Stark::default() security, checked by the verifier INCLUDING the AIR — and, where tests/golden/spin_digests.json holds the
     oracle's digest of the same instance, word for word: degree-lowering main columns, auxiliary table, proof: all from the GPU."""
     import tvm_b200
-    program, inp = _workload(workload)
-    inst = program_instance(program, inp, 160, ldt)
+    program, inp, ram = _workload(workload)
+    inst = program_instance(program, inp, 160, ldt, ram=ram)
     log2_padded_height = inst["padded_height"].bit_length() - 1
     claim, want_main = inst["claim"], inst["main"]
     main = want_main.copy()

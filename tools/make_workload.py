@@ -3,6 +3,7 @@
 
     python tools/make_workload.py spin_20 /tmp/spin20           # ProgramToBench::spin(20), Stark::default()
     python tools/make_workload.py fib_100 /tmp/fib100 [--security 160] [--ldt auto|fri|stir]
+    python tools/make_workload.py verifier_11500 /tmp/ver20      # verifier-shaped program (hashing from memory, u32, X-field, RAM), 2^20
     PROVE_TABLES_REPS=3 ./prove_tables /tmp/spin20              # 149 table columns -> proof, verified incl. the AIR
 
 The tables come from the oracle's VM and table fill (oracle/tracegen.py — bit-identical to the reference on its whole-proof
@@ -27,8 +28,8 @@ def main():
     ap.add_argument("--seed", type=int, default=41)
     a = ap.parse_args()
     import test_vm_programs as tvp
-    program, inp = tvp._workload(a.workload)
-    inst = tvp.program_instance(program, inp, a.security, None if a.ldt == "auto" else a.ldt, a.seed)
+    program, inp, ram = tvp._workload(a.workload)          # spin_K | fib_N | verifier_N (verifier-shaped mixed program)
+    inst = tvp.program_instance(program, inp, a.security, None if a.ldt == "auto" else a.ldt, a.seed, ram=ram)
     os.makedirs(a.out_dir, exist_ok=True)
     main_t = inst["main"].copy()
     main_t[149:] = 0
