@@ -27,7 +27,7 @@ def test_parameter_derivation_matches_reference_facts():
 @pytest.mark.parametrize("sec,le,ph", [(160, 2, 1 << 20), (160, 2, 1 << 10), (160, 2, 1 << 16), (4, 2, 16), (32, 2, 256),
                                         (160, 2, 1 << 22), (160, 1, 1 << 12), (80, 3, 1 << 9)])
 def test_c_abi_derive_domains_matches_oracle(sec, le, ph):
-    a = tvm_b200.derive_domains(sec, le, ph)            # default ldt_choice: LdtChoice::Fri
+    a = tvm_b200.derive_domains(sec, le, ph, tvm_b200.LDT_FRI)
     b = S.Stark(sec, le, "fri").derive(ph)
     assert all(a[k] == b[k] for k in a if k in b and not k.startswith("stir") and k != "ldt"), (a, b)
 
