@@ -58,7 +58,8 @@ def _worker(rank, world, port, params, q):
 
 
 @pytest.mark.parametrize("world,params", [(2, (8, 2, 64, 2, "fri")), (4, (32, 2, 256, 3, "fri")), (8, (8, 2, 64, 7, "fri")),
-                                          (2, (6, 2, 256, 12, "stir"))])
+                                          (2, (6, 2, 256, 12, "stir")),
+                                          (2, (6, 2, 4096, 5, "stir"))])     # large enough for the sharded STIR leaf hashing
 def test_sharded_proof_equals_single_gpu_proof(world, params):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

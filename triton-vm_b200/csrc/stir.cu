@@ -190,8 +190,18 @@ std::vector<uint32_t> stir_prove_run(Ctx &c, DevMem &mem, ProofStream &ps, const
     stir_stack_kernel<<<st_grid(3 * L), ST_THREADS, 0, c.stream>>>(d_cw, L, ff, cm.stack);
     launch_check(1);
     TVM_CUDA(cudaMemsetAsync(cm.nodes, 0, 40, c.stream));
-    hash_rows_run(c, cm.stack, cm.leaves, cm.leaves, 3 * ff, 0, cm.nodes + 5 * cm.leaves);
-    merkle_run(c, cm.nodes, cm.leaves);
+    const unsigned W = (unsigned)c.comm.world, rank = (unsigned)c.comm.rank;
+    if (W > 1 && cm.leaves >= (size_t)4096 * W) {
+      // multi-GPU: the codeword is replicated, so each rank hashes its 1/W of the stacked leaves; the leaf digests are
+      // all-gathered and every rank builds the (much cheaper) tree itself: queries are answered from the complete node array
+      const size_t per = cm.leaves / W;
+      hash_rows_run(c, cm.stack + (size_t)rank * per, cm.leaves, per, 3 * ff, 0, cm.nodes + 5 * (cm.leaves + (size_t)rank * per));
+      c.all_gather(cm.nodes + 5 * cm.leaves, per * 40);
+      merkle_run(c, cm.nodes, cm.leaves);
+    } else {
+      hash_rows_run(c, cm.stack, cm.leaves, cm.leaves, 3 * ff, 0, cm.nodes + 5 * cm.leaves);
+      merkle_run(c, cm.nodes, cm.leaves);
+    }
     std::vector<u64> root = d2h(c, cm.nodes + 5, 5);
     for (auto &v : root) v = from_mont(v);
     ps.enqueue(ItemKind::MerkleRoot, root);
