@@ -18,6 +18,8 @@ for v in "$@"; do
     minb2) build minb2 TVM_AIR_MIN_BLOCKS=2 ;;
     minb3) build minb3 TVM_AIR_MIN_BLOCKS=3 ;;
     budget60) build budget60 TVM_AIR_BUDGET=60 ;;
+    split400) build split400 TVM_AIR_SPLIT=1 TVM_AIR_SPLIT_BUDGET=400 ;;
+    split250) build split250 TVM_AIR_SPLIT=1 TVM_AIR_SPLIT_BUDGET=250 ;;
   esac
 done
 python -m airgen.codegen_cuda > /dev/null && make -j8 > /dev/null 2>&1 && echo "default restored: $(head -2 csrc/air_gen/air_chunks.inc | tail -1)"

@@ -37,8 +37,10 @@ MIN_BLOCKS = int(os.environ.get("TVM_AIR_MIN_BLOCKS", "2"))   # measured at 2^21
 # measured at 2^20: splitting the few oversized constraints (up to 1079 operations in one kernel) raises the emitted
 # operations by 8-29 % (shared sub-expressions are recomputed per piece) and does not pay: 168.6 ms unsplit,
 # 171.6 ms with 400-cost pieces, 240.7 ms with 250-cost pieces.  Off by default.
-SPLIT_BIG = os.environ.get("TVM_AIR_SPLIT", "0") != "0"
-SPLIT_BUDGET = float(os.environ.get("TVM_AIR_SPLIT_BUDGET", "250"))   # pieces of an oversized constraint may be this large
+# Round 2, with the 128-register cap (MIN_BLOCKS = 2) the balance tips: 157.8 ms unsplit, 152.4 ms with 400-cost pieces (the 1 079-
+# operation constraint no longer spills 1.4 KB), 199.8 ms with 250-cost pieces (profiles/r02_air_variants.md).  On by default at 400.
+SPLIT_BIG = os.environ.get("TVM_AIR_SPLIT", "1") != "0"
+SPLIT_BUDGET = float(os.environ.get("TVM_AIR_SPLIT_BUDGET", "400"))   # pieces of an oversized constraint may be this large
 WTAB_WORDS = 7   # per weight: b0, b1, b2, -b1, -b2, b0+b2, b1-b2
 
 

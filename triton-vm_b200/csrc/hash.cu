@@ -798,62 +798,18 @@ static void merkle_level_launch(Ctx &c, u64 *nodes, size_t lo, size_t count, boo
   c.launches++;
 }
 
-// The upper levels of a tree (width <= MERKLE_TOP_WIDTH) in ONE launch: a single CTA of 1024 threads walks the levels with the
-// IMMA permutation (512 nodes per step) and a block-wide barrier between levels.  Each of these levels used to be its own
-// launch of ~25-30 us of latency (ncu r02l: 77 level launches in one STIR prove, 2.3 ms), plus 124 us for the last seven.
-static constexpr int MERKLE_TOP_THREADS = 1024;
-static constexpr size_t MERKLE_TOP_WIDTH = 4096;
-__global__ void __launch_bounds__(MERKLE_TOP_THREADS) merkle_upper_mma_kernel(u64 *nodes, size_t top_width) {
-  __shared__ unsigned char lut[256];
-  __shared__ u64 rc[80];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
-  for (int i = threadIdx.x; i < 80; i += blockDim.x) rc[i] = c_tip5_rc[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, l = lane & 3;
-  const MdsFrag f = mds_fragments(lane);
-  constexpr int QUADS = MERKLE_TOP_THREADS / 4;
-  for (size_t w = top_width; w >= 1; w >>= 1) {
-    for (size_t base = 0; base < w; base += 2 * QUADS) {      // uniform trip count: every warp takes part in every IMMA
-      size_t node[2];
-      bool active[2];
-      u64 s[2][4];
-#pragma unroll
-      for (int t = 0; t < 2; t++) {
-        size_t q = base + (threadIdx.x >> 2) + (size_t)t * QUADS;
-        active[t] = q < w;
-        if (!active[t]) q = w - 1;
-        node[t] = w + q;
-        const u64 *ch = nodes + 10 * node[t];
-        s[t][0] = ch[l];
-        s[t][1] = ch[l + 4];
-        s[t][2] = l < 2 ? ch[l + 8] : MONT_ONE;
-        s[t][3] = MONT_ONE;
-      }
-      tip5_perm_quad2_mma(s[0], s[1], l, f, lut, rc);
-#pragma unroll
-      for (int t = 0; t < 2; t++) {
-        if (!active[t]) continue;
-        u64 *d = nodes + 5 * node[t];
-        d[l] = s[t][0];
-        if (l == 0) d[4] = s[t][1];
-      }
-    }
-    __threadfence_block();
-    __syncthreads();
-  }
-}
-
 // leaves already stored at nodes[nleaves .. 2*nleaves)
+// (measured and rejected in round 2: the levels of width <= 4096 / <= 512 fused into ONE launch of a single 1024-thread CTA on the
+// IMMA permutation - 25.9 / 24.8 ms for a STIR prove at 2^23 against 22.7 ms with one launch per level: one SM against 148.)
 void merkle_run(Ctx &c, u64 *nodes, size_t nleaves) {
   size_t w = nleaves / 2;
+  const size_t TOP = 64;
   static const bool thread_per_node = getenv("TVM_TIP5_IMAD_MDS") != nullptr;
-  const size_t TOP = thread_per_node ? 64 : MERKLE_TOP_WIDTH;
   for (; w > TOP; w >>= 1) {
     merkle_level_launch(c, nodes, w, w, thread_per_node);
   }
   if (w >= 1) {
-    if (thread_per_node) merkle_top_kernel<<<1, HASH_THREADS, 0, c.stream>>>(nodes, w);
-    else merkle_upper_mma_kernel<<<1, MERKLE_TOP_THREADS, 0, c.stream>>>(nodes, w);
+    merkle_top_kernel<<<1, HASH_THREADS, 0, c.stream>>>(nodes, w);
     c.launches++;
   }
   TVM_CUDA(cudaGetLastError());
