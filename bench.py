@@ -46,9 +46,9 @@ def measured_peaks():
 
 def measured_lde_traffic(alg_bytes):
     """DRAM bytes (read + write) of the LDE kernels from the committed ncu capture, scaled to this workload:
-    profiles/r01d_ntt_traffic.json holds dram bytes per algorithmic byte of one 16-column LDE batch at 2^20."""
+    profiles/r02h_ntt_traffic.json holds dram bytes per algorithmic byte of the tile-NTT passes of a column LDE at 2^20."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01d_ntt_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02h_ntt_traffic.json")))
         return float(t["dram_bytes_per_algorithmic_byte"]) * alg_bytes, t.get("source")
     except Exception:
         return None, None
@@ -318,7 +318,7 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "stages_ms": {k: round(v, 3) for k, v in stages.items()},
         "e2e_stages_ms": {k: round(v, 3) for k, v in e2e_stages.items()},
-        "roofline": {"bound": "hbm", "kernel": "coset LDE (ntt_pass_a/ntt_pass_b) of the 652 table columns",
+        "roofline": {"bound": "hbm", "kernel": "coset LDE (ntt_tile_kernel: interpolation + 8-coset evaluation passes) of the 652 table columns",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                      "algorithmic_bytes": alg,

@@ -421,37 +421,28 @@ int tvm_aux_extend(tvm_ctx *ctx, const uint64_t *main_trace, unsigned log2_n, co
   TVM_API_BEGIN(ctx)
   const size_t n = (size_t)1 << log2_n, NM = TVM_NUM_MAIN_COLUMNS, NA = TVM_NUM_AUX_COLUMNS;
   Ctx &c = *c__;
-  u64 *d_main = (u64 *)c.pool_alloc(NM * n * 8);
-  u64 *d_aux = (u64 *)c.pool_alloc(3 * NA * n * 8);      // planes; reused as staging for the interleaved output
-  u64 *d_out = (u64 *)c.pool_alloc(3 * NA * n * 8);
-  u64 *d_misc = (u64 *)c.pool_alloc((3 * TVM_NUM_CHALLENGES + 3 * n + aux_extend_scratch_words(n)) * 8);
-  auto release = [&]() {
-    cudaStreamSynchronize(c.stream);
-    c.pool_release(d_main); c.pool_release(d_aux); c.pool_release(d_out); c.pool_release(d_misc);
-  };
-  try {
-    u64 *d_ch = d_misc, *d_rc = d_misc + 3 * TVM_NUM_CHALLENGES, *d_scratch = d_rc + 3 * n;
-    TVM_CUDA(cudaMemcpyAsync(d_main, main_trace, NM * n * 8, cudaMemcpyDefault, c.stream));
-    TVM_CUDA(cudaMemcpyAsync(d_ch, challenges, 3 * TVM_NUM_CHALLENGES * 8, cudaMemcpyDefault, c.stream));
-    to_mont_run(c, d_main, NM * n);
-    to_mont_run(c, d_ch, 3 * TVM_NUM_CHALLENGES);
-    u64 *d_rplanes = d_aux + 3 * (NA - 1) * n;
-    if (randomizer_column) {
-      TVM_CUDA(cudaMemcpyAsync(d_rc, randomizer_column, 3 * n * 8, cudaMemcpyDefault, c.stream));
-      to_mont_run(c, d_rc, 3 * n);
-      deinterleave3_run(c, d_rc, d_rplanes, n, 1);
-    } else {
-      TVM_CUDA(cudaMemsetAsync(d_rplanes, 0, 3 * n * 8, c.stream));
-    }
-    aux_extend_run(c, d_main, n, d_ch, d_aux, d_scratch);
-    interleave3_from_mont_run(c, d_aux, d_out, n, NA);
-    TVM_CUDA(cudaMemcpyAsync(aux_trace_out, d_out, 3 * NA * n * 8, cudaMemcpyDefault, c.stream));
-    TVM_CUDA(cudaStreamSynchronize(c.stream));
-  } catch (...) {
-    release();
-    throw;
+  DevMem mem(c);      // RAII: every block goes back to the pool on all exit paths (an allocation failure used to strand the earlier ones)
+  u64 *d_main = mem.words(NM * n);
+  u64 *d_aux = mem.words(3 * NA * n);      // planes; reused as staging for the interleaved output
+  u64 *d_out = mem.words(3 * NA * n);
+  u64 *d_misc = mem.words(3 * TVM_NUM_CHALLENGES + 3 * n + aux_extend_scratch_words(n));
+  u64 *d_ch = d_misc, *d_rc = d_misc + 3 * TVM_NUM_CHALLENGES, *d_scratch = d_rc + 3 * n;
+  TVM_CUDA(cudaMemcpyAsync(d_main, main_trace, NM * n * 8, cudaMemcpyDefault, c.stream));
+  TVM_CUDA(cudaMemcpyAsync(d_ch, challenges, 3 * TVM_NUM_CHALLENGES * 8, cudaMemcpyDefault, c.stream));
+  to_mont_run(c, d_main, NM * n);
+  to_mont_run(c, d_ch, 3 * TVM_NUM_CHALLENGES);
+  u64 *d_rplanes = d_aux + 3 * (NA - 1) * n;
+  if (randomizer_column) {
+    TVM_CUDA(cudaMemcpyAsync(d_rc, randomizer_column, 3 * n * 8, cudaMemcpyDefault, c.stream));
+    to_mont_run(c, d_rc, 3 * n);
+    deinterleave3_run(c, d_rc, d_rplanes, n, 1);
+  } else {
+    TVM_CUDA(cudaMemsetAsync(d_rplanes, 0, 3 * n * 8, c.stream));
   }
-  release();
+  aux_extend_run(c, d_main, n, d_ch, d_aux, d_scratch);
+  interleave3_from_mont_run(c, d_aux, d_out, n, NA);
+  TVM_CUDA(cudaMemcpyAsync(aux_trace_out, d_out, 3 * NA * n * 8, cudaMemcpyDefault, c.stream));
+  TVM_CUDA(cudaStreamSynchronize(c.stream));
   TVM_API_END
 }
 
