@@ -10,6 +10,7 @@
 // whole absorb loop (all 5 rounds fused; no state traffic), tables stored column-major so that
 // a warp's loads of one column are a single coalesced 256-byte segment.  The S-box lookup table
 // lives in shared memory; the round constants in constant memory (warp-uniform index).
+#include <cstdint>
 #include <cstdlib>
 #include "ctx.h"
 #include "tip5.cuh"
@@ -569,6 +570,111 @@ __global__ void __launch_bounds__(HASHM_THREADS) tip5_hash_rows_mma_kernel(HashR
   }
 }
 
+// ---- the same kernel with the table tiles staged by the TMA engine ---------------------------------------------------
+// One absorption reads a [10 columns][64 rows] tile of the column-major table: ten 512-byte runs.  Thread 0 hands them to
+// the bulk-copy engine (cp.async.bulk.shared::cluster.global -> UBLKCP, completion counted on an mbarrier) two absorptions
+// AHEAD of the permutation that consumes them: the loads of block b + 2 are in flight while block b is permuted, no lane
+// spends address arithmetic or a scoreboard wait on them.  Rows of a tile column sit 68 words apart in shared memory
+// (16-byte aligned destinations; the quad layout then reads it bank-conflict free).  Needs full CTAs (nrows, and rows per
+// coset, multiples of 64) and 16-byte aligned columns; hash_rows_run falls back to the LDG kernel otherwise.
+static constexpr int STAGE_PITCH = 68;
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, u64 *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+               "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "TVM_MBAR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TVM_MBAR_DONE;\n\t"
+      "bra TVM_MBAR_WAIT;\n\t"
+      "TVM_MBAR_DONE:\n\t"
+      "}" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(HASHM_THREADS) tip5_hash_rows_mma_tma_kernel(HashRowsParams p) {
+  __shared__ unsigned char lut[256];
+  __shared__ u64 rc[80];
+  __shared__ __align__(16) u64 stage[2][10][STAGE_PITCH];
+  __shared__ __align__(8) u64 mbar[2];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_tip5_lut[i];
+  for (int i = threadIdx.x; i < 80; i += blockDim.x) rc[i] = c_tip5_rc[i];
+  const int lane = threadIdx.x & 31, l = lane & 3;
+  const MdsFrag f = mds_fragments(lane);
+  constexpr int QUADS = HASHM_THREADS / 4, ROWS = 2 * QUADS;
+  const size_t per = p.nrows >> p.log_r;
+  const size_t m0 = (size_t)blockIdx.x * ROWS, cs0 = m0 / per;
+  const u64 *tile0 = p.table + m0 + cs0 * (p.coset_mem_stride - 1) * per;      // first row of the CTA's tile, column 0
+  const unsigned full = p.ncols / 10, rem = p.ncols - 10 * full, nblk = full + 1;
+  auto issue = [&](unsigned b) {                       // thread 0 only
+    const unsigned cols = b < full ? 10u : rem;
+    if (!cols) return;
+    u64 *bar = &mbar[b & 1];
+    mbar_expect_tx(bar, cols * ROWS * 8);
+    for (unsigned i = 0; i < cols; i++) bulk_g2s(&stage[b & 1][i][0], tile0 + (size_t)(10 * b + i) * p.col_stride, ROWS * 8, bar);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    issue(0);
+    if (nblk > 1) issue(1);
+  }
+  const int ra = threadIdx.x >> 2, rb = ra + QUADS;    // this quad's two rows inside the tile
+  u64 a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  for (unsigned blk = 0; blk < nblk; blk++) {
+    const unsigned cols = blk < full ? 10u : rem;
+    const u64(*st)[STAGE_PITCH] = stage[blk & 1];
+    if (cols) mbar_wait(&mbar[blk & 1], (blk >> 1) & 1);
+    if (blk < full) {
+      a[0] = st[l][ra]; b[0] = st[l][rb];
+      a[1] = st[l + 4][ra]; b[1] = st[l + 4][rb];
+      if (l < 2) { a[2] = st[l + 8][ra]; b[2] = st[l + 8][rb]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const unsigned e = (unsigned)(l + 4 * i);
+        if (e < 10) {
+          u64 va = 0, vb = 0;
+          if (e < rem) { va = st[e][ra]; vb = st[e][rb]; }
+          else if (e == rem) { va = MONT_ONE; vb = MONT_ONE; }
+          a[i] = va; b[i] = vb;
+        }
+      }
+    }
+    __syncthreads();                                   // every lane has taken its words out of this stage
+    if (threadIdx.x == 0 && blk + 2 < nblk) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy overwrite
+      issue(blk + 2);
+    }
+    tip5_perm_quad2_mma(a, b, l, f, lut, rc);
+  }
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    const size_t m = m0 + (size_t)(t ? rb : ra);
+    const size_t coset = m / per, k = m - coset * per;
+    u64 *d = p.digests + (coset + (k << p.log_r)) * 5;
+    const u64 *s = t ? b : a;
+    d[l] = s[0];
+    if (l == 0) d[4] = s[1];
+  }
+}
+
 // Inner tree nodes on the same permutation: a quad computes nodes lo + q and lo + q + count/2... (two nodes per quad).
 __global__ void __launch_bounds__(HASHM_THREADS) merkle_level_mma_kernel(u64 *nodes, size_t lo, size_t count) {
   __shared__ unsigned char lut[256];
@@ -759,7 +865,12 @@ void hash_rows_run(Ctx &c, const u64 *table, size_t col_stride, size_t nrows, un
       !getenv("TVM_TIP5_SMEM_EXCHANGE")) {
     const size_t rows_per_cta = HASHM_THREADS / 2;
     unsigned grid = (unsigned)((nrows + rows_per_cta - 1) / rows_per_cta);
-    tip5_hash_rows_mma_kernel<<<grid, HASHM_THREADS, 0, c.stream>>>(p);
+    static const bool no_tma = getenv("TVM_TIP5_NO_TMA") != nullptr;        // A/B: per-lane LDG instead of bulk-copy staging
+    const size_t per = nrows >> log_r;
+    const bool tma_ok = !no_tma && nrows % rows_per_cta == 0 && per % rows_per_cta == 0 && ((uintptr_t)table % 16) == 0 &&
+                        (col_stride * sizeof(u64)) % 16 == 0;
+    if (tma_ok) tip5_hash_rows_mma_tma_kernel<<<grid, HASHM_THREADS, 0, c.stream>>>(p);
+    else tip5_hash_rows_mma_kernel<<<grid, HASHM_THREADS, 0, c.stream>>>(p);
   } else if (coset_mem_stride != 1) {   // of the A/B variants only quad2 knows about strided cosets
     const size_t rows_per_cta = HASHQ2_THREADS / 2;
     unsigned grid = (unsigned)((nrows + rows_per_cta - 1) / rows_per_cta);

@@ -20,6 +20,7 @@
 //   * interpolation: pass B multiplies by n^-1 offset^k (the coefficients are kept pre-scaled by offset^k).
 //   Both are geometric in k1 for a fixed thread: factor = base * step^k1, two table look-ups per thread and tile.
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 #include "ctx.h"
 #include "launch.h"
@@ -55,14 +56,44 @@ __device__ __forceinline__ u64 powtab_at(const PowTab &t, u64 e) {
 
 static constexpr int TILE_THREADS = 256;
 
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier completion - used to stage the contiguous rows of a pass-B tile
+__device__ __forceinline__ unsigned tile_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tile_mbar_init(u64 *bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n\tfence.mbarrier_init.release.cluster;" ::"r"(tile_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tile_mbar_expect_tx(u64 *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tile_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tile_bulk_g2s(void *dst, const void *src, unsigned bytes, u64 *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tile_smem_addr(dst)), "l"(src),
+               "r"(bytes), "r"(tile_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tile_mbar_wait(u64 *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "TVM_TILE_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TVM_TILE_DONE;\n\t"
+      "bra TVM_TILE_WAIT;\n\t"
+      "TVM_TILE_DONE:\n\t"
+      "}" ::"r"(tile_smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // PRE: coset pre-scale + randomizer fold on the way in; POST: 0 none, 1 twist, 2 scalar * power on the way out (compile-time:
 // the unused variants would otherwise double the unrolled code, ~100 KB of SASS, past the instruction cache)
 // STREAM: second pass - its input is the intermediate that should live in L2 only (last use: ld.global.cs = evict first) and
 // its output is not read again by the LDE (st.global.cs), so that the NEXT column's intermediate finds room in the L2.
-template <int LOGR, bool INV, bool PRE, int POST, bool LOOPED, bool STREAM>
+// BULK: the tile's rows are contiguous in memory (second pass): thread 0 hands the T rows to the TMA engine (one bulk copy of
+// M words per row into the exchange buffer's memory, row pitch M + 2 words: bank-conflict free for the (t, a) read-out), the
+// CTA waits on the mbarrier and fills its registers from shared memory; no lane issues a global load.
+template <int LOGR, bool INV, bool PRE, int POST, bool LOOPED, bool STREAM, bool BULK>
 __global__ void __launch_bounds__(TILE_THREADS, 2) ntt_tile_kernel(TileJob p) {
   constexpr int R = 1 << LOGR, M = R * R, LOGT = 8 - LOGR, T = 1 << LOGT;
-  extern __shared__ u64 smem[];
+  extern __shared__ __align__(16) u64 smem[];
   u64 *tw = smem;            // [M]
   u64 *ex = smem + M;        // [(k2 (R+1) + a) T + t]
   const int tid = threadIdx.x, t = tid & (T - 1), a = tid >> LOGT;
@@ -70,6 +101,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) ntt_tile_kernel(TileJob p) {
   const unsigned y = blockIdx.y;
   const u64 *in = p.in + (size_t)blockIdx.z * p.in_col_stride + (size_t)y * p.in_coset_stride;
   u64 *out = p.out + (size_t)blockIdx.z * p.out_col_stride + (size_t)y * p.out_coset_stride;
+  __shared__ __align__(8) u64 bulk_bar;
+  if (BULK) {
+    if (tid == 0) tile_mbar_init(&bulk_bar);
+    __syncthreads();
+    if (tid == 0) {
+      tile_mbar_expect_tx(&bulk_bar, (unsigned)(T * M * sizeof(u64)));
+      const u64 *src = in + ((size_t)blockIdx.x * T) * p.in_row_stride;
+      for (int r = 0; r < T; r++) tile_bulk_g2s(ex + (size_t)r * (M + 2), src + (size_t)r * p.in_row_stride, (unsigned)(M * sizeof(u64)), &bulk_bar);
+    }
+  }
   for (int i = tid; i < M; i += TILE_THREADS) tw[i] = __ldg(p.tw + i);
 
   // LOOPED: both rounds run through ONE copy of the unrolled R-point DFT (`unroll 1`), which keeps the kernel within the
@@ -81,8 +122,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) ntt_tile_kernel(TileJob p) {
     if (rnd == 0) {
       const size_t off0 = row * p.in_row_stride + (size_t)a * p.in_elem_stride;
       const size_t step = (size_t)R * p.in_elem_stride;
+      if (BULK) {
+        tile_mbar_wait(&bulk_bar, 0);
+        const u64 *st = ex + (size_t)t * (M + 2) + a;
 #pragma unroll
-      for (int b = 0; b < R; b++) v[b] = STREAM ? __ldcs(in + off0 + b * step) : in[off0 + b * step];
+        for (int b = 0; b < R; b++) v[b] = st[b * R];
+      } else {
+#pragma unroll
+        for (int b = 0; b < R; b++) v[b] = STREAM ? __ldcs(in + off0 + b * step) : in[off0 + b * step];
+      }
       if (PRE) {
         if (off0 < p.fold_count) v[0] = fadd(v[0], fmul(__ldg(p.fold_factor + y), in[p.fold_offset + off0]));
         const u64 *S = p.prescale + (size_t)y * M + a;
@@ -182,10 +230,17 @@ static void launch_tile(int logr, dim3 grid, cudaStream_t s, const TileJob &j) {
     kernel<<<grid, TILE_THREADS, smem, s>>>(j);
   };
   static const bool looped = getenv("TVM_NTT_LOOPED_ROUNDS") != nullptr;   // A/B switch (measured 10 % slower at 2^20: spills)
-  if (logr == 5 && looped) go(ntt_tile_kernel<5, INV, PRE, POST, true, STREAM>);
-  else if (logr == 5) go(ntt_tile_kernel<5, INV, PRE, POST, false, STREAM>);
-  else if (logr == 4) go(ntt_tile_kernel<4, INV, PRE, POST, false, STREAM>);
-  else go(ntt_tile_kernel<3, INV, PRE, POST, false, STREAM>);
+  static const bool no_bulk = getenv("TVM_NTT_NO_TMA") != nullptr;         // A/B switch: per-lane loads in the second pass too
+  // contiguous, 16-byte aligned rows of exactly M words (every second pass): staged by the TMA engine
+  const bool bulk = !PRE && !no_bulk && j.in_elem_stride == 1 && j.in_row_stride == (size_t)M && ((uintptr_t)j.in % 16) == 0 &&
+                    (j.in_col_stride * 8) % 16 == 0 && (j.in_coset_stride * 8) % 16 == 0;
+  if (logr == 5 && looped) go(ntt_tile_kernel<5, INV, PRE, POST, true, STREAM, false>);
+  else if (logr == 5 && bulk) go(ntt_tile_kernel<5, INV, false, POST, false, STREAM, true>);
+  else if (logr == 5) go(ntt_tile_kernel<5, INV, PRE, POST, false, STREAM, false>);
+  else if (logr == 4 && bulk) go(ntt_tile_kernel<4, INV, false, POST, false, STREAM, true>);
+  else if (logr == 4) go(ntt_tile_kernel<4, INV, PRE, POST, false, STREAM, false>);
+  else if (bulk) go(ntt_tile_kernel<3, INV, false, POST, false, STREAM, true>);
+  else go(ntt_tile_kernel<3, INV, PRE, POST, false, STREAM, false>);
   TVM_CUDA(cudaGetLastError());
 }
 
