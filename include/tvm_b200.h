@@ -184,6 +184,29 @@ typedef struct tvm_claim {
 int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height,
               const uint64_t *main_trace, const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user,
               const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len);
+/* ---- Stark::prove with the HOST keeping the transcript ("who keeps the sponge"): a Rust host hands callbacks
+ *      into its own `ProofStream` (proof_stream.rs:19-104); the library then only PRODUCES proof items and CONSUMES challenges,
+ *      in exactly the order of Prover::prove (stark.rs:331-719) - Fiat-Shamir, the item list, `Proof` and its BFieldCodec stay on
+ *      the host side.  All words canonical.
+ *        alter_fiat_shamir_state  ProofStream::alter_fiat_shamir_state_with(&claim): called once, first, with the Claim's encoding
+ *        enqueue                  ProofStream::enqueue(item): `variant` = index of the ProofItem variant in declaration order
+ *                                 (proof_item.rs:96-147: 0 MerkleRoot, 1 Log2PaddedHeight, 2 OutOfDomainMainRow, 3 OutOfDomainAuxRow,
+ *                                 4 OutOfDomainQuotientSegments, 5 Polynomial, 6 StirOutOfDomainValues, 7 AuthenticationStructure,
+ *                                 8 MasterMainTableRows, 9 MasterAuxTableRows, 10 QuotientSegmentsElements, 11 FriCodeword,
+ *                                 12 FriResponse, 13 StirResponse), `payload` = the variant's BFieldCodec payload
+ *        sample_scalars           ProofStream::sample_scalars(n) -> n X-field elements ([n][3])
+ *        sample_indices           ProofStream::sample_indices(upper_bound, n)
+ *      Every callback returns 0 on success.  Other arguments as tvm_prove; no proof buffer: the host's stream holds the items. --- */
+typedef struct tvm_transcript {
+  void *user;
+  int (*alter_fiat_shamir_state)(void *user, const uint64_t *words, size_t n);
+  int (*enqueue)(void *user, unsigned variant, const uint64_t *payload, size_t n);
+  int (*sample_scalars)(void *user, size_t n, uint64_t *out);
+  int (*sample_indices)(void *user, unsigned upper_bound, size_t n, unsigned *out);
+} tvm_transcript;
+int tvm_prove_transcript(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height,
+                         const uint64_t *main_trace, const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user,
+                         const uint64_t *quot_rand, const tvm_transcript *transcript);
 /* ---- Stark::prove with the table stages on the device: what Prover::prove does between
  *      MasterMainTable::new/pad and the proof (stark.rs:331-719 together with master_table.rs:975-983, 1006-1075).  The main
  *      trace is uploaded once and stays resident: MasterMainTable::extend (the nine tables' `extend` +

@@ -175,3 +175,45 @@ def test_prove_reports_errors_instead_of_falling_back(backend):
                       lambda ch: (rand_bfes(rng, (91, n1, 3)), rand_bfes(rng, (91, h1, 3))),
                       rand_bfes(rng, (d1["num_quotient_randomizer_coefficients"], 3)), security_level=4, log2_expansion=6, padded_height=16)
     assert e.value.code == -8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ldt,security,padded_height", [("fri", 4, 16), ("stir", 6, 64)])
+def test_host_kept_transcript_yields_the_same_proof(backend, ldt, security, padded_height):
+    """tvm_prove_transcript (the host keeps ProofStream): the library only produces items and consumes challenges through
+    callbacks; a host-side stream built on the oracle's sponge ends up holding exactly the proof tvm_prove returns."""
+    import tvm_b200
+    from oracle import codec
+
+    class HostStream(codec.ProofStream):           # the Rust host's ProofStream, played by the oracle's
+        def __init__(self):
+            super().__init__()
+            self.raw = []
+
+        def enqueue_raw(self, variant, payload):
+            e = [variant] + ([len(payload)] if variant > 4 else []) + list(payload)      # dynamically sized payloads carry their length
+            if variant <= 6:                                                             # proof_item.rs:96-147: in the Fiat-Shamir heuristic
+                self.alter_fiat_shamir_state_with(e)
+            self.raw.append(e)
+
+        def encode(self):
+            body = [len(self.raw)]
+            for e in self.raw:
+                body += [len(e)] + e
+            return [len(body)] + body
+
+    rng = np.random.default_rng(21)
+    st = S.Stark(security, 2, ldt)
+    d = st.derive(padded_height)
+    n, h = d["trace_len"], d["num_trace_randomizers"]
+    main, mrand = rand_bfes(rng, (379, n)), rand_bfes(rng, (379, h))
+    aux, arand = rand_bfes(rng, (91, n, 3)), rand_bfes(rng, (91, h, 3))
+    qrand = rand_bfes(rng, (d["num_quotient_randomizer_coefficients"], 3))
+    claim = ([1, 2, 3, 4, 5], [6], [7])
+    choice = tvm_b200.LDT_STIR if ldt == "stir" else tvm_b200.LDT_FRI
+    want = backend.prove(claim, main, mrand, lambda ch: (aux, arand), qrand, security_level=security, log2_expansion=2,
+                         padded_height=padded_height, ldt_choice=choice)
+    hs = HostStream()
+    backend.prove_transcript(claim, main, mrand, lambda ch: (aux, arand), qrand, hs, security_level=security, log2_expansion=2,
+                             padded_height=padded_height, ldt_choice=choice)
+    assert hs.encode() == [int(v) for v in want]

@@ -34,6 +34,9 @@ int translate_exception(Ctx *c) {
   } catch (const ApiError &e) {
     if (c) c->last_error = e.msg;
     return e.code;
+  } catch (const TranscriptCallbackError &) {
+    if (c) c->last_error = "a transcript callback failed (or returned an index outside its range)";
+    return TVM_ERR_INVALID_ARG;
   } catch (...) {
     if (c) c->last_error = "unknown internal error";
     return TVM_ERR_CUDA;
@@ -483,6 +486,24 @@ int tvm_prove(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, ui
   *proof_len = proof.size();
   if (!proof_out || cap < proof.size()) throw ApiError{TVM_ERR_INVALID_ARG, "proof buffer too small"};
   memcpy(proof_out, proof.data(), proof.size() * 8);
+  TVM_API_END
+}
+
+int tvm_prove_transcript(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height, const uint64_t *main_trace,
+                         const uint64_t *main_rand, tvm_aux_callback aux_cb, void *aux_user, const uint64_t *quot_rand,
+                         const tvm_transcript *transcript) {
+  if (!ctx || !params || !claim || !main_trace || !main_rand || !aux_cb || !quot_rand || !transcript) return TVM_ERR_INVALID_ARG;
+  if (!transcript->alter_fiat_shamir_state || !transcript->enqueue || !transcript->sample_scalars || !transcript->sample_indices)
+    return TVM_ERR_INVALID_ARG;
+  if (params->ldt_choice > 2 || !claim_ok(claim)) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  ClaimView cv{claim->program_digest, claim->version, claim->input, claim->num_input, claim->output, claim->num_output};
+  std::vector<u64> unused;
+  const ExternalTranscript ext{transcript->user, transcript->alter_fiat_shamir_state, transcript->enqueue, transcript->sample_scalars,
+                               transcript->sample_indices};
+  stark_prove(*c__, StarkParams{params->security_level, params->log2_ldt_expansion_factor, params->ldt_choice, params->soundness}, cv, padded_height,
+              (const u64 *)main_trace, (const u64 *)main_rand, (AuxCallback)aux_cb, aux_user, (const u64 *)quot_rand, unused, &ctx->timings, nullptr,
+              &ext);
   TVM_API_END
 }
 

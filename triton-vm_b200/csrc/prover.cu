@@ -195,7 +195,7 @@ void evaluate_cols(Ctx &c, const u64 *d_coef, size_t coef_stride, unsigned fold_
 
 void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t padded_height, const u64 *h_main_trace,
                  const u64 *h_main_rand, AuxCallback aux_cb, void *aux_user, const u64 *h_quot_rand, std::vector<u64> &proof,
-                 ProveTimings *timings, const DeviceTables *dev_tables) {
+                 ProveTimings *timings, const DeviceTables *dev_tables, const ExternalTranscript *ext) {
   StarkDerived d{};
   int rc = stark_derive(sp, padded_height, d);
   if (rc) throw ApiError{rc, "parameter derivation failed"};
@@ -252,6 +252,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
 
   DevMem mem(c);
   ProofStream ps;
+  ps.ext = ext;
   ps.alter_fiat_shamir_state_with(encode_claim(claim.program_digest, claim.version, claim.input, claim.num_input, claim.output,
                                                claim.num_output));
   ps.enqueue(ItemKind::Log2PaddedHeight, {(u64)ilog2(d.padded_height)});
@@ -403,7 +404,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   mark();  // 2: main Merkle
 
   // ---- challenges (stark.rs:374-376, challenges.rs:88-135) -------------------------------------------
-  std::vector<xfe> ch = ps.sponge.sample_scalars(59);
+  std::vector<xfe> ch = ps.sample_scalars(59);
   {
     u64 lut[256];
     for (int i = 0; i < 256; i++) lut[i] = TIP5_LOOKUP_HOST[i];
@@ -459,7 +460,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   mark();  // 5: aux Merkle
 
   // ---- quotient codeword (stark.rs:396-411, master_table.rs:1264-1363) ---------------------------------------
-  xfe w0 = ps.sponge.sample_scalars(1)[0];
+  xfe w0 = ps.sample_scalars(1)[0];
   std::vector<u64> consts(ch_mont);
   {
     xfe acc = xone();
@@ -531,7 +532,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   mem.release(d_qnat);
 
   // ---- out-of-domain rows (stark.rs:450-495) --------------------------------------------------------------------
-  const xfe alpha = ps.sponge.sample_scalars(1)[0];
+  const xfe alpha = ps.sample_scalars(1)[0];
   const u64 omega = root_of_unity_mont(log_n);
   const xfe alpha_next = xmulb(alpha, omega);
   const u64 off_inv = finv(off);
@@ -592,7 +593,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   mark();  // 9: OOD rows
 
   // ---- combination codeword (stark.rs:498-639) ----------------------------------------------------------------------
-  std::vector<xfe> cw3 = ps.sponge.sample_scalars(3);
+  std::vector<xfe> cw3 = ps.sample_scalars(3);
   std::vector<u64> wts;   // [470 main&aux][5 p][5 r] X-field weights
   {
     xfe acc = xone();
@@ -660,7 +661,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     u64 offset = off;
     for (size_t r = 0; r <= d.fri_num_rounds; r++) {
       if (r > 0) {
-        xfe chal = ps.sponge.sample_scalars(1)[0];
+        xfe chal = ps.sample_scalars(1)[0];
         u64 *nxt = mem.words(3 * (len / 2));
         fri_fold_run(c, cur, len, len, offset, chal, nxt, len / 2);
         cur = nxt; len /= 2; offset = fmul(offset, offset);
@@ -702,7 +703,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
       for (int dd = 0; dd < 3; dd++) payload.push_back(from_mont(co[dd * last.len + i]));
     ps.enqueue(ItemKind::Polynomial, payload);
   }
-  a_indices = ps.sponge.sample_indices((uint32_t)N, d.num_collinearity_checks);
+  a_indices = ps.sample_indices((uint32_t)N, d.num_collinearity_checks);
   auto reveal = [&](const Round &rd, const std::vector<uint32_t> &idx) {
     TVM_CUDA(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, c.stream));
     gather_rows_run(c, rd.cw, rd.len, 3, d_idx, (unsigned)idx.size(), 0, -1, d_gather);
@@ -722,7 +723,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     for (size_t i = 0; i < b.size(); i++) b[i] = (uint32_t)(((size_t)a_indices[i] + rounds[r].len / 2) % rounds[r].len);
     reveal(rounds[r], b);
   }
-  ps.sponge.sample_scalars(1);   // fri.rs:764-769
+  ps.sample_scalars(1);   // fri.rs:764-769
   }
   const unsigned nq = (unsigned)a_indices.size();
   mark();  // 11: FRI

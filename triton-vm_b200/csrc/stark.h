@@ -62,7 +62,7 @@ struct DeviceTables {
 
 void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t padded_height, const u64 *h_main_trace,
                  const u64 *h_main_rand, AuxCallback aux_cb, void *aux_user, const u64 *h_quot_rand, std::vector<u64> &proof,
-                 ProveTimings *timings, const DeviceTables *dev_tables = nullptr);
+                 ProveTimings *timings, const DeviceTables *dev_tables = nullptr, const struct ExternalTranscript *ext = nullptr);
 
 // ---- stark_kernels.cu ----
 struct SegmentArgs {

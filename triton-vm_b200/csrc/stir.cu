@@ -279,7 +279,7 @@ std::vector<uint32_t> stir_prove_run(Ctx &c, DevMem &mem, ProofStream &ps, const
   bool have_first = false;
 
   for (int round = 0; round < sd.num_rounds; round++) {
-    const xfe r = ps.sponge.sample_scalars(1)[0];
+    const xfe r = ps.sample_scalars(1)[0];
     const size_t f_len = cur_len / ff, n_len = cur_len / 2;
     const u64 n_off = fmul(fmul(cur_off, cur_off), cur_off);                 // next_round_domain: offset^2 * offset
     const u64 f_off = fmul(fmul(cur_off, cur_off), fmul(cur_off, cur_off));  // domain.pow(4)
@@ -293,7 +293,7 @@ std::vector<uint32_t> stir_prove_run(Ctx &c, DevMem &mem, ProofStream &ps, const
 
     // out-of-domain queries (stir.rs:921-926)
     const size_t num_ood = sd.out_of_domain[round];
-    std::vector<xfe> ood_queries = ps.sponge.sample_scalars(num_ood);
+    std::vector<xfe> ood_queries = ps.sample_scalars(num_ood);
     std::vector<xfe> ood_values(num_ood);
     {
       u64 *d_pw = d_scratch;                  // power vector [3][f_len] (d_scratch is free again)
@@ -312,7 +312,7 @@ std::vector<uint32_t> stir_prove_run(Ctx &c, DevMem &mem, ProofStream &ps, const
     }
 
     // in-domain queries against the previous commitment (stir.rs:928-940)
-    std::vector<uint32_t> queried = ps.sponge.sample_indices((uint32_t)cur_len, sd.in_domain[round]);
+    std::vector<uint32_t> queried = ps.sample_indices((uint32_t)cur_len, sd.in_domain[round]);
     std::vector<uint32_t> folded_idx = dedup_folded(queried, f_len);
     respond(commitment, folded_idx);
 
@@ -362,7 +362,7 @@ std::vector<uint32_t> stir_prove_run(Ctx &c, DevMem &mem, ProofStream &ps, const
       TVM_CUDA(cudaMemcpyAsync(d_small, host.data(), host.size() * 8, cudaMemcpyHostToDevice, c.stream));
       TVM_CUDA(cudaStreamSynchronize(c.stream));
     }
-    const xfe rho = ps.sponge.sample_scalars(1)[0];       // degree-correction randomness
+    const xfe rho = ps.sample_scalars(1)[0];       // degree-correction randomness
 
     // next round's polynomial (stir.rs:958-972)
     {
@@ -391,7 +391,7 @@ std::vector<uint32_t> stir_prove_run(Ctx &c, DevMem &mem, ProofStream &ps, const
 
   // ---- final round (stir.rs:975-991) ----
   {
-    const xfe r = ps.sponge.sample_scalars(1)[0];
+    const xfe r = ps.sample_scalars(1)[0];
     const size_t f_len = cur_len / ff;
     u64 *d_final = mem.words(3 * f_len);
     stir_fold_kernel<<<st_grid(f_len), ST_THREADS, 0, c.stream>>>(d_poly, cur_len, r, xmul(r, r), xmul(xmul(r, r), r), d_final, f_len);
@@ -405,7 +405,7 @@ std::vector<uint32_t> stir_prove_run(Ctx &c, DevMem &mem, ProofStream &ps, const
     for (size_t i = 0; i < deg_plus_1; i++)
       for (int dd = 0; dd < 3; dd++) payload.push_back(from_mont(co[dd * f_len + i]));
     ps.enqueue(ItemKind::Polynomial, payload);
-    std::vector<uint32_t> queried = ps.sponge.sample_indices((uint32_t)cur_len, sd.final_num_in_domain_queries);
+    std::vector<uint32_t> queried = ps.sample_indices((uint32_t)cur_len, sd.final_num_in_domain_queries);
     respond(commitment, dedup_folded(queried, f_len));
     if (!have_first) first_round_indices = queried;
     mem.release(d_final);

@@ -78,12 +78,51 @@ struct Sponge {                       // Tip5::init(): variable-length domain, a
   }
 };
 
+// A host that keeps `ProofStream` itself ("who keeps the sponge") hands these callbacks to tvm_prove_transcript: the
+// library then only PRODUCES proof items and CONSUMES challenges - Fiat-Shamir, the item list and the proof encoding stay with
+// the host's own ProofStream / BFieldCodec (proof_stream.rs:40-103).  All words canonical.
+struct ExternalTranscript {
+  void *user;
+  int (*alter_fiat_shamir_state)(void *user, const u64 *words, size_t n);            // ProofStream::alter_fiat_shamir_state_with
+  int (*enqueue)(void *user, unsigned variant, const u64 *payload, size_t n);         // ProofStream::enqueue(item): variant index, BFieldCodec payload
+  int (*sample_scalars)(void *user, size_t n, u64 *out);                              // [n][3]
+  int (*sample_indices)(void *user, unsigned upper_bound, size_t n, unsigned *out);
+};
+struct TranscriptCallbackError {};
+
 struct ProofStream {
   Sponge sponge;
   std::vector<std::vector<u64>> items;   // full item encodings [variant, (len,) payload...]
+  const ExternalTranscript *ext = nullptr;
 
-  void alter_fiat_shamir_state_with(const std::vector<u64> &encoding) { sponge.pad_and_absorb_all(encoding); }
+  std::vector<xfe> sample_scalars(size_t n) {
+    if (!ext) return sponge.sample_scalars(n);
+    std::vector<u64> w(3 * n);
+    if (ext->sample_scalars(ext->user, n, w.data())) throw TranscriptCallbackError{};
+    std::vector<xfe> out(n);
+    for (size_t i = 0; i < n; i++) out[i] = xmake(to_mont(w[3 * i] % P), to_mont(w[3 * i + 1] % P), to_mont(w[3 * i + 2] % P));
+    return out;
+  }
+  std::vector<uint32_t> sample_indices(uint32_t upper_bound, size_t n) {
+    if (!ext) return sponge.sample_indices(upper_bound, n);
+    std::vector<uint32_t> out(n);
+    if (ext->sample_indices(ext->user, upper_bound, n, out.data())) throw TranscriptCallbackError{};
+    for (uint32_t v : out)
+      if (v >= upper_bound) throw TranscriptCallbackError{};
+    return out;
+  }
+  void alter_fiat_shamir_state_with(const std::vector<u64> &encoding) {
+    if (ext) {
+      if (ext->alter_fiat_shamir_state(ext->user, encoding.data(), encoding.size())) throw TranscriptCallbackError{};
+      return;
+    }
+    sponge.pad_and_absorb_all(encoding);
+  }
   void enqueue(ItemKind k, const std::vector<u64> &payload) {
+    if (ext) {
+      if (ext->enqueue(ext->user, (unsigned)(int)k, payload.data(), payload.size())) throw TranscriptCallbackError{};
+      return;
+    }
     std::vector<u64> e;
     e.reserve(payload.size() + 2);
     e.push_back((u64)(int)k);

@@ -111,6 +111,8 @@ _SIGNATURES = {
                                  AUX_CALLBACK, _vp, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
     "tvm_prove_tables": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, _u64p, ctypes.c_int,
                                         _u64p, _u64p, _u64p, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
+    "tvm_prove_transcript": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, _u64p, _u64p,
+                                            AUX_CALLBACK, _vp, _u64p, ctypes.c_void_p]),
     "tvm_stir_prove": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u64p, _u64p,
                                       ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_size_t)]),
     "tvm_stir_verify": (ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u64p, ctypes.c_size_t,
@@ -415,6 +417,73 @@ class Backend:
             raise err[0]
         self._chk(rc)
         return buf[:cap.value].copy()
+
+    def prove_transcript(self, claim, main_trace, main_rand, aux_provider, quot_rand, transcript, security_level=160, log2_expansion=2,
+                         padded_height=None, ldt_choice=LDT_AUTO, conjectured=False):
+        """tvm_prove_transcript: Stark::prove with the HOST keeping the proof stream.  `transcript` is any object with
+        alter_fiat_shamir_state_with(words), enqueue_raw(variant, payload_words), sample_scalars(n) -> n triples,
+        sample_indices(upper_bound, n) -> n ints (e.g. a subclass of oracle.codec.ProofStream in the tests)."""
+        mt, mtp, mt_shape = _u64_arg(main_trace)
+        mr, mrp, mr_shape = _u64_arg(main_rand)
+        qr, qrp = _np_u64(quot_rand)
+        n = mt_shape[1]
+        ph = padded_height or n
+        dom = derive_domains(security_level, log2_expansion, ph, ldt_choice, conjectured)
+        h = dom["num_trace_randomizers"]
+        digest, inp, out = claim[0], claim[1], claim[2]
+        version = claim[3] if len(claim) > 3 else 6
+        ia, iap = _np_u64(np.array(list(inp), dtype=np.uint64))
+        oa, oap = _np_u64(np.array(list(out), dtype=np.uint64))
+        cs = ClaimStruct((ctypes.c_uint64 * 5)(*[int(v) for v in digest]), version, iap, ia.size, oap, oa.size)
+        err, keep = [], []
+
+        def cb(_user, ch_p, trace_pp, rand_pp):
+            try:
+                t, r = aux_provider(np.ctypeslib.as_array(ch_p, shape=(63, 3)).copy())
+                t, tp, ts = _u64_arg(t)
+                r, rp, rs = _u64_arg(r)
+                assert int(np.prod(ts)) == 91 * n * 3 and int(np.prod(rs)) == 91 * h * 3, (ts, rs)
+                keep.extend([t, r])
+                trace_pp[0] = tp
+                rand_pp[0] = rp
+                return 0
+            except Exception as e:  # noqa: BLE001
+                err.append(e)
+                return 1
+
+        def guard(fn):
+            def wrapped(*a):
+                try:
+                    fn(*a)
+                    return 0
+                except Exception as e:  # noqa: BLE001 - must not propagate through the C frame
+                    err.append(e)
+                    return 1
+            return wrapped
+
+        F_ABS = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, _u64p, ctypes.c_size_t)
+        F_ENQ = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint, _u64p, ctypes.c_size_t)
+        F_SCA = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, _u64p)
+        F_IDX = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint))
+
+        def f_abs(_u, w, k): transcript.alter_fiat_shamir_state_with([int(w[i]) for i in range(k)])
+        def f_enq(_u, variant, w, k): transcript.enqueue_raw(int(variant), [int(w[i]) for i in range(k)])
+        def f_sca(_u, k, out_p):
+            for i, x in enumerate(transcript.sample_scalars(k)):
+                out_p[3 * i], out_p[3 * i + 1], out_p[3 * i + 2] = int(x[0]), int(x[1]), int(x[2])
+        def f_idx(_u, ub, k, out_p):
+            for i, v in enumerate(transcript.sample_indices(int(ub), k)):
+                out_p[i] = int(v)
+
+        class T(ctypes.Structure):
+            _fields_ = [("user", ctypes.c_void_p), ("abs", F_ABS), ("enq", F_ENQ), ("sca", F_SCA), ("idx", F_IDX)]
+        ts_ = T(None, F_ABS(guard(f_abs)), F_ENQ(guard(f_enq)), F_SCA(guard(f_sca)), F_IDX(guard(f_idx)))
+        p = Params(security_level, log2_expansion, ldt_choice, int(conjectured))
+        rc = self._l.tvm_prove_transcript(self._h, ctypes.byref(p), ctypes.byref(cs), ph, mtp, mrp, AUX_CALLBACK(cb), None, qrp,
+                                          ctypes.cast(ctypes.byref(ts_), ctypes.c_void_p))
+        if err:
+            raise err[0]
+        self._chk(rc)
 
     def prove_tables(self, claim, main_table, main_rand, aux_rand, randomizer_column, quot_rand, security_level=160, log2_expansion=2,
                      padded_height=None, ldt_choice=LDT_AUTO, conjectured=False, fill_derived_main_columns=True):
