@@ -374,7 +374,26 @@ def run_gpu_workload(args):
         b.set_low_memory(args.low_memory)
     dv = [t.to(dev) for t in (main_t, main_rand, aux_rand, col90)]
 
+    aet_host = aet_dev = None
+    if args.from_aet:                              # tvm_prove_aet: the witness itself crosses the boundary, no table on the host
+        import glob
+        aet_host, aet_dev = {}, {}
+        for f in sorted(glob.glob(os.path.join(d, "aet_*.u*"))):
+            name, ext = os.path.basename(f)[4:].rsplit(".", 1)
+            a = np.fromfile(f, dtype="<u4" if ext == "u32" else "<u8")
+            if name in ("program", "instruction_multiplicities", "lookup_table_lookup_multiplicities"):
+                aet_host[name] = aet_dev[name] = a                   # small; the multiplicities are widened on the host
+                continue
+            width = tvm_b200._AET_WIDTHS[name]
+            t = torch.empty((a.size // width, width), dtype=torch.int64, pin_memory=True)
+            t.numpy().view(np.uint64)[...] = a.reshape(-1, width)
+            aet_host[name], aet_dev[name] = t, t.to(dev)
+        assert len(aet_host) == 11, "no AET in the workload directory: tools/make_workload.py --aet"
+
     def step(tabs):
+        if args.from_aet:
+            return b.prove_aet(claim, aet_host if tabs[0] is main_t else aet_dev, tabs[1], tabs[2], tabs[3], quot_rand, security, log2_exp,
+                               padded_height, ldtc)
         return b.prove_tables(claim, tabs[0], tabs[1], tabs[2], tabs[3], quot_rand, security, log2_exp, padded_height, ldtc)
 
     def timed(tabs):
@@ -406,10 +425,13 @@ def run_gpu_workload(args):
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "real execution trace of the reference's benchmark program (tables from tools/make_workload.py, outside the timed region)",
         "config": {"workload": f"{os.path.basename(os.path.normpath(d))}: " + workload_string(log2h, ldt_name, ldtc != 0, h),
-                   "entry_point": "tvm_prove_tables: 149 table columns in, degree-lowering columns + MasterMainTable::extend on the device",
+                   "entry_point": ("tvm_prove_aet: the AlgebraicExecutionTrace in; MasterMainTable::new + pad, degree-lowering columns + "
+                                   "MasterMainTable::extend on the device" if args.from_aet else
+                                   "tvm_prove_tables: 149 table columns in, degree-lowering columns + MasterMainTable::extend on the device"),
                    "parallelism": "single GPU", "lde_tables": "just-in-time (low-memory mode)" if b.last_prove_low_memory else "cached in HBM"},
         "e2e": {"value": e2e_ms, "unit": "ms",
-                "h2d_bytes_per_step": int(8 * (149 * n + NM * h + NA * h * 3 + n * 3 + nqr * 3)), "d2h_bytes_per_step": int(proof.nbytes)},
+                "h2d_bytes_per_step": int(8 * ((sum(int(np.prod(v.shape)) for v in aet_host.values()) if args.from_aet else 149 * n)
+                                               + NM * h + NA * h * 3 + n * 3 + nqr * 3)), "d2h_bytes_per_step": int(proof.nbytes)},
         "gpu_launches": int(launches), "stages_ms": stages, "e2e_stages_ms": e2e_stages, "clocks": clocks,
         "proof_check": {"verifier": "tvm_verify (Stark::verify) INCLUDING the out-of-domain AIR identity", "accepted": bool(accepted),
                         "reason": reason, "ms": round(verify_ms, 1), "proof_words": int(proof.size)},
@@ -501,6 +523,8 @@ def main():
     ap.add_argument("--workload-dir", default=None,
                     help="directory written by tools/make_workload.py (e.g. spin_20): prove the reference's own benchmark program "
                          "from its 149 table columns with tvm_prove_tables (all table stages on the device) instead of synthetic tables")
+    ap.add_argument("--from-aet", action="store_true",
+                    help="with --workload-dir: tvm_prove_aet on the AET arrays written by tools/make_workload.py --aet (table fill on the device)")
     ap.add_argument("--ldt", default="auto", choices=["auto", "fri", "stir"],
                     help="low-degree test; auto = the reference's own choice (STIR from padded height 2^16 on)")
     args = ap.parse_args()

@@ -222,6 +222,45 @@ int tvm_prove_transcript(tvm_ctx *ctx, const tvm_params *params, const tvm_claim
 int tvm_prove_tables(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height,
                      const uint64_t *main_table, int fill_derived_main_columns, const uint64_t *main_rand, const uint64_t *aux_rand,
                      const uint64_t *randomizer_column, const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len);
+/* ---- The witness at the boundary: AlgebraicExecutionTrace (aet.rs:41-91) -> MasterMainTable::new + pad + the proof
+ *      (SURVEY.md 8(f).4).  Every array is what the reference's AET holds, row-major, canonical words:
+ *        program                    Program::to_bwords()
+ *        instruction_multiplicities [program_len]                          (aet.rs:52)
+ *        processor_trace            [processor_rows][39]                   (aet.rs:55; ProcessorMainColumn order)
+ *        op_stack_underflow_trace   [op_stack_rows][4]                     (aet.rs:57; clk, IB1 shrink, stack pointer, element)
+ *        ram_trace                  [ram_rows][7]                          (aet.rs:59; columns 4..6 unused, as RamTableCall::to_table_row leaves them)
+ *        program_hash_trace / sponge_trace / hash_trace  [rows][67]        (aet.rs:67-76; HashMainColumn order, CI set, Mode unset)
+ *        u32_entries                [u32_count][4]: opcode, left operand, right operand, multiplicity, in IndexMap order (aet.rs:85)
+ *        cascade_table_lookup_multiplicities [cascade_count][2]: 16-bit limb, multiplicity, in IndexMap order (aet.rs:90)
+ *        lookup_table_lookup_multiplicities  [256]                         (aet.rs:93) --- */
+typedef struct tvm_aet {
+  const uint64_t *program; uint64_t program_len;
+  const uint32_t *instruction_multiplicities;
+  const uint64_t *processor_trace; uint64_t processor_rows;
+  const uint64_t *op_stack_underflow_trace; uint64_t op_stack_rows;
+  const uint64_t *ram_trace; uint64_t ram_rows;
+  const uint64_t *program_hash_trace; uint64_t program_hash_rows;
+  const uint64_t *sponge_trace; uint64_t sponge_rows;
+  const uint64_t *hash_trace; uint64_t hash_rows;
+  const uint64_t *u32_entries; uint64_t u32_count;
+  const uint64_t *cascade_table_lookup_multiplicities; uint64_t cascade_count;
+  const uint64_t *lookup_table_lookup_multiplicities;
+} tvm_aet;
+/*      tvm_main_table_from_aet: MasterMainTable::new + pad (master_table.rs:881-974) on the device: the nine tables' `fill`
+ *      (sorting the memory-like tables, clock-jump-difference multiplicities, the RAM table's Bezout coefficient
+ *      polynomials ram.rs:162-214, the u32 sections u32.rs:193-290), their `pad`, and the degree-lowering columns.
+ *        num_rows       rows of the table (a power of two >= every table's length; the trace-domain length)
+ *        main_table_out [379][num_rows] canonical, column-major (host memory)
+ *        table_lengths_out (optional) [9]: program, processor, op stack, ram, jump stack, hash, cascade, lookup, u32
+ *      tvm_prove_aet: the same fill as the first stage of tvm_prove_tables; nothing but the AET and the randomness is
+ *      uploaded, the table never exists on the host.  Other arguments as tvm_prove_tables. --- */
+int tvm_main_table_from_aet(tvm_ctx *ctx, const tvm_aet *aet, uint64_t num_rows, uint64_t *main_table_out, uint64_t *table_lengths_out);
+int tvm_prove_aet(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height, const tvm_aet *aet,
+                  const uint64_t *main_rand, const uint64_t *aux_rand, const uint64_t *randomizer_column, const uint64_t *quot_rand,
+                  uint64_t *proof_out, size_t *proof_len);
+/* Bezout coefficient polynomials of rp = prod (x - roots[i]) and its formal derivative (ram.rs:162-214), kernel-level entry
+ * point: `roots` m distinct canonical elements; a_out, b_out [m] canonical coefficients, lowest first. */
+int tvm_bezout_coefficients(tvm_ctx *ctx, const uint64_t *roots, uint64_t m, uint64_t *a_out, uint64_t *b_out);
 /* ---- STIR as a stand-alone low-degree test: Stir::prove / Stir::verify (low_degree_test/stir.rs:885-993, 995-1108) of the sealed
  *      `LowDegreeTest` trait (mod.rs:48-100) for ARBITRARY StirParameters (stir.rs:395-435; folding factor 2^2 as Stark::ldt fixes
  *      it, stark.rs:2023).  Used by the restated property tests of the reference (stir.rs:1813-2010) and by hosts that keep

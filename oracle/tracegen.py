@@ -498,6 +498,54 @@ def table_heights(words, ex):
                 cascade=len(_lookup_multiplicities(traces)[0]), lookup=256, u32=u32)
 
 
+def _hash_table_row(ci, rnd, st):
+    """hash.rs:60-70 `trace_row_to_table_row` (+ CI, as aet.rs:203-205, 264-297 set it): one row of the AET's hash traces"""
+    c = MAIN["hash"]
+    names = c.names
+    row = [0] * c.COUNT
+    row[names.index("CI")], row[names.index("RoundNumber")] = ci, rnd
+    for e in range(4):
+        lb = limbs16(st[e])
+        for k, part in enumerate(("Lowest", "MidLow", "MidHigh", "Highest")):
+            row[names.index(f"State{e}{part}LkIn")] = lb[k]
+            row[names.index(f"State{e}{part}LkOut")] = lookup16(lb[k])
+        row[names.index(f"State{e}Inv")] = inv_or_zero((1 << 32) - 1 - ((lb[3] << 16) + lb[2]))
+    for e in range(4, 16):
+        row[names.index(f"State{e}")] = st[e]
+    for k in range(16):
+        row[names.index(f"Constant{k}")] = tip5.ROUND_CONSTANTS[16 * rnd + k] if rnd < 5 else 0
+    return row
+
+
+def aet_arrays(words, ex):
+    """The arrays an AlgebraicExecutionTrace holds (aet.rs:41-91), in the reference's layout: what crosses the C ABI as
+    `tvm_aet` (include/tvm_b200.h).  `ex` = execute(words, ...)."""
+    program = list(words)
+    h_op = OPCODES["hash"]
+    _, program_hash_rows, program_traces, _ = _program_hash(program)
+    cascade_mult, lookup_mult = _lookup_multiplicities(program_traces + ex.lookup_traces)
+    proc = np.zeros((len(ex.rows), 39), dtype=np.uint64)
+    for i, r in enumerate(ex.rows):
+        ci = r["ci"]
+        proc[i] = ([r["clk"], 0, r["ip"], ci, r["nia"]] + [(ci >> b) & 1 for b in range(7)] + [r["jsp"], r["jso"], r["jsd"]]
+                   + list(r["st"]) + [r["osp"]] + list(r["hv"]) + [0])
+
+    def arr(rows, width):
+        return np.array(rows, dtype=np.uint64).reshape(-1, width)
+    return dict(
+        program=np.array(program, dtype=np.uint64),
+        instruction_multiplicities=np.array(ex.multiplicities, dtype=np.uint32),
+        processor_trace=proc,
+        op_stack_underflow_trace=arr([[clk, shrink, ptr, payload] for clk, shrink, ptr, payload in ex.op_stack_entries], 4),
+        ram_trace=arr([[clk, 0 if is_write else 1, ptr, val, 0, 0, 0] for clk, is_write, ptr, val in ex.ram_calls], 7),
+        program_hash_trace=arr([_hash_table_row(h_op, rnd, st) for rnd, st in program_hash_rows], 67),
+        sponge_trace=arr([_hash_table_row(ci, rnd, st) for ci, rnd, st in ex.sponge_rows], 67),
+        hash_trace=arr([_hash_table_row(h_op, rnd, st) for trace in ex.hash_traces for rnd, st in enumerate(trace)], 67),
+        u32_entries=arr([[OPCODES[i], lhs, rhs, mult] for (i, lhs, rhs), mult in ex.u32_entries.items()], 4),
+        cascade_table_lookup_multiplicities=arr([[limb, m] for limb, m in cascade_mult.items()], 2),
+        lookup_table_lookup_multiplicities=np.array(lookup_mult, dtype=np.uint64))
+
+
 # ---- main table -------------------------------------------------------------------------------------
 def main_table(words, public_input, n, secret_input=(), initial_ram=None, secret_digests=(), evaluate_substitutions=False):
     """[379][n] canonical ints: MasterMainTable::new + pad (master_table.rs:881-1004).

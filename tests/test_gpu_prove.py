@@ -113,11 +113,15 @@ def test_stir_with_other_expansion_factors(backend, log2_exp):
         assert [int(v) for v in got] == want, mode
 
 
-@pytest.mark.parametrize("ldt", ["fri", "stir"])
+@pytest.mark.parametrize("ldt", ["fri", "stir", "fri_tiles"])
 def test_low_memory_mode_produces_the_same_proof(backend, ldt):
-    """Just-in-time LDE (tables never stored, every coset re-evaluated for hashing, AIR and openings) vs cached tables."""
+    """Just-in-time LDE (tables never stored, every coset re-evaluated for hashing, AIR and openings) vs cached tables.
+    "fri_tiles": a trace domain of 2^12, where the square-tile NTT (ntt_tile.cu) evaluates one coset per call."""
     import tvm_b200
-    if ldt == "stir":
+    if ldt == "fri_tiles":
+        st, d, claim, main, mrand, aux_provider, qrand = synthetic_instance(4, 2, 4096, 23)
+        kw = dict(security_level=4, log2_expansion=2, padded_height=4096)
+    elif ldt == "stir":
         st, d, claim, main, mrand, aux_provider, qrand = synthetic_stir_instance(6, 256, 21)
         kw = dict(security_level=6, log2_expansion=2, padded_height=256, ldt_choice=tvm_b200.LDT_STIR)
     else:

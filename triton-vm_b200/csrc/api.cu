@@ -7,6 +7,7 @@
 #include "stark.h"
 #include <cstring>
 #include <new>
+#include <stdexcept>
 
 using namespace tvm;
 
@@ -522,6 +523,64 @@ int tvm_prove_tables(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *cl
   *proof_len = proof.size();
   if (!proof_out || cap < proof.size()) throw ApiError{TVM_ERR_INVALID_ARG, "proof buffer too small"};
   memcpy(proof_out, proof.data(), proof.size() * 8);
+  TVM_API_END
+}
+
+int tvm_main_table_from_aet(tvm_ctx *ctx, const tvm_aet *aet, uint64_t num_rows, uint64_t *main_table_out, uint64_t *table_lengths_out) {
+  if (!ctx || !aet || !main_table_out) return TVM_ERR_INVALID_ARG;
+  if (num_rows < 256 || (num_rows & (num_rows - 1)) || num_rows > ((uint64_t)1 << 26)) return TVM_ERR_DOMAIN;
+  TVM_API_BEGIN(ctx)
+  Ctx &c = *c__;
+  const size_t n = (size_t)num_rows, NM = TVM_NUM_MAIN_COLUMNS, NB = TVM_NUM_MAIN_TABLE_COLUMNS;
+  DevMem mem(c);
+  u64 *d_main = mem.words(NM * n);
+  main_fill_run(c, mem, *aet, n, d_main, table_lengths_out);
+  to_mont_run(c, d_main, NB * n);
+  main_derived_run(c, d_main, n);
+  from_mont_run(c, d_main, NM * n);
+  TVM_CUDA(cudaMemcpyAsync(main_table_out, d_main, NM * n * 8, cudaMemcpyDefault, c.stream));
+  TVM_CUDA(cudaStreamSynchronize(c.stream));
+  TVM_API_END
+}
+
+int tvm_prove_aet(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height, const tvm_aet *aet,
+                  const uint64_t *main_rand, const uint64_t *aux_rand, const uint64_t *randomizer_column, const uint64_t *quot_rand,
+                  uint64_t *proof_out, size_t *proof_len) {
+  if (!ctx || !params || !claim || !aet || !main_rand || !aux_rand || !quot_rand || !proof_len) return TVM_ERR_INVALID_ARG;
+  if (params->ldt_choice > 2 || !claim_ok(claim)) return TVM_ERR_INVALID_ARG;
+  TVM_API_BEGIN(ctx)
+  ClaimView cv{claim->program_digest, claim->version, claim->input, claim->num_input, claim->output, claim->num_output};
+  std::vector<u64> proof;
+  DeviceTables dt{(const u64 *)aux_rand, (const u64 *)randomizer_column, true, aet};
+  stark_prove(*c__, StarkParams{params->security_level, params->log2_ldt_expansion_factor, params->ldt_choice, params->soundness}, cv, padded_height,
+              nullptr, (const u64 *)main_rand, nullptr, nullptr, (const u64 *)quot_rand, proof, &ctx->timings, &dt);
+  size_t cap = *proof_len;
+  *proof_len = proof.size();
+  if (!proof_out || cap < proof.size()) throw ApiError{TVM_ERR_INVALID_ARG, "proof buffer too small"};
+  memcpy(proof_out, proof.data(), proof.size() * 8);
+  TVM_API_END
+}
+
+int tvm_bezout_coefficients(tvm_ctx *ctx, const uint64_t *roots, uint64_t m, uint64_t *a_out, uint64_t *b_out) {
+  if (!ctx || (m && (!roots || !a_out || !b_out))) return TVM_ERR_INVALID_ARG;
+  if (m > ((uint64_t)1 << 24)) return TVM_ERR_DOMAIN;
+  if (!m) return TVM_OK;
+  TVM_API_BEGIN(ctx)
+  Ctx &c = *c__;
+  DevMem mem(c);
+  u64 *d_r = mem.words(m), *d_a = mem.words(m), *d_b = mem.words(m);
+  TVM_CUDA(cudaMemcpyAsync(d_r, roots, m * 8, cudaMemcpyDefault, c.stream));
+  to_mont_run(c, d_r, m);
+  try {
+    bezout_run(c, mem, d_r, (size_t)m, d_a, d_b);
+  } catch (const std::runtime_error &e) {
+    throw ApiError{TVM_ERR_UNSUPPORTED, e.what()};
+  }
+  from_mont_run(c, d_a, m);
+  from_mont_run(c, d_b, m);
+  TVM_CUDA(cudaMemcpyAsync(a_out, d_a, m * 8, cudaMemcpyDefault, c.stream));
+  TVM_CUDA(cudaMemcpyAsync(b_out, d_b, m * 8, cudaMemcpyDefault, c.stream));
+  TVM_CUDA(cudaStreamSynchronize(c.stream));
   TVM_API_END
 }
 

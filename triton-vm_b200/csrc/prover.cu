@@ -391,7 +391,17 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     ExtendOpts o;
     if (dev_tables) {
       o.keep_in = &d_main_trace;
-      if (dev_tables->fill_derived_main) {
+      if (dev_tables->aet) {              // MasterMainTable::new + pad on the device, then the degree-lowering columns
+        o.upload_cols = 0;
+        o.after_upload = [&](u64 *d_in) {
+          {
+            DevMem fill_mem(c);             // the AET's device copy and the fill's scratch go back to the pool right after
+            main_fill_run(c, fill_mem, *dev_tables->aet, n, d_in, nullptr);
+          }
+          to_mont_run(c, d_in, (size_t)TVM_NUM_MAIN_TABLE_COLUMNS * n);
+          main_derived_run(c, d_in, n);
+        };
+      } else if (dev_tables->fill_derived_main) {
         o.upload_cols = TVM_NUM_MAIN_TABLE_COLUMNS;
         o.after_upload = [&](u64 *d_in) { main_derived_run(c, d_in, n); };
       }
@@ -789,7 +799,7 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
   proof = ps.encode();
   if (timings) {
     TVM_CUDA(cudaStreamSynchronize(c.stream));
-    const char *names[] = {"setup", dev_tables && dev_tables->fill_derived_main ? "upload+derived columns+LDE(main)" : "upload+LDE(main)",
+    const char *names[] = {"setup", dev_tables && dev_tables->aet ? "table fill+derived columns+LDE(main)" : dev_tables && dev_tables->fill_derived_main ? "upload+derived columns+LDE(main)" : "upload+LDE(main)",
                            "Merkle(main)", dev_tables ? "extend(device)" : "extend(caller)", dev_tables ? "LDE(aux)" : "upload+LDE(aux)",
                            "Merkle(aux)", "quotient(AIR)", "quotient LDE", "Merkle(quot)", "OOD rows", "linear combination+DEEP",
                            "low-degree test", "open"};

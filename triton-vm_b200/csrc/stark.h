@@ -58,11 +58,16 @@ struct DeviceTables {
   const u64 *aux_rand;            // [91][h][3] canonical (host or device)
   const u64 *randomizer_column;   // [n][3] canonical: aux column 90 (master_table.rs:1019-1025); nullptr = zeros
   bool fill_derived_main;         // columns 149..378 of the main trace are computed, not read
+  const tvm_aet *aet = nullptr;   // the nine tables' columns come from the AET (main_fill.cu), no main trace is read at all
 };
 
 void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t padded_height, const u64 *h_main_trace,
                  const u64 *h_main_rand, AuxCallback aux_cb, void *aux_user, const u64 *h_quot_rand, std::vector<u64> &proof,
                  ProveTimings *timings, const DeviceTables *dev_tables = nullptr, const struct ExternalTranscript *ext = nullptr);
+
+// ---- main_fill.cu: MasterMainTable::new + pad from the AET; d_table [>= 149][n] receives CANONICAL columns ----
+void main_fill_run(Ctx &c, struct DevMem &mem, const tvm_aet &aet, size_t n, u64 *d_table, uint64_t *lengths9);
+void bezout_run(Ctx &c, struct DevMem &mem, const u64 *d_roots_mont, size_t m, u64 *d_a, u64 *d_b);
 
 // ---- stark_kernels.cu ----
 struct SegmentArgs {

@@ -65,6 +65,56 @@ class ClaimStruct(ctypes.Structure):
                 ("num_input", ctypes.c_size_t), ("output", _u64p), ("num_output", ctypes.c_size_t)]
 
 
+class AetStruct(ctypes.Structure):   # tvm_aet (aet.rs:41-91)
+    _fields_ = [("program", _u64p), ("program_len", ctypes.c_uint64),
+                ("instruction_multiplicities", ctypes.POINTER(ctypes.c_uint32)),
+                ("processor_trace", _u64p), ("processor_rows", ctypes.c_uint64),
+                ("op_stack_underflow_trace", _u64p), ("op_stack_rows", ctypes.c_uint64),
+                ("ram_trace", _u64p), ("ram_rows", ctypes.c_uint64),
+                ("program_hash_trace", _u64p), ("program_hash_rows", ctypes.c_uint64),
+                ("sponge_trace", _u64p), ("sponge_rows", ctypes.c_uint64),
+                ("hash_trace", _u64p), ("hash_rows", ctypes.c_uint64),
+                ("u32_entries", _u64p), ("u32_count", ctypes.c_uint64),
+                ("cascade_table_lookup_multiplicities", _u64p), ("cascade_count", ctypes.c_uint64),
+                ("lookup_table_lookup_multiplicities", _u64p)]
+
+
+_AET_WIDTHS = dict(processor_trace=39, op_stack_underflow_trace=4, ram_trace=7, program_hash_trace=67, sponge_trace=67, hash_trace=67,
+                   u32_entries=4, cascade_table_lookup_multiplicities=2)
+_AET_COUNTS = dict(processor_trace="processor_rows", op_stack_underflow_trace="op_stack_rows", ram_trace="ram_rows",
+                   program_hash_trace="program_hash_rows", sponge_trace="sponge_rows", hash_trace="hash_rows", u32_entries="u32_count",
+                   cascade_table_lookup_multiplicities="cascade_count")
+
+
+def aet_struct(arrays):
+    """dict of numpy arrays named like the fields of tvm_aet -> (AetStruct, keep-alive list)"""
+    keep = []
+    s = AetStruct()
+    prog = np.ascontiguousarray(arrays["program"], dtype=np.uint64)
+    mult = np.ascontiguousarray(arrays["instruction_multiplicities"], dtype=np.uint32)
+    assert prog.ndim == 1 and mult.shape == prog.shape
+    keep += [prog, mult]
+    s.program, s.program_len = prog.ctypes.data_as(_u64p), prog.size
+    s.instruction_multiplicities = mult.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+    for name, width in _AET_WIDTHS.items():
+        x = arrays[name]
+        if hasattr(x, "data_ptr"):                      # contiguous torch tensor (pinned host or CUDA): [rows, width] 8-byte words
+            assert x.is_contiguous() and x.element_size() == 8 and (x.numel() == 0 or x.shape[-1] == width)
+            keep.append(x)
+            setattr(s, name, ctypes.cast(x.data_ptr(), _u64p))
+            setattr(s, _AET_COUNTS[name], x.numel() // width)
+            continue
+        a = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, width)
+        keep.append(a)
+        setattr(s, name, a.ctypes.data_as(_u64p))
+        setattr(s, _AET_COUNTS[name], a.shape[0])
+    lk = np.ascontiguousarray(arrays["lookup_table_lookup_multiplicities"], dtype=np.uint64)
+    assert lk.shape == (256,)
+    keep.append(lk)
+    s.lookup_table_lookup_multiplicities = lk.ctypes.data_as(_u64p)
+    return s, keep
+
+
 AUX_CALLBACK = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _u64p, ctypes.POINTER(_u64p), ctypes.POINTER(_u64p))
 ALL_GATHER_CB = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, ctypes.c_size_t, _vp)
 ALL_REDUCE_CB = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _u64p, ctypes.c_size_t, _vp)
@@ -111,6 +161,10 @@ _SIGNATURES = {
                                  AUX_CALLBACK, _vp, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
     "tvm_prove_tables": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, _u64p, ctypes.c_int,
                                         _u64p, _u64p, _u64p, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
+    "tvm_main_table_from_aet": (ctypes.c_int, [_vp, ctypes.POINTER(AetStruct), ctypes.c_uint64, _u64p, _u64p]),
+    "tvm_prove_aet": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, ctypes.POINTER(AetStruct),
+                                     _u64p, _u64p, _u64p, _u64p, _u64p, ctypes.POINTER(ctypes.c_size_t)]),
+    "tvm_bezout_coefficients": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint64, _u64p, _u64p]),
     "tvm_prove_transcript": (ctypes.c_int, [_vp, ctypes.POINTER(Params), ctypes.POINTER(ClaimStruct), ctypes.c_uint64, _u64p, _u64p,
                                             AUX_CALLBACK, _vp, _u64p, ctypes.c_void_p]),
     "tvm_stir_prove": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u64p, _u64p,
@@ -516,6 +570,56 @@ class Backend:
         cap = ctypes.c_size_t(est)
         rc = self._l.tvm_prove_tables(self._h, ctypes.byref(p), ctypes.byref(cs), ph, mtp, int(bool(fill_derived_main_columns)), mrp, arp,
                                       rcp, qrp, buf.ctypes.data_as(_u64p), ctypes.byref(cap))
+        self._chk(rc)
+        return buf[:cap.value].copy()
+
+    def main_table_from_aet(self, aet, num_rows):
+        """tvm_main_table_from_aet: MasterMainTable::new + pad + degree-lowering columns on the device.
+        aet: dict of arrays named like tvm_aet's fields -> ([379, num_rows] canonical, the nine table lengths)"""
+        s, keep = aet_struct(aet)
+        out = np.empty((NUM_MAIN_COLUMNS, num_rows), dtype=np.uint64)
+        lengths = np.zeros(9, dtype=np.uint64)
+        rc = self._l.tvm_main_table_from_aet(self._h, ctypes.byref(s), num_rows, out.ctypes.data_as(_u64p), lengths.ctypes.data_as(_u64p))
+        del keep
+        self._chk(rc)
+        return out, [int(v) for v in lengths]
+
+    def bezout_coefficients(self, roots):
+        """tvm_bezout_coefficients (ram.rs:162-214): distinct canonical roots -> (a, b) coefficient arrays"""
+        r, rp = _np_u64(np.asarray(roots, dtype=np.uint64))
+        a, b = np.zeros(r.size, dtype=np.uint64), np.zeros(r.size, dtype=np.uint64)
+        self._chk(self._l.tvm_bezout_coefficients(self._h, rp, r.size, a.ctypes.data_as(_u64p), b.ctypes.data_as(_u64p)))
+        return a, b
+
+    def prove_aet(self, claim, aet, main_rand, aux_rand, randomizer_column, quot_rand, security_level=160, log2_expansion=2,
+                  padded_height=None, ldt_choice=LDT_AUTO, conjectured=False):
+        """tvm_prove_aet: Stark::prove from the AlgebraicExecutionTrace — table fill, padding, degree lowering, extension and
+        the proof on the device.  aet: dict of arrays named like tvm_aet's fields; the rest as prove_tables."""
+        s, keep = aet_struct(aet)
+        mr, mrp, mr_shape = _u64_arg(main_rand)
+        ar, arp, ar_shape = _u64_arg(aux_rand)
+        qr, qrp = _np_u64(quot_rand)
+        ph = int(padded_height)
+        dom = derive_domains(security_level, log2_expansion, ph, ldt_choice, conjectured)
+        h, n = dom["num_trace_randomizers"], dom["trace_len"]
+        assert mr_shape == (379, h) and int(np.prod(ar_shape)) == 91 * h * 3, (mr_shape, ar_shape)
+        assert qr.size == 3 * dom["num_quotient_randomizer_coefficients"]
+        rcp = None
+        if randomizer_column is not None:
+            rc_, rcp, rc_shape = _u64_arg(randomizer_column)
+            assert int(np.prod(rc_shape)) == 3 * n
+        digest, inp, out = claim[0], claim[1], claim[2]
+        version = claim[3] if len(claim) > 3 else 6
+        ia, iap = _np_u64(np.array(list(inp), dtype=np.uint64))
+        oa, oap = _np_u64(np.array(list(out), dtype=np.uint64))
+        cs = ClaimStruct((ctypes.c_uint64 * 5)(*[int(v) for v in digest]), version, iap, ia.size, oap, oa.size)
+        p = Params(security_level, log2_expansion, ldt_choice, int(conjectured))
+        est = _proof_capacity(dom)
+        buf = np.empty(est, dtype=np.uint64)
+        cap = ctypes.c_size_t(est)
+        rc = self._l.tvm_prove_aet(self._h, ctypes.byref(p), ctypes.byref(cs), ph, ctypes.byref(s), mrp, arp, rcp, qrp,
+                                   buf.ctypes.data_as(_u64p), ctypes.byref(cap))
+        del keep
         self._chk(rc)
         return buf[:cap.value].copy()
 
