@@ -206,6 +206,27 @@ def test_plain_c_prover_client_builds_and_fails_loudly_without_a_gpu(tmp_path):
         assert r.returncode == 0 and "verified" in r.stdout, r.stderr
 
 
+def _write_aet_files(tmp_path):
+    """the AET of `halt` next to the files of _write_prove_tables_dir (tools/make_workload.py --aet writes the same)"""
+    from oracle import tracegen as tg
+    words = [tg.OP_HALT]
+    for name, arr in tg.aet_arrays(words, tg.execute(words)).items():
+        u32 = name == "instruction_multiplicities"
+        np.ascontiguousarray(arr, dtype="<u4" if u32 else "<u8").tofile(str(tmp_path / ("aet_%s.%s" % (name, "u32" if u32 else "u64"))))
+
+
+def test_plain_c_aet_client_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    import subprocess
+    exe = _build_example(tmp_path, "prove_aet")
+    _write_prove_tables_dir(tmp_path)
+    _write_aet_files(tmp_path)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    if tvm_b200.lib().tvm_device_count() == 0:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr
+    else:
+        assert r.returncode == 0 and "verified" in r.stdout, r.stderr
+
+
 def test_different_ldts_and_proximity_regimes_are_mutually_incompatible():
     """different_ldts_are_mutually_incompatible / different_proximty_regimes_are_mutually_incompatible (stark.rs:4840-4876) on the
     program `halt`: a proof verifies under exactly the (low-degree test, proximity regime) it was made for"""

@@ -79,3 +79,17 @@ def test_aet_with_a_table_above_the_height_is_rejected(backend):
     ex = tg.execute(list(program), inp, (), ram)
     with pytest.raises(tvm_b200.TvmError):
         backend.main_table_from_aet(tg.aet_arrays(list(program), ex), 256)
+
+
+def test_plain_c_aet_client_proves_halt_on_the_gpu(tmp_path):
+    """examples/prove_aet.c: same proof words as examples/prove_tables.c on the same randomness (the tables of `halt`)"""
+    import subprocess
+    from test_native_verifier import _build_example, _write_prove_tables_dir, _write_aet_files
+    digest = _write_prove_tables_dir(tmp_path)
+    _write_aet_files(tmp_path)
+    for name in ("prove_aet", "prove_tables"):
+        r = subprocess.run([_build_example(tmp_path, name), str(tmp_path)], capture_output=True, text=True)
+        assert r.returncode == 0 and "verified" in r.stdout, r.stderr
+    from_aet = np.fromfile(str(tmp_path / "proof_aet.u64"), dtype="<u8")
+    assert np.array_equal(from_aet, np.fromfile(str(tmp_path / "proof.u64"), dtype="<u8"))
+    assert tvm_b200.verify((digest, [], []), from_aet, 8, 2, ldt_choice=tvm_b200.LDT_FRI) == (True, "")
