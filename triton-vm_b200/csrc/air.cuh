@@ -53,7 +53,8 @@ __device__ __forceinline__ void air_acc_zero(AirAcc &c) {
   for (int i = 0; i < 3; i++) { c.lo[i] = 0; c.hi[i] = 0; c.ov[i] = 0; }
 }
 __device__ __forceinline__ void air_mac(u64 &lo, u64 &hi, u32 &ov, u64 x, u64 y) {
-  u64 plo = x * y, phi = __umul64hi(x, y);
+  const unsigned __int128 p128 = (unsigned __int128)x * y;   // one 128-bit product: 4 IMAD.WIDE (x * y and __umul64hi form the low half twice)
+  u64 plo = (u64)p128, phi = (u64)(p128 >> 64);
   asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
       : "+l"(lo), "+l"(hi), "+r"(ov) : "l"(plo), "l"(phi));
 }

@@ -492,6 +492,7 @@ FillInfo main_table_from_aet(Ex &ex, const AetView &aet, const u64 *consts /* fi
     u64 *perm = ex.alloc(plen), *keys = ex.alloc(plen), *kmax = ex.alloc(1);
     ex.launch(plen, TVM_FILL_BODY(size_t i) { keys[i] = tr[i * W_PROCESSOR + PROC_JSP]; });
     ex.sort_perm(keys, perm, plen);
+    ex.launch(1, TVM_FILL_BODY(size_t) { kmax[0] = plen - 1; });      // (a trace whose CLK column is not the row index)
     ex.launch(plen, TVM_FILL_BODY(size_t i) {
       if (tr[perm[i] * W_PROCESSOR + PROC_CLK] == plen - 1) kmax[0] = i;
       if (i + 1 < plen) {

@@ -125,7 +125,8 @@ void xpow_vector_run(Ctx &c, xfe base, u64 *out, size_t stride, size_t len) {
 // a second kernel adds the `split` partial results of a column.
 static constexpr int DOT_THREADS = 256;
 __device__ __forceinline__ void dot_mac(u64 &lo, u64 &hi, u32 &ov, u64 x, u64 y) {
-  u64 plo = x * y, phi = __umul64hi(x, y);
+  const unsigned __int128 p128 = (unsigned __int128)x * y;   // one 128-bit product: 4 IMAD.WIDE (x * y and __umul64hi form the low half twice)
+  u64 plo = (u64)p128, phi = (u64)(p128 >> 64);
   asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
       : "+l"(lo), "+l"(hi), "+r"(ov) : "l"(plo), "l"(phi));
 }
