@@ -218,7 +218,8 @@ int tvm_prove_transcript(tvm_ctx *ctx, const tvm_params *params, const tvm_claim
  *      aux_rand     [91][h][3]  trace-randomizer coefficients of the auxiliary columns
  *      randomizer_column [trace_len][3]  auxiliary column 90 (master_table.rs:1019-1025); NULL = zeros
  *      other arguments and the proof: as tvm_prove (identical proof words for identical tables and randomness).
- *      Single GPU (a context with tvm_ctx_set_comm world > 1 returns TVM_ERR_UNSUPPORTED). --- */
+ *      With tvm_ctx_set_comm (world > 1) every rank is handed the same table: each holds the whole main trace, runs the
+ *      extension itself and interpolates its own block of columns; the cosets are sharded as in tvm_prove. --- */
 int tvm_prove_tables(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height,
                      const uint64_t *main_table, int fill_derived_main_columns, const uint64_t *main_rand, const uint64_t *aux_rand,
                      const uint64_t *randomizer_column, const uint64_t *quot_rand, uint64_t *proof_out, size_t *proof_len);
@@ -253,7 +254,7 @@ typedef struct tvm_aet {
  *        main_table_out [379][num_rows] canonical, column-major (host memory)
  *        table_lengths_out (optional) [9]: program, processor, op stack, ram, jump stack, hash, cascade, lookup, u32
  *      tvm_prove_aet: the same fill as the first stage of tvm_prove_tables; nothing but the AET and the randomness is
- *      uploaded, the table never exists on the host.  Other arguments as tvm_prove_tables. --- */
+ *      uploaded, the table never exists on the host.  Other arguments (and the multi-GPU behaviour) as tvm_prove_tables. --- */
 int tvm_main_table_from_aet(tvm_ctx *ctx, const tvm_aet *aet, uint64_t num_rows, uint64_t *main_table_out, uint64_t *table_lengths_out);
 int tvm_prove_aet(tvm_ctx *ctx, const tvm_params *params, const tvm_claim *claim, uint64_t padded_height, const tvm_aet *aet,
                   const uint64_t *main_rand, const uint64_t *aux_rand, const uint64_t *randomizer_column, const uint64_t *quot_rand,

@@ -284,9 +284,37 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     const size_t cpr = (ncols + W - 1) / W;             // columns per rank (the last block may be short)
     const size_t own0 = std::min(ncols, rank * cpr), own1 = std::min(ncols, own0 + cpr), nown = own1 - own0;
     const size_t bcols = ncols * xf;                    // B-field columns
-    const size_t up_cols = std::min(nown, opt.upload_cols);   // (device-table mode is single-GPU: own0 == 0)
+    const size_t up_cols = std::min(nown, opt.upload_cols);
     d_coef = mem.words(cpr * W * xf * cs);
     d_lde = jit ? nullptr : mem.words(bcols * NLe);
+    if (W > 1 && !opt.d_ready && (opt.keep_in || opt.after_upload)) {
+      // Device-table mode on several ranks: every rank holds the WHOLE main trace (uploads the table columns or fills them
+      // from the AET, computes the derived ones) because MasterMainTable::extend needs all of it; the interpolation is
+      // still sharded by columns.
+      if (xf != 1) throw ApiError{TVM_ERR_UNSUPPORTED, "device-table mode: base-field trace expected"};
+      const size_t U = std::min(ncols, opt.upload_cols);
+      u64 *d_in = mem.words(ncols * n + ncols * h), *d_rand_in = d_in + ncols * n;
+      cudaEvent_t e0 = c.get_copy_event(nevt++), e1 = c.get_copy_event(nevt++);
+      TVM_CUDA(cudaEventRecord(e0, c.stream));
+      TVM_CUDA(cudaStreamWaitEvent(cs_copy, e0, 0));
+      TVM_CUDA(cudaMemcpyAsync(d_rand_in, src_rand, ncols * h * 8, cudaMemcpyDefault, cs_copy));
+      if (U) TVM_CUDA(cudaMemcpyAsync(d_in, src_trace, U * n * 8, cudaMemcpyDefault, cs_copy));
+      TVM_CUDA(cudaEventRecord(e1, cs_copy));
+      TVM_CUDA(cudaStreamWaitEvent(c.stream, e1, 0));
+      to_mont_run(c, d_rand_in, ncols * h);
+      if (U) to_mont_run(c, d_in, U * n);
+      if (opt.after_upload) opt.after_upload(d_in);
+      const size_t bstep = std::max<size_t>(1, tmp_cols);
+      for (size_t c0 = 0; c0 < nown; c0 += bstep) {
+        const size_t b = std::min(bstep, nown - c0), q0 = own0 + c0;
+        lde_interpolate_run(c, d_in + q0 * n, d_rand_in + q0 * h, (unsigned)h, (unsigned)hpad, log_n, off, b, d_coef + q0 * cs, cs, d_tmp);
+      }
+      c.all_gather(d_coef, cpr * cs * 8);
+      if (!jit) evaluate_cols(c, d_coef, cs, (unsigned)h, bcols, log_n, log_re, she, d_lde, d_tmp, tmp_cols);
+      if (opt.keep_in) *opt.keep_in = d_in;
+      else mem.release(d_in);
+      return;
+    }
     u64 *d_in = opt.d_ready ? mem.words(ncols * xf * h) : mem.words(std::max<size_t>(1, nown) * xf * n + ncols * xf * h);
     u64 *d_rand_in = opt.d_ready ? d_in : d_in + std::max<size_t>(1, nown) * xf * n;
     u64 *d_planar = opt.d_ready ? opt.d_ready : (xf == 3 ? mem.words(std::max<size_t>(1, nown) * 3 * n + ncols * 3 * h) : d_in);
@@ -327,7 +355,8 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
         if (xf == 3) deinterleave3_run(c, d_in + c0 * 3 * n, d_planar + c0 * 3 * n, n, b);
       }
       const size_t q0 = (own0 + c0) * xf;               // first B-field column of the batch
-      lde_interpolate_run(c, d_planar + c0 * xf * n, d_rand + q0 * h, (unsigned)h, (unsigned)hpad, log_n, off, b * xf,
+      // (a table that is already on the device is complete on every rank: this rank's block starts at column own0)
+      lde_interpolate_run(c, d_planar + ((opt.d_ready ? own0 : 0) + c0) * xf * n, d_rand + q0 * h, (unsigned)h, (unsigned)hpad, log_n, off, b * xf,
                           d_coef + q0 * cs, cs, d_tmp);
       if (W == 1 && !jit) lde_evaluate_run(c, d_coef + q0 * cs, cs, (unsigned)h, log_n, log_re, she.first, she.step, she.count, b * xf,
                                            d_lde + q0 * NLe, d_tmp);
@@ -384,7 +413,6 @@ void stark_prove(Ctx &c, const StarkParams &sp, const ClaimView &claim, size_t p
     ps.enqueue(ItemKind::MerkleRoot, root);
   };
 
-  if (dev_tables && W > 1) throw ApiError{TVM_ERR_UNSUPPORTED, "device-side table stages are single-GPU"};
   u64 *d_main_coef = nullptr, *d_main_lde = nullptr;
   u64 *d_main_trace = nullptr;          // device-table mode: the Montgomery main trace stays resident for the extension
   {
