@@ -42,6 +42,13 @@ MIN_BLOCKS = int(os.environ.get("TVM_AIR_MIN_BLOCKS", "2"))   # measured at 2^21
 SPLIT_BIG = os.environ.get("TVM_AIR_SPLIT", "1") != "0"
 SPLIT_BUDGET = float(os.environ.get("TVM_AIR_SPLIT_BUDGET", "400"))   # pieces of an oversized constraint may be this large
 WTAB_WORDS = 7   # per weight: b0, b1, b2, -b1, -b2, b0+b2, b1-b2
+# Degree split: the trace polynomials have degree < 2n, so the weighted sum of the constraints of degree <= 2 of one zerofier
+# class has degree < 4n and is determined by its values on every second coset of the 8n-point quotient domain.  Those
+# constraints get their own ("lo") chunks; quotient.cu runs them on half of the rows and extends the four class sums with two
+# transforms per coordinate (exact: same field elements as evaluating everywhere).  25 % of the circuit's cost is in lo chunks.
+DEGREE_SPLIT = os.environ.get("TVM_AIR_DEGREE_SPLIT", "1") != "0"
+LOW_DEGREE = 2
+CHUNK_CLASS = {}   # chunk index -> "hi" | "lo" (filled by chunk_constraints)
 
 
 def mont(v):
@@ -128,23 +135,29 @@ def chunk_constraints(air, budget=None):
         b = air.builders[cat]
         cs = air.constraints[cat]
         memo = {}
-        cur, seen, cost = [], set(), 0.0
-        for j, c in enumerate(cs):
-            pieces = split_piece(b, c, max(budget, SPLIT_BUDGET), memo) if SPLIT_BIG else [("node", c)]
-            for piece in pieces:
-                leaves = piece_leaves(piece)
-                new = [x for x in reachable_postorder(leaves) if id(x) not in seen and x.kind in "+*"]
-                new_cost = sum(node_cost(b, x) for x in new) + 6.0
-                if cur and cost + new_cost > budget:
-                    chunks.append((cat, cur))
-                    cur, seen, cost = [], set(), 0.0
-                    new = [x for x in reachable_postorder(leaves) if x.kind in "+*"]
+        classes = ("hi", "lo") if DEGREE_SPLIT else ("hi",)
+        for cls in classes:
+            cur, seen, cost = [], set(), 0.0
+            for j, c in enumerate(cs):
+                if DEGREE_SPLIT and (b.degree(c) <= LOW_DEGREE) != (cls == "lo"):
+                    continue
+                pieces = split_piece(b, c, max(budget, SPLIT_BUDGET), memo) if SPLIT_BIG else [("node", c)]
+                for piece in pieces:
+                    leaves = piece_leaves(piece)
+                    new = [x for x in reachable_postorder(leaves) if id(x) not in seen and x.kind in "+*"]
                     new_cost = sum(node_cost(b, x) for x in new) + 6.0
-                cur.append((offset + j, piece))
-                seen.update(id(x) for x in new)
-                cost += new_cost
-        if cur:
-            chunks.append((cat, cur))
+                    if cur and cost + new_cost > budget:
+                        CHUNK_CLASS[len(chunks)] = cls
+                        chunks.append((cat, cur))
+                        cur, seen, cost = [], set(), 0.0
+                        new = [x for x in reachable_postorder(leaves) if x.kind in "+*"]
+                        new_cost = sum(node_cost(b, x) for x in new) + 6.0
+                    cur.append((offset + j, piece))
+                    seen.update(id(x) for x in new)
+                    cost += new_cost
+            if cur:
+                CHUNK_CLASS[len(chunks)] = cls
+                chunks.append((cat, cur))
         offset += len(cs)
     return chunks
 
@@ -293,10 +306,13 @@ static __device__ __noinline__ void %(bname)s(const u64 *mc, const u64 *mn, cons
 """
 
 TU_FOOTER = """
-void %(tuname)s_launch(const AirArgs &a, const u64 *d_wtab, const u64 *d_challenges, cudaStream_t s, unsigned long long *launches) {
+// `lo`: the arguments of the chunks of constraints of degree <= 2 (see AirArgs::low_out); the same as `a` unless the caller splits
+void %(tuname)s_launch(const AirArgs &a, const AirArgs &lo, const u64 *d_wtab, const u64 *d_challenges, cudaStream_t s, unsigned long long *launches) {
   cudaMemcpyToSymbolAsync(c_w, d_wtab, sizeof(u64) * %(nw)d, 0, cudaMemcpyDeviceToDevice, s);
   cudaMemcpyToSymbolAsync(c_ch, d_challenges, sizeof(u64) * 189, 0, cudaMemcpyDeviceToDevice, s);
   unsigned grid = (unsigned)((a.nrows + AIR_THREADS - 1) / AIR_THREADS);
+  unsigned grid_lo = (unsigned)((lo.nrows + AIR_THREADS - 1) / AIR_THREADS);
+  (void)grid_lo;
 %(launches)s
   *launches += %(nk)d;
 }
@@ -326,7 +342,8 @@ def emit_body(air, idx, cat, items, fused):
 
 def emit_chunk(air, idx, cat, items):
     body, accs, nops = emit_body(air, idx, cat, items, False)
-    kname = f"air_chunk_{idx:03d}_{cat}"
+    low = CHUNK_CLASS.get(idx) == "lo"
+    kname = f"air_chunk_{idx:03d}_{cat}" + ("_lo" if low else "")
     if SYNC_EVERY:
         guard = "  const bool active = m < a.nrows;\n  if (!active) m = 0;   // keep every thread alive for the block-wide barriers below"
     else:
@@ -335,7 +352,10 @@ def emit_chunk(air, idx, cat, items):
     src.append("  " + "\n  ".join(body))
     src.append("  AirAcc acc; air_acc_zero(acc);")
     src.extend("  " + x for x in accs)
-    src.append(f"  if (active) air_accumulate_{cat}(a, m, coset, air_acc_reduce(acc));")
+    if low:
+        src.append(f"  if (active) air_accumulate_low<{CATEGORIES.index(cat)}>(a, m, coset, air_acc_reduce(acc));")
+    else:
+        src.append(f"  if (active) air_accumulate_{cat}(a, m, coset, air_acc_reduce(acc));")
     src.append("}")
     return kname, "\n".join(src), nops
 
@@ -414,6 +434,7 @@ def main():
     load = [0.0] * NUM_TUS
     names, total_ops = [], 0
     if FUSED:
+        assert not DEGREE_SPLIT, "the fused-group variant predates the degree split: TVM_AIR_DEGREE_SPLIT=0"
         groups = group_chunks(air, chunks)
         units = {g: emit_group(air, g, cat, ids, chunks) for g, (cat, ids) in enumerate(groups)}
         unit_meta = {g: (cat, sum(len(chunks[i][1]) for i in ids)) for g, (cat, ids) in enumerate(groups)}
@@ -441,7 +462,10 @@ def main():
             names.append((kname, cat, ncons, nops))
             total_ops += nops
             parts.append(src)
-            launches.append(f"  {kname}<<<grid, AIR_THREADS, 0, s>>>(a);")
+            if kname.endswith("_lo"):
+                launches.append(f"  {kname}<<<grid_lo, AIR_THREADS, 0, s>>>(lo);")
+            else:
+                launches.append(f"  {kname}<<<grid, AIR_THREADS, 0, s>>>(a);")
         parts.append(TU_FOOTER % {"tuname": tuname, "nw": nw, "launches": "\n".join(launches), "nk": len(idxs)})
         with open(os.path.join(OUT_DIR, tuname + ".cu"), "w") as f:
             f.write("\n".join(parts))
@@ -450,6 +474,7 @@ def main():
         f.write("// GENERATED by airgen/codegen_cuda.py - do not edit.\n")
         f.write(f"// {len(names)} {'group' if FUSED else 'chunk'} kernels ({len(chunks)} chunk bodies) in {len(tu_names)} translation units, "
                 f"{total_ops} binary operations emitted ({unique_ops} unique in the circuit), chunk budget {CHUNK_COST_BUDGET:g}\n")
+        f.write(f"#define TVM_AIR_HAS_LOW_CHUNKS {1 if DEGREE_SPLIT else 0}   // chunks of constraints of degree <= {LOW_DEGREE} carry the suffix _lo\n")
         for tuname in tu_names:
             f.write(f"TVM_AIR_TU({tuname})\n")
         for kname, cat, ncons, nops in sorted(names):

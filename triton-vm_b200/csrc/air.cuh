@@ -33,6 +33,12 @@ struct AirArgs {
   const u64 *zi_tran;   // (x - w_n^-1) / (x^n - 1)            (1216-1237)
   const u64 *zi_term;   // 1 / (x - w_n^-1)                    (1239-1252)
   u64 cons_zerofier_inv[AIR_MAX_COSETS];  // 1 / (x^n - 1), constant on a coset   (1204-1214)
+  // Degree split (quotient.cu): for tables that are low-degree extensions (degree < 2n), the weighted sum of the constraints
+  // of degree <= 2 of one zerofier class is a polynomial of degree < 4n.  The kernels of those constraints ("lo" chunks) then
+  // run on every second coset only and add their sums WITHOUT the zerofier inverse to low_out: class t (init, cons, tran,
+  // term), coordinate d at low_out + (3t + d) * low_stride, compact row index.  nullptr: they behave like all other chunks.
+  u64 *low_out;
+  size_t low_stride;
 };
 
 // strides handed to the chunk bodies of a fused group kernel (generated code refers to them as a.main_stride / a.aux_stride)
@@ -102,6 +108,21 @@ __device__ __forceinline__ void air_accumulate_tran(const AirArgs &a, size_t m, 
 }
 __device__ __forceinline__ void air_accumulate_term(const AirArgs &a, size_t m, size_t, xfe acc) {
   air_add_out(a, m, xmulb(acc, a.zi_term[m]));
+}
+
+template <int TYPE>
+__device__ __forceinline__ void air_accumulate_low(const AirArgs &a, size_t m, size_t coset, xfe acc) {
+  if (a.low_out) {
+    u64 *o = a.low_out + (size_t)(3 * TYPE) * a.low_stride + m;
+    o[0] = fadd(o[0], acc.c0);
+    o[a.low_stride] = fadd(o[a.low_stride], acc.c1);
+    o[2 * a.low_stride] = fadd(o[2 * a.low_stride], acc.c2);
+    return;
+  }
+  if (TYPE == 0) air_accumulate_init(a, m, coset, acc);
+  else if (TYPE == 1) air_accumulate_cons(a, m, coset, acc);
+  else if (TYPE == 2) air_accumulate_tran(a, m, coset, acc);
+  else air_accumulate_term(a, m, coset, acc);
 }
 
 }  // namespace tvm

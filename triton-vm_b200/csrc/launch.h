@@ -58,7 +58,7 @@ void from_mont_run(Ctx &c, u64 *d, size_t n);
 void air_quotient_run(Ctx &c, const u64 *d_main, size_t main_stride, const u64 *d_aux, size_t aux_stride,
                       const u64 *d_challenges, const u64 *d_weights, unsigned log_n, unsigned log_r,
                       unsigned coset_first, unsigned coset_step, unsigned num_cosets, unsigned coset_mem_stride,
-                      u64 offset_mont, u64 *d_out, size_t out_stride);
+                      u64 offset_mont, u64 *d_out, size_t out_stride, bool low_degree_tables = false);   // see AirArgs::low_out
 // auxiliary-table extension (aux_extend.cu): d_main [379][n], d_ch [63*3], d_aux [273][n] planes, all Montgomery;
 // the batch-randomizer planes (column 90) are the caller's.  d_scratch: aux_extend_scratch_words(n) words
 size_t aux_extend_scratch_words(size_t n);
