@@ -142,3 +142,43 @@ def test_fill_rejects_a_table_height_below_a_table(host):
     arrays = tg.aet_arrays(list(program), ex)
     with pytest.raises(ValueError):
         host_main_table(host, arrays, 256)
+
+
+def test_u32_sections_match_the_oracle_on_random_entries(host):
+    """u32.rs:193-290 on operands no test program produces: every u32 instruction with random and edge-case operands (0, 1,
+    2^32 - 1, powers of two; `pow` with a full-width base).  The fill does not look at the consistency of the AET, so the
+    entries are planted into the AET of `halt`."""
+    rng = np.random.default_rng(99)
+    ops = ["split", "lt", "and", "log_2_floor", "pow", "pop_count"]
+    edge = [0, 1, 2, 3, (1 << 31), (1 << 32) - 1, (1 << 16), 0x55555555]
+    entries = []
+    for op in ops:
+        pairs = [(a, b) for a in edge for b in edge] + [(int(a), int(b)) for a, b in rng.integers(0, 1 << 32, size=(40, 2))]
+        for lhs, rhs in pairs:
+            if op == "log_2_floor" and lhs == 0:
+                continue                                   # a VM error: never recorded
+            if op == "pow":
+                lhs = int(rng.integers(0, P, dtype=np.uint64)) if lhs > 3 else lhs      # the base is any field element
+            if op in ("log_2_floor", "pop_count"):
+                rhs = 0
+            entries.append((op, lhs, rhs, int(rng.integers(1, 1000))))
+    entries = list({(o, l, r): (o, l, r, m) for o, l, r, m in entries}.values())
+    want_rows = []
+    for op, lhs, rhs, mult in entries:
+        for r in tg._u32_section(op, lhs, rhs, mult):
+            want_rows.append([r["flag"], r["bits"], tg.F.inv((r["bits"] - 33) % P), tg.OPCODES[op], r["lhs"], tg.inv_or_zero(r["lhs"]), r["rhs"],
+                              tg.inv_or_zero(r["rhs"]), r["result"], r["mult"]])
+    total = len(want_rows)
+    n = 1 << max(8, (total - 1).bit_length())
+    words = [tg.OP_HALT]
+    arrays = tg.aet_arrays(words, tg.execute(words))
+    arrays["u32_entries"] = np.array([[tg.OPCODES[o], l, r, m] for o, l, r, m in entries], dtype=np.uint64)
+    got, lengths = host_main_table(host, arrays, n)
+    assert lengths[8] == total
+    want = np.array(want_rows, dtype=np.uint64).T                      # [10][total]
+    assert np.array_equal(got[139:149, :total], want)
+    last = want_rows[-1]                                               # padding (u32.rs:126-154)
+    pad = got[139:149, total:]
+    assert (pad[0] == 0).all() and (pad[1] == 0).all() and (pad[2] == tg.F.inv((-33) % P)).all() and (pad[3] == last[3]).all()
+    assert (pad[4] == last[4]).all() and (pad[5] == last[5]).all() and (pad[6] == 0).all() and (pad[7] == 0).all() and (pad[9] == 0).all()
+    assert (pad[8] == (2 if last[3] == tg.OPCODES["lt"] else last[8])).all()
